@@ -1,0 +1,156 @@
+/* picsp_b200.h — the C ABI of the B200-native PICSP particle loop.
+ *
+ * This is the drop-in boundary for PICSP's per-timestep hot path.  The reference
+ * (sayanadhikari/picsp) has no plugin/FFI layer: its hot path is the set of free
+ * functions declared at src/main.cpp:202-231, which take raw `double*` grids and
+ * `Species*`, read a handful of globals (`domain`, `timeStep`, `EPS`), return
+ * void/bool and never throw.  Each entry point below replaces one of them and
+ * cites it.  A maintainer of the reference binds this header directly from C++
+ * (see INTEGRATION.md for the patch to src/main.cpp).
+ *
+ * Conventions
+ *  - plain C, no CUDA/torch types in any signature; `extern "C"` linkage.
+ *  - one opaque context per GPU rank; the library owns all device memory and one
+ *    CUDA stream; the caller owns every host buffer it passes in.
+ *  - every call returns PICSP_OK (0) or a negative error code; nothing throws.
+ *    picsp_last_error() gives a human-readable message for the last failure.
+ *  - calls are stream-ordered; the ones that fill host memory synchronise.
+ *  - grids are nix*niy doubles, F[i][j] = F[i*niy + j] (y contiguous),
+ *    nix = numxCells+1, niy = numyCells+1 (src/main.cpp:363,371,378-381).
+ *  - species index: 0 = ions, 1 = electrons (src/main.cpp:407-412).
+ *  - there is NO CPU fallback: without a CUDA device picsp_create fails with
+ *    PICSP_ERR_NO_DEVICE.
+ */
+#ifndef PICSP_B200_H
+#define PICSP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PICSP_B200_ABI_VERSION 1
+
+typedef struct picsp_ctx picsp_ctx;
+
+enum {
+    PICSP_OK = 0,
+    PICSP_ERR_INVALID = -1,     /* bad argument */
+    PICSP_ERR_NO_DEVICE = -2,   /* no CUDA device / driver: there is no CPU path */
+    PICSP_ERR_CUDA = -3,
+    PICSP_ERR_CUFFT = -4,
+    PICSP_ERR_NCCL = -5,
+    PICSP_ERR_STATE = -6,       /* call sequence error (e.g. download before upload) */
+    PICSP_ERR_DISPLACEMENT = -7,/* a particle moved >= one particle tile in one step */
+    PICSP_ERR_NOT_CONVERGED = -8/* SOR hit the reference's 200000-sweep cap (main.cpp:955) */
+};
+
+/* Grid selectors for picsp_grid_upload / picsp_grid_download. */
+enum {
+    PICSP_DEN_I = 0,  /* ions.den       (src/main.cpp:417) */
+    PICSP_DEN_E = 1,  /* electrons.den  (src/main.cpp:420) */
+    PICSP_RHO   = 2,  /* domain.rho     (src/main.cpp:381) */
+    PICSP_PHI   = 3,  /* domain.phi     (src/main.cpp:378) */
+    PICSP_EFX   = 4,  /* domain.efx     (src/main.cpp:379) */
+    PICSP_EFY   = 5   /* domain.efy     (src/main.cpp:380) */
+};
+
+enum {
+    PICSP_SOLVER_SPECTRAL = 1,  /* solverType 1: spectralPotentialSolver (src/main.cpp:960) */
+    PICSP_SOLVER_SOR = 2        /* solverType 2: solvePotential          (src/main.cpp:904) */
+};
+
+/* Flags.  0 = the reference's behaviour, bug for bug. */
+enum {
+    PICSP_FLAG_CLEAR_DENSITY = 1 << 0,  /* extension: zero den before each deposit (the reference never does, main.cpp:692) */
+    PICSP_FLAG_NO_SORT       = 1 << 1,  /* keep particles in upload order (no periodic tile sort) */
+    PICSP_FLAG_NO_FUSE       = 1 << 2   /* push does not pre-accumulate the next step's deposit */
+};
+
+/* Normalised quantities, i.e. the reference's globals after parse_ini_file
+ * (src/main.cpp:279-294). */
+typedef struct picsp_params {
+    int32_t numxCells;        /* grid:numxCells  */
+    int32_t numyCells;        /* grid:numyCells  */
+    double  stepSize;         /* normalised dx = dy (main.cpp:289,364,372) */
+    double  timeStep;         /* normalised dt (main.cpp:288) */
+    int32_t solverType;       /* PICSP_SOLVER_* */
+    int32_t flags;            /* PICSP_FLAG_* */
+    double  charge[2];        /* +chargeE, -chargeE (main.cpp:407-408) */
+    double  mass[2];          /* massI, massE */
+    double  spwt[2];          /* ion_spwt, electron_spwt (main.cpp:401-402) */
+    int64_t capacity[2];      /* max particles of each species held by THIS rank */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t reserved;
+} picsp_params;
+
+/* ---- lifetime -------------------------------------------------------------- */
+int  picsp_abi_version(void);
+int  picsp_create(const picsp_params *params, picsp_ctx **out);
+void picsp_destroy(picsp_ctx *ctx);
+const char *picsp_last_error(void);
+int  picsp_sync(picsp_ctx *ctx);
+
+/* ---- state exchange (host buffers; these are what parity tests use) --------- */
+/* Replaces filling Species::part_list (src/main.cpp:140,594,613): n particles in list order. */
+int picsp_species_upload(picsp_ctx *ctx, int species, const double *x, const double *y,
+                         const double *vx, const double *vy, int64_t n);
+/* Particles come back in upload (list) order regardless of any internal sort. */
+int picsp_species_download(picsp_ctx *ctx, int species, double *x, double *y, double *vx, double *vy);
+int picsp_species_count(picsp_ctx *ctx, int species, int64_t *n);
+/* Same, [n][4] rows of {x, y, vx, vy}: the layout writeSpecies dumps (src/main.cpp:1152-1162). */
+int picsp_species_download_rows(picsp_ctx *ctx, int species, double *rows);
+int picsp_grid_upload(picsp_ctx *ctx, int which, const double *host);
+int picsp_grid_download(picsp_ctx *ctx, int which, double *host);
+
+/* ---- the hot path, one entry per reference function -------------------------- */
+int picsp_deposit(picsp_ctx *ctx, int species);     /* scatterSpecies            src/main.cpp:684-721 (+scatter :655-668) */
+int picsp_compute_rho(picsp_ctx *ctx);              /* computeRho                src/main.cpp:869-901; all-reduces when a communicator is attached */
+int picsp_solve(picsp_ctx *ctx);                    /* the solverType switch     src/main.cpp:492-497 */
+int picsp_solve_spectral(picsp_ctx *ctx);           /* spectralPotentialSolver   src/main.cpp:960-1058 */
+int picsp_solve_sor(picsp_ctx *ctx, int64_t *sweeps, double *l2); /* solvePotential src/main.cpp:904-957 (outputs may be NULL) */
+int picsp_compute_ef(picsp_ctx *ctx);               /* computeEF                 src/main.cpp:1111-1139 */
+int picsp_push(picsp_ctx *ctx, int species);        /* pushSpecies (+gather)     src/main.cpp:772-847, :671-681 */
+int picsp_rewind(picsp_ctx *ctx, int species);      /* rewindSpecies             src/main.cpp:850-866 */
+int picsp_bootstrap(picsp_ctx *ctx);                /* pre-loop sequence         src/main.cpp:453-472 */
+int picsp_step(picsp_ctx *ctx, int nsteps);         /* nsteps bodies of the loop src/main.cpp:481-504 (dead scatterSpeciesVel omitted) */
+
+/* ---- diagnostics ------------------------------------------------------------- */
+int picsp_compute_ke(picsp_ctx *ctx, int species, double *ke);        /* computeKE  src/main.cpp:1190-1203 (summed over ranks when a communicator is attached) */
+int picsp_delta_phi(picsp_ctx *ctx, double *max_phi, double *phi0);   /* max(phi), phi[0]  src/main.cpp:509-516 */
+int picsp_repush_count(picsp_ctx *ctx, int species, int64_t *n);      /* extra pushes done by the last picsp_push (main.cpp:807-845) */
+
+/* ---- multi-GPU: particles sharded by index range, grid replicated ------------ */
+/* One communicator per rank; id is an NCCL unique id (128 bytes) created by rank 0
+ * with picsp_comm_unique_id and distributed by the caller (e.g. torch.distributed). */
+int picsp_comm_unique_id(void *id128);
+int picsp_comm_attach(picsp_ctx *ctx, const void *id128, int rank, int nranks);
+
+/* ---- bench-only synthetic loader (NOT reference behaviour) ------------------- */
+/* Fills n particles of a species on the device: positions uniform in the box,
+ * velocities vth*sqrt(2)*(r1+r2+r3-1.5) (+/- drift alternating in x), counter-based
+ * RNG keyed by (seed, global particle index = first_index + p). */
+int picsp_species_fill_synthetic(picsp_ctx *ctx, int species, int64_t n, int64_t first_index,
+                                 uint64_t seed, double vth, double xdrift);
+
+/* ---- instrumentation ---------------------------------------------------------- */
+enum {
+    PICSP_PHASE_DEPOSIT = 0,   /* standalone deposit kernels + finalize/fold */
+    PICSP_PHASE_RHO = 1,
+    PICSP_PHASE_ALLREDUCE = 2,
+    PICSP_PHASE_SOLVE = 3,
+    PICSP_PHASE_EF = 4,
+    PICSP_PHASE_PUSH = 5,      /* the mover (fused with the next deposit unless NO_FUSE) */
+    PICSP_PHASE_SORT = 6,
+    PICSP_PHASE_COUNT = 7
+};
+int picsp_profile_enable(picsp_ctx *ctx, int on);                       /* CUDA events around every phase on the library's stream */
+int picsp_profile_get(picsp_ctx *ctx, int phase, double *ms, int64_t *calls); /* synchronises; accumulates since last reset */
+int picsp_profile_reset(picsp_ctx *ctx);
+int picsp_kernel_launches(picsp_ctx *ctx, int64_t *n);                  /* number of this library's kernels launched so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PICSP_B200_H */

@@ -1,0 +1,656 @@
+// picsp_b200/csrc/abi.cu — the extern "C" boundary declared in include/picsp_b200.h.
+//
+// Host-side orchestration only: allocation, launch order, stream/event plumbing,
+// NCCL.  All arithmetic is in the kernels (grid_kernels.cuh, particle_kernels.cuh).
+// There is no CPU implementation of any operation in this library.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+
+#include "ctx.cuh"
+#include "grid_kernels.cuh"
+#include "particle_kernels.cuh"
+
+using namespace picsp;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(const Error &e) { g_last_error = e.what(); return e.code; }
+int fail(int code, const std::string &m) { g_last_error = m; return code; }
+
+#define PICSP_API_BEGIN try {
+#define PICSP_API_END                                                                  \
+    return PICSP_OK; }                                                                 \
+    catch (const Error &e) { return fail(e); }                                         \
+    catch (const std::exception &e) { return fail(PICSP_ERR_INVALID, e.what()); }      \
+    catch (...) { return fail(PICSP_ERR_INVALID, "unknown exception"); }
+
+void check_ctx(picsp_ctx *c) { PICSP_REQUIRE(c != nullptr, PICSP_ERR_INVALID, "null context"); }
+void check_species(int s) { PICSP_REQUIRE(s == 0 || s == 1, PICSP_ERR_INVALID, "species must be 0 (ions) or 1 (electrons)"); }
+
+PushConst push_const(const picsp_ctx *c, int s) {
+    const Geom &g = c->g;
+    const Species &sp = c->sp[s];
+    PushConst pc;
+    const double qm = sp.q / sp.m;                 // src/main.cpp:775
+    pc.dx = g.dx; pc.dt = g.dt;
+    pc.dtqm = g.dt * qm;                           // src/main.cpp:793
+    pc.hdtqm = 0.5 * g.dt * qm;                    // src/main.cpp:863
+    pc.xl = g.xl; pc.yl = g.yl;
+    pc.nix = g.nix; pc.niy = g.niy; pc.ntx = g.ntx; pc.nty = g.nty;
+    pc.nn = g.nn; pc.guard = g.guard;
+    return pc;
+}
+
+template <class T> void dalloc(T **p, size_t count) {
+    PICSP_CUDA(cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T)));
+}
+
+int particle_blocks(const picsp_ctx *c, long long n, int threads) {
+    return blocks_for(n, threads, c->num_sms * 16);
+}
+
+// -- device error flag ------------------------------------------------------------
+void check_device_error(picsp_ctx *c) {
+    int *h = reinterpret_cast<int *>(c->h_pinned + 8);
+    PICSP_CUDA(cudaMemcpyAsync(h, c->d_error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PICSP_CUDA(cudaStreamSynchronize(c->stream));
+    if (*h) {
+        int v = *h;
+        PICSP_CUDA(cudaMemsetAsync(c->d_error, 0, sizeof(int), c->stream));
+        if (v & ERR_BIT_RUNAWAY)
+            throw Error(PICSP_ERR_DISPLACEMENT, "a particle needed more than 64 consecutive re-pushes (non-finite or absurd velocity)");
+        throw Error(PICSP_ERR_DISPLACEMENT, "a particle moved by more than one particle tile (16 cells) in a single step");
+    }
+}
+
+// -- histogram / fixed-point scale --------------------------------------------------
+void ensure_hist(picsp_ctx *c, int s) {
+    Species &sp = c->sp[s];
+    if (sp.hist_valid) return;
+    const int nt = c->g.ntx * c->g.nty;
+    PICSP_CUDA(cudaMemsetAsync(sp.hist, 0, sizeof(unsigned int) * nt, c->stream));
+    if (sp.n > 0)
+        PICSP_LAUNCH(c, k_tile_hist, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, (long long)sp.n, push_const(c, s), sp.hist);
+    sp.hist_valid = true;
+}
+void compute_frac(picsp_ctx *c, int s) {
+    Species &sp = c->sp[s];
+    PICSP_LAUNCH(c, k_frac_from_hist, 1, 1024, 0, sp.hist, c->g.ntx, c->g.nty, sp.frac);
+}
+
+// -- operations ---------------------------------------------------------------------
+void op_deposit(picsp_ctx *c, int s) {
+    PhaseScope ph(c, PICSP_PHASE_DEPOSIT);
+    Species &sp = c->sp[s];
+    const Geom &g = c->g;
+    if (!sp.acc_valid) {
+        ensure_hist(c, s);
+        compute_frac(c, s);
+        if (sp.n > 0)
+            PICSP_LAUNCH(c, k_deposit, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, (long long)sp.n,
+                         push_const(c, s), sp.acc, sp.frac);
+    }
+    const double weight = sp.spwt / (g.dx * g.dx);   // value/dxdy, src/main.cpp:657,664
+    const int clear = (c->prm.flags & PICSP_FLAG_CLEAR_DENSITY) ? 1 : 0;
+    PICSP_LAUNCH(c, k_deposit_finalize, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, sp.den, sp.acc, sp.frac, weight, g.nn, clear);
+    PICSP_LAUNCH(c, k_fold_periodic, 1, 1024, 0, sp.den, g.nix, g.niy);
+    sp.acc_valid = false;
+}
+
+void op_allreduce_rho(picsp_ctx *c);   // comm section below
+
+void op_compute_rho(picsp_ctx *c) {
+    const Geom &g = c->g;
+    {
+        PhaseScope ph(c, PICSP_PHASE_RHO);
+        PICSP_LAUNCH(c, k_compute_rho, blocks_for((long long)(g.nix - 2) * (g.niy - 2), 256, c->num_sms * 8), 256, 0,
+                     c->rho, c->sp[0].den, c->sp[1].den, c->sp[0].q, c->sp[1].q, g.nix, g.niy);
+    }
+    if (c->comm) op_allreduce_rho(c);
+    {
+        PhaseScope ph(c, PICSP_PHASE_RHO);
+        PICSP_LAUNCH(c, k_fold_periodic, 1, 1024, 0, c->rho, g.nix, g.niy);
+    }
+}
+
+void op_solve_spectral(picsp_ctx *c) {
+    PhaseScope ph(c, PICSP_PHASE_SOLVE);
+    const Geom &g = c->g;
+    PICSP_REQUIRE(c->have_plans, PICSP_ERR_STATE, "cuFFT plans missing");
+    PICSP_CUFFT(cufftExecD2Z(c->plan_fwd, c->rho, c->rhok));
+    const int Nh = g.niy / 2 + 1;
+    PICSP_LAUNCH(c, k_kspace_green, blocks_for((long long)g.nix * Nh, 256, c->num_sms * 8), 256, 0, c->rhok, c->phik,
+                 g.nix, g.niy, g.xl, g.yl);
+    PICSP_CUFFT(cufftExecZ2D(c->plan_inv, c->phik, c->phi));
+}
+
+void op_solve_sor(picsp_ctx *c) {
+    PhaseScope ph(c, PICSP_PHASE_SOLVE);
+    const Geom &g = c->g;
+    PICSP_LAUNCH(c, k_sor_solve, 1, 1024, 0, c->phi, c->rho, g.nix, g.niy, g.dx, g.dx, c->d_sor_status, c->d_scalars + 3, 200000);
+}
+
+void op_solve(picsp_ctx *c) {
+    if (c->prm.solverType == PICSP_SOLVER_SPECTRAL) op_solve_spectral(c);
+    else op_solve_sor(c);
+}
+
+void op_compute_ef(picsp_ctx *c) {
+    PhaseScope ph(c, PICSP_PHASE_EF);
+    const Geom &g = c->g;
+    PICSP_LAUNCH(c, k_compute_ef, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, c->phi, c->E, g.nix, g.niy, g.dx, g.dx);
+}
+
+void op_push(picsp_ctx *c, int s) {
+    Species &sp = c->sp[s];
+    const bool fuse = !(c->prm.flags & PICSP_FLAG_NO_FUSE);
+    if (fuse) {
+        ensure_hist(c, s);           // histogram of the positions about to be pushed -> bound for acc
+        compute_frac(c, s);
+    }
+    PhaseScope ph(c, PICSP_PHASE_PUSH);
+    PICSP_CUDA(cudaMemsetAsync(sp.repush, 0, sizeof(unsigned long long), c->stream));
+    const int nt = c->g.ntx * c->g.nty;
+    if (fuse) {
+        PICSP_CUDA(cudaMemsetAsync(sp.hist_next, 0, sizeof(unsigned int) * nt, c->stream));
+        if (sp.acc_valid)   // a previous fused push was never consumed by a deposit: drop it
+            PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
+    }
+    if (sp.n > 0) {
+        const int blocks = particle_blocks(c, sp.n, 256);
+        if (fuse)
+            PICSP_LAUNCH(c, (k_push<true>), blocks, 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n, push_const(c, s),
+                         c->E, sp.acc, sp.frac, sp.hist_next, sp.repush, c->d_error);
+        else
+            PICSP_LAUNCH(c, (k_push<false>), blocks, 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n, push_const(c, s),
+                         c->E, sp.acc, sp.frac, sp.hist_next, sp.repush, c->d_error);
+    }
+    if (fuse) {
+        std::swap(sp.hist, sp.hist_next);
+        sp.hist_valid = true;
+        sp.acc_valid = true;
+    } else {
+        sp.hist_valid = false;
+        sp.acc_valid = false;
+    }
+}
+
+void op_rewind(picsp_ctx *c, int s) {
+    PhaseScope ph(c, PICSP_PHASE_PUSH);
+    Species &sp = c->sp[s];
+    if (sp.n > 0)
+        PICSP_LAUNCH(c, k_rewind, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n,
+                     push_const(c, s), c->E);
+}
+
+double read_scalar(picsp_ctx *c, const double *dptr) {
+    PICSP_CUDA(cudaMemcpyAsync(c->h_pinned, dptr, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PICSP_CUDA(cudaStreamSynchronize(c->stream));
+    return c->h_pinned[0];
+}
+
+// -- NCCL, loaded lazily so the library has no link-time dependency on it -------------
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi &nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        // if the process (e.g. PyTorch) already loaded an NCCL, this resolves to that same copy
+        api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.handle) return;
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+        api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+        api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+    });
+    PICSP_REQUIRE(api.handle && api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy,
+                  PICSP_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    return api;
+}
+#define PICSP_NCCL(expr)                                                                        \
+    do {                                                                                        \
+        ncclResult_t r__ = (expr);                                                              \
+        if (r__ != ncclSuccess)                                                                 \
+            throw Error(PICSP_ERR_NCCL, std::string(#expr) + ": " +                             \
+                        (nccl().GetErrorString ? nccl().GetErrorString(r__) : "nccl error"));   \
+    } while (0)
+
+void op_allreduce_rho(picsp_ctx *c) {
+    // every rank holds the partial interior rho of its own particles; boundary nodes are 0 (Q3)
+    PhaseScope ph(c, PICSP_PHASE_ALLREDUCE);
+    PICSP_NCCL(nccl().AllReduce(c->rho, c->rho, (size_t)c->g.nn, ncclFloat64, ncclSum, c->comm, c->stream));
+}
+
+}  // namespace
+
+// ====================================================================================
+// extern "C"
+// ====================================================================================
+extern "C" {
+
+int picsp_abi_version(void) { return PICSP_B200_ABI_VERSION; }
+const char *picsp_last_error(void) { return g_last_error.c_str(); }
+
+int picsp_create(const picsp_params *p, picsp_ctx **out) {
+    picsp_ctx *c = nullptr;
+    try {
+        PICSP_REQUIRE(p && out, PICSP_ERR_INVALID, "null argument");
+        *out = nullptr;
+        PICSP_REQUIRE(p->numxCells >= 2 && p->numyCells >= 2, PICSP_ERR_INVALID, "numxCells/numyCells must be >= 2");
+        PICSP_REQUIRE(p->stepSize > 0 && p->timeStep > 0, PICSP_ERR_INVALID, "stepSize and timeStep must be positive");
+        PICSP_REQUIRE(p->solverType == PICSP_SOLVER_SPECTRAL || p->solverType == PICSP_SOLVER_SOR, PICSP_ERR_INVALID,
+                      "solverType must be 1 (spectral) or 2 (SOR)");   // src/main.cpp:310
+        PICSP_REQUIRE(p->capacity[0] >= 0 && p->capacity[1] >= 0, PICSP_ERR_INVALID, "negative capacity");
+        PICSP_REQUIRE(p->capacity[0] <= 0xFFFFFFFFll && p->capacity[1] <= 0xFFFFFFFFll, PICSP_ERR_INVALID,
+                      "per-rank species capacity is limited to 2^32-1 particles");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            return fail(PICSP_ERR_NO_DEVICE, "no CUDA device available: picsp_b200 has no CPU path");
+        }
+        PICSP_REQUIRE(p->device >= 0 && p->device < ndev, PICSP_ERR_INVALID, "bad device ordinal");
+        PICSP_CUDA(cudaSetDevice(p->device));
+
+        c = new picsp_ctx();
+        c->prm = *p;
+        Geom &g = c->g;
+        g.ncx = p->numxCells; g.ncy = p->numyCells;
+        g.nix = g.ncx + 1; g.niy = g.ncy + 1;                   // src/main.cpp:363,371
+        g.dx = p->stepSize; g.dt = p->timeStep;
+        g.xl = (g.nix - 1) * g.dx; g.yl = (g.niy - 1) * g.dx;   // src/main.cpp:366,374
+        g.nn = (long long)g.nix * g.niy;
+        g.guard = 4ll * g.niy + 8;
+        g.ntx = (g.ncx + TILE - 1) / TILE; g.nty = (g.ncy + TILE - 1) / TILE;
+
+        cudaDeviceProp prop;
+        PICSP_CUDA(cudaGetDeviceProperties(&prop, p->device));
+        c->num_sms = prop.multiProcessorCount;
+        PICSP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+
+        for (int s = 0; s < 2; s++) {
+            Species &sp = c->sp[s];
+            sp.cap = p->capacity[s]; sp.q = p->charge[s]; sp.m = p->mass[s]; sp.spwt = p->spwt[s];
+            dalloc(&sp.x, sp.cap); dalloc(&sp.y, sp.cap); dalloc(&sp.vx, sp.cap); dalloc(&sp.vy, sp.cap);
+            dalloc(&sp.den, g.nn); dalloc(&sp.acc, g.nn); dalloc(&sp.frac, 1);
+            dalloc(&sp.hist, (size_t)g.ntx * g.nty); dalloc(&sp.hist_next, (size_t)g.ntx * g.nty);
+            dalloc(&sp.repush, 1);
+            PICSP_CUDA(cudaMemsetAsync(sp.den, 0, sizeof(double) * g.nn, c->stream));      // src/main.cpp:427,431
+            PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * g.nn, c->stream));
+            PICSP_CUDA(cudaMemsetAsync(sp.frac, 0, sizeof(int), c->stream));
+            PICSP_CUDA(cudaMemsetAsync(sp.repush, 0, sizeof(unsigned long long), c->stream));
+        }
+        dalloc(&c->rho, g.nn); dalloc(&c->phi, g.nn);
+        dalloc(&c->E_alloc, (size_t)(g.nn + 2 * g.guard));
+        c->E = c->E_alloc + g.guard;
+        PICSP_CUDA(cudaMemsetAsync(c->rho, 0, sizeof(double) * g.nn, c->stream));          // src/main.cpp:392-395
+        PICSP_CUDA(cudaMemsetAsync(c->phi, 0, sizeof(double) * g.nn, c->stream));
+        PICSP_CUDA(cudaMemsetAsync(c->E_alloc, 0, sizeof(double2) * (g.nn + 2 * g.guard), c->stream));
+        dalloc(&c->d_red, RED_BLOCKS); dalloc(&c->d_scalars, 8); dalloc(&c->d_sor_status, 2); dalloc(&c->d_error, 1);
+        PICSP_CUDA(cudaMemsetAsync(c->d_scalars, 0, sizeof(double) * 8, c->stream));
+        PICSP_CUDA(cudaMemsetAsync(c->d_sor_status, 0, sizeof(long long) * 2, c->stream));
+        PICSP_CUDA(cudaMemsetAsync(c->d_error, 0, sizeof(int), c->stream));
+        PICSP_CUDA(cudaMallocHost((void **)&c->h_pinned, 64 * sizeof(double)));
+
+        if (p->solverType == PICSP_SOLVER_SPECTRAL) {
+            const size_t nk = (size_t)g.nix * (g.niy / 2 + 1);
+            dalloc(&c->rhok, nk); dalloc(&c->phik, nk);
+            PICSP_CUFFT(cufftPlan2d(&c->plan_fwd, g.nix, g.niy, CUFFT_D2Z));
+            PICSP_CUFFT(cufftPlan2d(&c->plan_inv, g.nix, g.niy, CUFFT_Z2D));
+            PICSP_CUFFT(cufftSetStream(c->plan_fwd, c->stream));
+            PICSP_CUFFT(cufftSetStream(c->plan_inv, c->stream));
+            c->have_plans = true;
+        }
+        PICSP_CUDA(cudaStreamSynchronize(c->stream));
+        *out = c;
+        return PICSP_OK;
+    } catch (const Error &e) {
+        if (c) picsp_destroy(c);
+        return fail(e);
+    } catch (const std::exception &e) {
+        if (c) picsp_destroy(c);
+        return fail(PICSP_ERR_INVALID, e.what());
+    }
+}
+
+void picsp_destroy(picsp_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->prm.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) { try { nccl().CommDestroy(c->comm); } catch (...) {} }
+    if (c->have_plans) { cufftDestroy(c->plan_fwd); cufftDestroy(c->plan_inv); }
+    for (int s = 0; s < 2; s++) {
+        Species &sp = c->sp[s];
+        cudaFree(sp.x); cudaFree(sp.y); cudaFree(sp.vx); cudaFree(sp.vy); cudaFree(sp.id);
+        cudaFree(sp.den); cudaFree(sp.acc); cudaFree(sp.frac); cudaFree(sp.hist); cudaFree(sp.hist_next); cudaFree(sp.repush);
+    }
+    cudaFree(c->rho); cudaFree(c->phi); cudaFree(c->E_alloc); cudaFree(c->rhok); cudaFree(c->phik);
+    cudaFree(c->d_red); cudaFree(c->d_scalars); cudaFree(c->d_sor_status); cudaFree(c->d_error); cudaFree(c->stage);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (auto &t : c->timers) for (auto e : t.pool) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int picsp_sync(picsp_ctx *c) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    check_device_error(c);
+    PICSP_API_END
+}
+
+// ---- state exchange -------------------------------------------------------------------
+int picsp_species_upload(picsp_ctx *c, int s, const double *x, const double *y, const double *vx, const double *vy, int64_t n) {
+    PICSP_API_BEGIN
+    check_ctx(c); check_species(s);
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    Species &sp = c->sp[s];
+    PICSP_REQUIRE(n >= 0 && n <= sp.cap, PICSP_ERR_INVALID, "particle count exceeds the capacity given to picsp_create");
+    PICSP_REQUIRE(n == 0 || (x && y && vx && vy), PICSP_ERR_INVALID, "null particle array");
+    const size_t bytes = sizeof(double) * (size_t)n;
+    PICSP_CUDA(cudaMemcpyAsync(sp.x, x, bytes, cudaMemcpyHostToDevice, c->stream));
+    PICSP_CUDA(cudaMemcpyAsync(sp.y, y, bytes, cudaMemcpyHostToDevice, c->stream));
+    PICSP_CUDA(cudaMemcpyAsync(sp.vx, vx, bytes, cudaMemcpyHostToDevice, c->stream));
+    PICSP_CUDA(cudaMemcpyAsync(sp.vy, vy, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (sp.acc_valid) PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
+    PICSP_CUDA(cudaStreamSynchronize(c->stream));
+    sp.n = n; sp.hist_valid = false; sp.acc_valid = false;
+    if (sp.id) { cudaFree(sp.id); sp.id = nullptr; }
+    PICSP_API_END
+}
+
+static void ensure_stage(picsp_ctx *c, int64_t n) {
+    if (c->stage_cap >= n) return;
+    cudaFree(c->stage); c->stage = nullptr; c->stage_cap = 0;
+    dalloc(&c->stage, (size_t)n);
+    c->stage_cap = n;
+}
+
+int picsp_species_download(picsp_ctx *c, int s, double *x, double *y, double *vx, double *vy) {
+    PICSP_API_BEGIN
+    check_ctx(c); check_species(s);
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    Species &sp = c->sp[s];
+    const size_t bytes = sizeof(double) * (size_t)sp.n;
+    double *src[4] = {sp.x, sp.y, sp.vx, sp.vy};
+    double *dst[4] = {x, y, vx, vy};
+    for (int k = 0; k < 4; k++) {
+        if (!dst[k] || sp.n == 0) continue;
+        if (sp.id) {
+            ensure_stage(c, sp.n);
+            PICSP_LAUNCH(c, k_unpermute, particle_blocks(c, sp.n, 256), 256, 0, src[k], sp.id, c->stage, (long long)sp.n);
+            PICSP_CUDA(cudaMemcpyAsync(dst[k], c->stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            PICSP_CUDA(cudaMemcpyAsync(dst[k], src[k], bytes, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    check_device_error(c);
+    PICSP_API_END
+}
+
+int picsp_species_download_rows(picsp_ctx *c, int s, double *rows) {
+    PICSP_API_BEGIN
+    check_ctx(c); check_species(s);
+    PICSP_REQUIRE(rows != nullptr, PICSP_ERR_INVALID, "null rows");
+    Species &sp = c->sp[s];
+    std::vector<double> tmp((size_t)sp.n * 4);
+    double *a = tmp.data();
+    int rc = picsp_species_download(c, s, a, a + sp.n, a + 2 * sp.n, a + 3 * sp.n);
+    if (rc != PICSP_OK) return rc;
+    for (int64_t p = 0; p < sp.n; p++) {   // writeSpecies row layout {x, y, vx, vy}, src/main.cpp:1156-1159
+        rows[4 * p + 0] = a[p]; rows[4 * p + 1] = a[sp.n + p];
+        rows[4 * p + 2] = a[2 * sp.n + p]; rows[4 * p + 3] = a[3 * sp.n + p];
+    }
+    PICSP_API_END
+}
+
+int picsp_species_count(picsp_ctx *c, int s, int64_t *n) {
+    PICSP_API_BEGIN
+    check_ctx(c); check_species(s);
+    PICSP_REQUIRE(n != nullptr, PICSP_ERR_INVALID, "null output");
+    *n = c->sp[s].n;
+    PICSP_API_END
+}
+
+int picsp_grid_upload(picsp_ctx *c, int which, const double *host) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    PICSP_REQUIRE(host != nullptr, PICSP_ERR_INVALID, "null host buffer");
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    const Geom &g = c->g;
+    const size_t bytes = sizeof(double) * (size_t)g.nn;
+    double *dst = nullptr;
+    switch (which) {
+        case PICSP_DEN_I: dst = c->sp[0].den; break;
+        case PICSP_DEN_E: dst = c->sp[1].den; break;
+        case PICSP_RHO: dst = c->rho; break;
+        case PICSP_PHI: dst = c->phi; break;
+        case PICSP_EFX: case PICSP_EFY: break;
+        default: throw Error(PICSP_ERR_INVALID, "bad grid selector");
+    }
+    if (dst) {
+        PICSP_CUDA(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        ensure_stage(c, g.nn);
+        PICSP_CUDA(cudaMemcpyAsync(c->stage, host, bytes, cudaMemcpyHostToDevice, c->stream));
+        PICSP_LAUNCH(c, k_ef_set_component, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, c->E, c->stage, g.nn,
+                     which == PICSP_EFY ? 1 : 0);
+    }
+    PICSP_CUDA(cudaStreamSynchronize(c->stream));
+    PICSP_API_END
+}
+
+int picsp_grid_download(picsp_ctx *c, int which, double *host) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    PICSP_REQUIRE(host != nullptr, PICSP_ERR_INVALID, "null host buffer");
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    const Geom &g = c->g;
+    const size_t bytes = sizeof(double) * (size_t)g.nn;
+    const double *src = nullptr;
+    switch (which) {
+        case PICSP_DEN_I: src = c->sp[0].den; break;
+        case PICSP_DEN_E: src = c->sp[1].den; break;
+        case PICSP_RHO: src = c->rho; break;
+        case PICSP_PHI: src = c->phi; break;
+        case PICSP_EFX: case PICSP_EFY: break;
+        default: throw Error(PICSP_ERR_INVALID, "bad grid selector");
+    }
+    if (!src) {
+        ensure_stage(c, g.nn);
+        PICSP_LAUNCH(c, k_ef_get_component, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, c->E, c->stage, g.nn,
+                     which == PICSP_EFY ? 1 : 0);
+        src = c->stage;
+    }
+    PICSP_CUDA(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    check_device_error(c);
+    PICSP_API_END
+}
+
+// ---- hot path ---------------------------------------------------------------------------
+#define PICSP_OP(body)                                   \
+    PICSP_API_BEGIN                                      \
+    check_ctx(c);                                        \
+    PICSP_CUDA(cudaSetDevice(c->prm.device));            \
+    body;                                                \
+    PICSP_API_END
+
+int picsp_deposit(picsp_ctx *c, int s) { PICSP_OP(check_species(s); op_deposit(c, s)) }
+int picsp_compute_rho(picsp_ctx *c) { PICSP_OP(op_compute_rho(c)) }
+int picsp_solve(picsp_ctx *c) { PICSP_OP(op_solve(c)) }
+int picsp_solve_spectral(picsp_ctx *c) {
+    PICSP_OP(PICSP_REQUIRE(c->have_plans, PICSP_ERR_STATE, "context was created with solverType 2: no cuFFT plans"); op_solve_spectral(c))
+}
+int picsp_solve_sor(picsp_ctx *c, int64_t *sweeps, double *l2) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    op_solve_sor(c);
+    if (sweeps || l2) {
+        long long *h = reinterpret_cast<long long *>(c->h_pinned + 16);
+        PICSP_CUDA(cudaMemcpyAsync(h, c->d_sor_status, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        double v = read_scalar(c, c->d_scalars + 3);
+        if (sweeps) *sweeps = *h;
+        if (l2) *l2 = v;
+        if (*h < 0) throw Error(PICSP_ERR_NOT_CONVERGED, "Gauss-Seidel solver failed to converge");   // src/main.cpp:955
+    }
+    PICSP_API_END
+}
+int picsp_compute_ef(picsp_ctx *c) { PICSP_OP(op_compute_ef(c)) }
+int picsp_push(picsp_ctx *c, int s) { PICSP_OP(check_species(s); op_push(c, s)) }
+int picsp_rewind(picsp_ctx *c, int s) { PICSP_OP(check_species(s); op_rewind(c, s)) }
+
+int picsp_bootstrap(picsp_ctx *c) {   // src/main.cpp:453-472
+    PICSP_OP(op_deposit(c, 0); op_deposit(c, 1); op_compute_rho(c); op_solve(c); op_compute_ef(c);
+             op_rewind(c, 0); op_rewind(c, 1))
+}
+
+int picsp_step(picsp_ctx *c, int nsteps) {   // src/main.cpp:481-504
+    PICSP_API_BEGIN
+    check_ctx(c);
+    PICSP_REQUIRE(nsteps >= 0, PICSP_ERR_INVALID, "negative step count");
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    for (int it = 0; it < nsteps; it++) {
+        op_deposit(c, 0); op_deposit(c, 1);
+        op_compute_rho(c);
+        op_solve(c);
+        op_compute_ef(c);
+        op_push(c, 0); op_push(c, 1);
+        if (c->profiling && c->timers[PICSP_PHASE_PUSH].used > 2048) profile_collect(c);
+    }
+    PICSP_API_END
+}
+
+// ---- diagnostics -------------------------------------------------------------------------
+int picsp_compute_ke(picsp_ctx *c, int s, double *ke) {
+    PICSP_API_BEGIN
+    check_ctx(c); check_species(s);
+    PICSP_REQUIRE(ke != nullptr, PICSP_ERR_INVALID, "null output");
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    Species &sp = c->sp[s];
+    PICSP_LAUNCH(c, k_ke_partial, RED_BLOCKS, RED_THREADS, 0, sp.vx, sp.vy, (long long)sp.n, c->d_red);
+    PICSP_LAUNCH(c, k_sum_final, 1, 1024, 0, c->d_red, RED_BLOCKS, c->d_scalars + 0);
+    if (c->comm) PICSP_NCCL(nccl().AllReduce(c->d_scalars, c->d_scalars, 1, ncclFloat64, ncclSum, c->comm, c->stream));
+    double sum = read_scalar(c, c->d_scalars + 0);
+    sum += 0.5 * (sp.spwt * sp.m);   // src/main.cpp:1198: added, not multiplied (Q10)
+    sum /= 1.0;                      // chargeE == 1 after normalisation, src/main.cpp:1201
+    *ke = sum;
+    PICSP_API_END
+}
+
+int picsp_delta_phi(picsp_ctx *c, double *max_phi, double *phi0) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    PICSP_LAUNCH(c, k_max_partial, RED_BLOCKS, RED_THREADS, 0, c->phi, c->g.nn, c->d_red);
+    PICSP_LAUNCH(c, k_max_final, 1, 1024, 0, c->d_red, RED_BLOCKS, c->phi, c->d_scalars + 1, c->d_scalars + 2);
+    PICSP_CUDA(cudaMemcpyAsync(c->h_pinned, c->d_scalars + 1, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PICSP_CUDA(cudaStreamSynchronize(c->stream));
+    if (max_phi) *max_phi = c->h_pinned[0];
+    if (phi0) *phi0 = c->h_pinned[1];
+    PICSP_API_END
+}
+
+int picsp_repush_count(picsp_ctx *c, int s, int64_t *n) {
+    PICSP_API_BEGIN
+    check_ctx(c); check_species(s);
+    PICSP_REQUIRE(n != nullptr, PICSP_ERR_INVALID, "null output");
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    unsigned long long *h = reinterpret_cast<unsigned long long *>(c->h_pinned + 24);
+    PICSP_CUDA(cudaMemcpyAsync(h, c->sp[s].repush, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    PICSP_CUDA(cudaStreamSynchronize(c->stream));
+    *n = (int64_t)*h;
+    PICSP_API_END
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------
+int picsp_comm_unique_id(void *id128) {
+    PICSP_API_BEGIN
+    PICSP_REQUIRE(id128 != nullptr, PICSP_ERR_INVALID, "null id");
+    static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id is 128 bytes");
+    ncclUniqueId id;
+    PICSP_NCCL(nccl().GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    PICSP_API_END
+}
+
+int picsp_comm_attach(picsp_ctx *c, const void *id128, int rank, int nranks) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    PICSP_REQUIRE(id128 && nranks >= 1 && rank >= 0 && rank < nranks, PICSP_ERR_INVALID, "bad communicator arguments");
+    PICSP_REQUIRE(c->comm == nullptr, PICSP_ERR_STATE, "communicator already attached");
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    PICSP_NCCL(nccl().CommInitRank(&c->comm, nranks, id, rank));
+    c->rank = rank; c->nranks = nranks;
+    PICSP_API_END
+}
+
+// ---- bench-only loader ---------------------------------------------------------------------
+int picsp_species_fill_synthetic(picsp_ctx *c, int s, int64_t n, int64_t first_index, uint64_t seed, double vth, double xdrift) {
+    PICSP_API_BEGIN
+    check_ctx(c); check_species(s);
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    Species &sp = c->sp[s];
+    PICSP_REQUIRE(n >= 0 && n <= sp.cap, PICSP_ERR_INVALID, "particle count exceeds capacity");
+    if (n > 0)
+        PICSP_LAUNCH(c, k_fill_synthetic, particle_blocks(c, n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)n,
+                     (long long)first_index, seed, c->g.xl, c->g.yl, vth, xdrift);
+    if (sp.acc_valid) PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
+    sp.n = n; sp.hist_valid = false; sp.acc_valid = false;
+    if (sp.id) { cudaFree(sp.id); sp.id = nullptr; }
+    PICSP_CUDA(cudaStreamSynchronize(c->stream));
+    PICSP_API_END
+}
+
+// ---- instrumentation -------------------------------------------------------------------------
+int picsp_profile_enable(picsp_ctx *c, int on) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    if (c->profiling && !on) profile_collect(c);
+    c->profiling = on != 0;
+    PICSP_API_END
+}
+int picsp_profile_get(picsp_ctx *c, int phase, double *ms, int64_t *calls) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    PICSP_REQUIRE(phase >= 0 && phase < PICSP_PHASE_COUNT, PICSP_ERR_INVALID, "bad phase");
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    PICSP_CUDA(cudaStreamSynchronize(c->stream));
+    profile_collect(c);
+    if (ms) *ms = c->timers[phase].ms;
+    if (calls) *calls = c->timers[phase].calls;
+    PICSP_API_END
+}
+int picsp_profile_reset(picsp_ctx *c) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    PICSP_CUDA(cudaStreamSynchronize(c->stream));
+    profile_collect(c);
+    for (auto &t : c->timers) { t.ms = 0.0; t.calls = 0; }
+    PICSP_API_END
+}
+int picsp_kernel_launches(picsp_ctx *c, int64_t *n) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    PICSP_REQUIRE(n != nullptr, PICSP_ERR_INVALID, "null output");
+    *n = c->launches;
+    PICSP_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// picsp_b200/csrc/ctx.cuh — internal context and helpers (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <nccl.h>      // types only; the library is dlopen'ed in comm.cuh
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/picsp_b200.h"
+
+namespace picsp {
+
+// ---------------------------------------------------------------------------
+// error plumbing: internal code throws, the extern "C" layer converts to codes
+// ---------------------------------------------------------------------------
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define PICSP_CUDA(expr)                                                                      \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            throw ::picsp::Error(PICSP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+#define PICSP_CUFFT(expr)                                                                     \
+    do {                                                                                      \
+        cufftResult r__ = (expr);                                                             \
+        if (r__ != CUFFT_SUCCESS)                                                             \
+            throw ::picsp::Error(PICSP_ERR_CUFFT, std::string(#expr) + ": cufft error " + std::to_string((int)r__)); \
+    } while (0)
+
+#define PICSP_REQUIRE(cond, code, msg)                                  \
+    do {                                                                \
+        if (!(cond)) throw ::picsp::Error((code), (msg));               \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// geometry (reference globals `domain`, `timeStep`; src/main.cpp:363-375)
+// ---------------------------------------------------------------------------
+constexpr int TILE = 16;   // particle-tile edge in cells (binning, fixed-point bound, smem windows)
+
+struct Geom {
+    int nix, niy;          // nodes
+    int ncx, ncy;          // cells
+    int ntx, nty;          // particle tiles
+    long long nn;          // nix*niy
+    long long guard;       // zero guard band (elements) either side of E, reference UB -> defined zero
+    double dx;             // == dy
+    double dt;
+    double xl, yl;         // == xmax, ymax since x0 = y0 = 0
+};
+
+// ---------------------------------------------------------------------------
+// per-species device store: structure of arrays, double precision
+// ---------------------------------------------------------------------------
+struct Species {
+    double *x = nullptr, *y = nullptr, *vx = nullptr, *vy = nullptr;
+    uint32_t *id = nullptr;        // slot -> index in upload order; nullptr == identity
+    int64_t n = 0, cap = 0;
+    double q = 0, m = 0, spwt = 0;
+    double *den = nullptr;         // nn, accumulating
+    long long *acc = nullptr;      // nn, fixed-point deposit accumulator (order-independent => deterministic)
+    int *frac = nullptr;           // device scalar: fixed-point fraction bits acc was filled with
+    unsigned int *hist = nullptr;      // particles per tile at the positions currently stored
+    unsigned int *hist_next = nullptr; // filled by the mover for the positions it writes
+    bool hist_valid = false;
+    bool acc_valid = false;        // acc holds the deposit of the stored positions (filled by the fused mover)
+    unsigned long long *repush = nullptr; // device counter of extra pushes in the last push
+};
+
+struct PhaseTimer {
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    double ms = 0.0;
+    int64_t calls = 0;
+};
+
+}  // namespace picsp
+
+struct picsp_ctx {
+    picsp_params prm;
+    picsp::Geom g;
+    cudaStream_t stream = nullptr;
+    picsp::Species sp[2];
+
+    double *rho = nullptr, *phi = nullptr;
+    double2 *E_alloc = nullptr, *E = nullptr;     // interleaved {efx, efy}; E = E_alloc + guard
+    cufftHandle plan_fwd = 0, plan_inv = 0;
+    bool have_plans = false;
+    cufftDoubleComplex *rhok = nullptr, *phik = nullptr;
+
+    // small device scratch
+    double *d_red = nullptr;        // reduction partials
+    double *d_scalars = nullptr;    // [0..7] results (ke, maxphi, phi0, sor l2, ...)
+    long long *d_sor_status = nullptr;
+    int *d_error = nullptr;         // sticky device-side error flag
+    double *h_pinned = nullptr;     // small pinned staging for scalar read-backs
+
+    // staging for un-permuted downloads
+    double *stage = nullptr; int64_t stage_cap = 0;
+
+    // multi-GPU
+    ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+
+    // instrumentation
+    bool profiling = false;
+    picsp::PhaseTimer timers[PICSP_PHASE_COUNT];
+    int64_t launches = 0;
+    int num_sms = 148;
+};
+
+namespace picsp {
+
+// RAII phase scope: CUDA events on the library's stream when profiling is on.
+struct PhaseScope {
+    picsp_ctx *c; int phase; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    PhaseScope(picsp_ctx *ctx, int ph) : c(ctx), phase(ph) {
+        if (!c->profiling) return;
+        PhaseTimer &t = c->timers[phase];
+        while (t.pool.size() < t.used + 2) {
+            cudaEvent_t e; PICSP_CUDA(cudaEventCreate(&e)); t.pool.push_back(e);
+        }
+        e0 = t.pool[t.used]; e1 = t.pool[t.used + 1]; t.used += 2;
+        PICSP_CUDA(cudaEventRecord(e0, c->stream));
+    }
+    ~PhaseScope() {
+        if (e1) cudaEventRecord(e1, c->stream);
+        if (c->profiling) c->timers[phase].calls++;
+    }
+};
+
+inline void profile_collect(picsp_ctx *c) {
+    for (int p = 0; p < PICSP_PHASE_COUNT; p++) {
+        PhaseTimer &t = c->timers[p];
+        for (size_t i = 0; i + 1 < t.used; i += 2) {
+            float ms = 0.f;
+            PICSP_CUDA(cudaEventSynchronize(t.pool[i + 1]));
+            PICSP_CUDA(cudaEventElapsedTime(&ms, t.pool[i], t.pool[i + 1]));
+            t.ms += ms;
+        }
+        t.used = 0;
+    }
+}
+
+inline int blocks_for(long long n, int threads, int max_blocks) {
+    long long b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (int)b;
+}
+
+#define PICSP_LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
+    do {                                                                                    \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                    \
+        (ctx)->launches++;                                                                  \
+        PICSP_CUDA(cudaGetLastError());                                                     \
+    } while (0)
+
+}  // namespace picsp

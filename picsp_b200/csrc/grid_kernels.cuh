@@ -1,0 +1,276 @@
+// picsp_b200/csrc/grid_kernels.cuh — field-side kernels (all O(grid), L2-resident).
+//
+// Each kernel names the reference statements it replaces (/root/reference/src/main.cpp).
+#pragma once
+#include "ctx.cuh"
+
+namespace picsp {
+
+// The reference's truncated pi (src/main.cpp:61) — used in k, NOT in the FFT twiddles.
+__device__ __constant__ double kRefPi = 3.14159265359;
+
+// ---------------------------------------------------------------------------
+// finalize: den += (spwt/(dx*dy)) * acc * 2^-frac ; acc = 0
+// (the accumulate-into semantics of scatterSpecies, src/main.cpp:689-700: the
+//  clearing memset at :692 is commented out, so den is a running sum — Q1)
+// ---------------------------------------------------------------------------
+__global__ void k_deposit_finalize(double *__restrict__ den, long long *__restrict__ acc,
+                                   const int *__restrict__ frac, double weight, long long nn, int clear) {
+    const double scale = weight * exp2((double)(-*frac));
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nn;
+         k += (long long)gridDim.x * blockDim.x) {
+        long long a = acc[k];
+        double base = clear ? 0.0 : den[k];
+        den[k] = base + (double)a * scale;
+        acc[k] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// periodic fold, rows first then columns (src/main.cpp:702-712 and :880-890).
+// One CTA: the two phases are ordered (corners take both), 2*(nix+niy) updates.
+// ---------------------------------------------------------------------------
+__global__ void k_fold_periodic(double *f, int nix, int niy) {
+    for (int j = threadIdx.x; j < niy; j += blockDim.x) {
+        double v = f[j] + f[(long long)(nix - 1) * niy + j];
+        f[j] = v;
+        f[(long long)(nix - 1) * niy + j] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nix; i += blockDim.x) {
+        double v = f[(long long)i * niy] + f[(long long)i * niy + niy - 1];
+        f[(long long)i * niy] = v;
+        f[(long long)i * niy + niy - 1] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// rho interior (src/main.cpp:874-878); boundary nodes are left as they are (Q3)
+// ---------------------------------------------------------------------------
+__global__ void k_compute_rho(double *__restrict__ rho, const double *__restrict__ den_i,
+                              const double *__restrict__ den_e, double q_i, double q_e, int nix, int niy) {
+    long long nint = (long long)(nix - 2) * (niy - 2);
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nint;
+         k += (long long)gridDim.x * blockDim.x) {
+        int i = 1 + (int)(k / (niy - 2)), j = 1 + (int)(k % (niy - 2));
+        long long idx = (long long)i * niy + j;
+        rho[idx] = q_i * den_i[idx] + q_e * den_e[idx];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k-space Green's function (src/main.cpp:996-1025) + 1/(Nx*Ny) (:1051-1055).
+//  * kx = 2*PI*i/Lx for i < Nx/2, 2*PI*(Nx-i)/Lx for i > Nx/2, Lx = xl (:999-1021)
+//  * row i == Nx/2 is never written by the reference -> defined as 0 (Q7)
+//  * DC bin zeroed (:1023-1024)
+//  * the zeroed row breaks Hermitian symmetry in the self-conjugate columns; FFTW's
+//    c2r silently keeps only the real part after the dim-0 transform, cuFFT's Z2D
+//    leaves that case undefined, so those columns are symmetrised here:
+//        P[i,j] <- (P[i,j] + conj P[(Nx-i)%Nx, j]) / 2      for j == 0 (and j == Ny/2, Ny even)
+//    which gives the identical real output (Re of the dim-0 transform).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double2 green_bin(const cufftDoubleComplex *__restrict__ rhok, int i, int j,
+                                             int Nx, int Nh, double Lx, double Ly) {
+    if (i == Nx / 2 || (i == 0 && j == 0)) return make_double2(0.0, 0.0);
+    double ky = 2.0 * kRefPi * j / Ly;
+    double kx = (i < Nx / 2) ? 2.0 * kRefPi * i / Lx : 2.0 * kRefPi * (Nx - i) / Lx;
+    double k2 = kx * kx + ky * ky;
+    cufftDoubleComplex r = rhok[(long long)i * Nh + j];
+    return make_double2(r.x / k2, r.y / k2);
+}
+
+__global__ void k_kspace_green(const cufftDoubleComplex *__restrict__ rhok, cufftDoubleComplex *__restrict__ phik,
+                               int Nx, int Ny, double Lx, double Ly) {
+    const int Nh = Ny / 2 + 1;
+    const double norm = (double)((long long)Nx * Ny);
+    long long total = (long long)Nx * Nh;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total;
+         k += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(k / Nh), j = (int)(k % Nh);
+        double2 p = green_bin(rhok, i, j, Nx, Nh, Lx, Ly);
+        bool self_conj = (j == 0) || ((Ny % 2 == 0) && (j == Ny / 2));
+        if (self_conj) {
+            double2 m = green_bin(rhok, (Nx - i) % Nx, j, Nx, Nh, Lx, Ly);
+            p.x = 0.5 * (p.x + m.x);
+            p.y = 0.5 * (p.y - m.y);
+        }
+        phik[k].x = p.x / norm;
+        phik[k].y = p.y / norm;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// SOR (src/main.cpp:904-957): in-place lexicographic sweeps with omega = 1.4 and
+// periodic wrap indices.  The lexicographic order is reproduced EXACTLY by an
+// anti-diagonal wavefront: node (i,j) needs the new values of (i-1,j), (i,j-1)
+// (diagonal d-1), the new (1,j) when i == nix-1 and the new (i,1) when j == niy-1
+// (earlier diagonals), and the OLD values of (i+1,j), (i,j+1), (nix-2,j) for i == 0
+// and (i,niy-2) for j == 0 (all on later diagonals).  One CTA marches the
+// nix+niy-1 diagonals with a block barrier between them; nodes on one diagonal are
+// independent.  Convergence is tested after sweeps 0,100,200,... exactly as the
+// reference does (in practice the first test passes: one sweep per call, Q6).
+// status[0] = sweeps done (negative: cap hit), d_l2 = last L2.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double ldcg(const double *p) { return __ldcg(p); }
+
+__global__ void __launch_bounds__(1024, 1)
+k_sor_solve(double *phi, const double *__restrict__ rho, int nix, int niy, double dx, double dy,
+            long long *status, double *d_l2, int max_sweeps) {
+    __shared__ double s_red[32];
+    __shared__ double s_l2;
+    const double dx2 = dx * dx, dy2 = dy * dy, eps = 1.0;
+    const double coef = 0.5 * (1 / ((1 / dx2) + (1 / dy2)));
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double L2 = 0.0;
+    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+        for (int d = 0; d <= nix + niy - 2; d++) {
+            int i_lo = d - (niy - 1); if (i_lo < 0) i_lo = 0;
+            int i_hi = d < nix - 1 ? d : nix - 1;
+            for (int i = i_lo + tid; i <= i_hi; i += nt) {
+                int j = d - i;
+                int p = i - 1; if (p < 0) p = nix - 2;
+                int q = i + 1; if (q > nix - 1) q = 1;
+                int r = j - 1; if (r < 0) r = niy - 2;
+                int s = j + 1; if (s > niy - 1) s = 1;
+                long long c = (long long)i * niy + j;
+                double g = coef * (((ldcg(&phi[(long long)p * niy + j]) + ldcg(&phi[(long long)q * niy + j])) / dx2) +
+                                   ((ldcg(&phi[(long long)i * niy + r]) + ldcg(&phi[(long long)i * niy + s])) / dy2) +
+                                   (rho[c] / eps));
+                double old = ldcg(&phi[c]);
+                __stcg(&phi[c], old + 1.4 * (g - old));
+            }
+            __syncthreads();
+        }
+        if (sweep % 100 == 0) {
+            double sum = 0.0;
+            long long nn = (long long)nix * niy;
+            for (long long k = tid; k < nn; k += nt) {
+                int i = (int)(k / niy), j = (int)(k % niy);
+                int p = i - 1; if (p < 0) p = nix - 2;
+                int q = i + 1; if (q > nix - 1) q = 1;
+                int r = j - 1; if (r < 0) r = niy - 2;
+                int s = j + 1; if (s > niy - 1) s = 1;
+                double R = 0.25 * (ldcg(&phi[(long long)p * niy + j]) + ldcg(&phi[(long long)q * niy + j]) +
+                                   ldcg(&phi[(long long)i * niy + r]) + ldcg(&phi[(long long)i * niy + s]) +
+                                   (dx2 * rho[k] / eps)) - ldcg(&phi[k]);
+                sum = sum + (R * R);
+            }
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if ((tid & 31) == 0) s_red[tid >> 5] = sum;
+            __syncthreads();
+            if (tid == 0) {
+                double t = 0.0;
+                for (int w = 0; w < (nt + 31) / 32; w++) t += s_red[w];
+                s_l2 = sqrt(t) / (nix * niy);
+            }
+            __syncthreads();
+            L2 = s_l2;
+            if (L2 < 1e-2) {
+                if (tid == 0) { status[0] = sweep + 1; *d_l2 = L2; }
+                return;
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) { status[0] = -(long long)max_sweeps; *d_l2 = L2; }
+}
+
+// ---------------------------------------------------------------------------
+// E field (src/main.cpp:1111-1139).  Interior: central differences.  Rows i = 0 and
+// i = nix-1 get the one-sided efx (divided by 2*dx as the reference does), columns
+// j = 0 and j = niy-1 the one-sided efy.  efx[i][0], efx[i][niy-1] for interior i
+// and efy[0][j], efy[nix-1][j] for interior j are never written (Q8).
+// E is stored interleaved {efx, efy} so that a gather corner is one 16-byte load.
+// ---------------------------------------------------------------------------
+__global__ void k_compute_ef(const double *__restrict__ phi, double2 *__restrict__ E, int nix, int niy,
+                             double dx, double dy) {
+    long long nn = (long long)nix * niy;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nn;
+         k += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(k / niy), j = (int)(k % niy);
+        bool ii = (i >= 1 && i <= nix - 2), jj = (j >= 1 && j <= niy - 2);
+        if (ii && jj) {
+            double2 e;
+            e.x = (phi[k - niy] - phi[k + niy]) / (2 * dx);
+            e.y = (phi[k - 1] - phi[k + 1]) / (2 * dy);
+            E[k] = e;
+            continue;
+        }
+        if (i == 0)            E[k].x = -(phi[k + niy] - phi[k]) / (2 * dx);
+        else if (i == nix - 1) E[k].x = -(phi[k] - phi[k - niy]) / (2 * dx);
+        if (j == 0)            E[k].y = -(phi[k + 1] - phi[k]) / (2 * dy);
+        else if (j == niy - 1) E[k].y = -(phi[k] - phi[k - 1]) / (2 * dy);
+    }
+}
+
+// split/merge for the ABI's separate efx / efy views
+__global__ void k_ef_get_component(const double2 *__restrict__ E, double *__restrict__ out, long long nn, int comp) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nn; k += (long long)gridDim.x * blockDim.x)
+        out[k] = comp ? E[k].y : E[k].x;
+}
+__global__ void k_ef_set_component(double2 *__restrict__ E, const double *__restrict__ in, long long nn, int comp) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nn; k += (long long)gridDim.x * blockDim.x) {
+        if (comp) E[k].y = in[k]; else E[k].x = in[k];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// deterministic reductions (fixed grid, fixed tree): sum(vx^2+vy^2) and max(phi)
+// ---------------------------------------------------------------------------
+constexpr int RED_BLOCKS = 592;   // 4 per SM on 148 SMs
+constexpr int RED_THREADS = 256;
+
+__device__ __forceinline__ double block_sum(double v, double *s_red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (blockDim.x + 31) / 32; w++) t += s_red[w];
+    return t;   // valid on thread 0
+}
+
+__global__ void k_ke_partial(const double *__restrict__ vx, const double *__restrict__ vy, long long n,
+                             double *__restrict__ partial) {
+    __shared__ double s_red[32];
+    double s = 0.0;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x)
+        s += vx[p] * vx[p] + vy[p] * vy[p];
+    double t = block_sum(s, s_red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+__global__ void k_sum_final(const double *__restrict__ partial, int n, double *__restrict__ out) {
+    __shared__ double s_red[32];
+    double s = 0.0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) s += partial[k];
+    double t = block_sum(s, s_red);
+    if (threadIdx.x == 0) *out = t;
+}
+__global__ void k_max_partial(const double *__restrict__ f, long long n, double *__restrict__ partial) {
+    __shared__ double s_red[32];
+    double m = f[0];
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+        m = f[k] > m ? f[k] : m;
+    for (int o = 16; o > 0; o >>= 1) { double t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < (blockDim.x + 31) / 32; w++) m = s_red[w] > m ? s_red[w] : m;
+        partial[blockIdx.x] = m;
+    }
+}
+__global__ void k_max_final(const double *__restrict__ partial, int n, const double *__restrict__ f,
+                            double *__restrict__ out_max, double *__restrict__ out_f0) {
+    __shared__ double s_red[32];
+    double m = f[0];
+    for (int k = threadIdx.x; k < n; k += blockDim.x) m = partial[k] > m ? partial[k] : m;
+    for (int o = 16; o > 0; o >>= 1) { double t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < (blockDim.x + 31) / 32; w++) m = s_red[w] > m ? s_red[w] : m;
+        *out_max = m; *out_f0 = f[0];
+    }
+}
+
+}  // namespace picsp

@@ -1,0 +1,231 @@
+// picsp_b200/csrc/particle_kernels.cuh — particle-side kernels.
+//
+// Particle state is structure-of-arrays (x[], y[], vx[], vy[], f64) in HBM.
+// Deposition accumulates 64-bit FIXED-POINT weights with integer atomics: integer
+// addition is associative, so the density is bit-for-bit independent of particle
+// order, launch order and atomic arrival order (deterministic within a GPU), which a
+// floating-point atomic cannot give.  The number of fraction bits is chosen on the
+// device from a per-tile particle histogram so that no node can overflow 2^62 while
+// keeping the quantum far below double rounding of the node value.
+#pragma once
+#include "ctx.cuh"
+
+namespace picsp {
+
+struct PushConst {
+    double dx;        // == dy
+    double dt;
+    double dtqm;      // timeStep*qm            (src/main.cpp:793: evaluated as (timeStep*qm)*E)
+    double hdtqm;     // 0.5*timeStep*qm        (src/main.cpp:863: ((0.5*timeStep)*qm)*E)
+    double xl, yl;    // domain.xl == xmax, domain.yl == ymax (x0 = y0 = 0)
+    int nix, niy;
+    int ntx, nty;
+    long long nn, guard;
+};
+
+// XtoL / YtoL, src/main.cpp:643-652: true division, x0 = y0 = 0.
+__device__ __forceinline__ double to_logical(double pos, double dx) { return (pos - 0.0) / dx; }
+
+// ---------------------------------------------------------------------------
+// gather, src/main.cpp:671-681.  (int) casts truncate toward zero; indexing is
+// flat, i*niy+j, exactly as the reference, so a j == niy-1 cell reads the next row
+// (Q5).  Reads outside the array — undefined behaviour in the reference — return 0:
+// E carries a zeroed guard band and anything beyond it is clamped to 0 as well.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double2 load_E(const double2 *__restrict__ E, long long idx, long long nn, long long guard) {
+    if (idx < -guard || idx >= nn + guard) return make_double2(0.0, 0.0);
+    return E[idx];
+}
+
+__device__ __forceinline__ double2 gather_E(const double2 *__restrict__ E, const PushConst &c, double lx, double ly) {
+    int i = __double2int_rz(lx);
+    int j = __double2int_rz(ly);
+    double di = lx - i, dj = ly - j;
+    long long b = (long long)i * c.niy + j;
+    double2 f00, f10, f01, f11;
+    if (i >= 0 && i <= c.nix - 2 && j >= 0 && j <= c.niy - 2) {   // all four corners are real nodes
+        f00 = E[b]; f10 = E[b + c.niy]; f01 = E[b + 1]; f11 = E[b + c.niy + 1];
+    } else {
+        f00 = load_E(E, b, c.nn, c.guard); f10 = load_E(E, b + c.niy, c.nn, c.guard);
+        f01 = load_E(E, b + 1, c.nn, c.guard); f11 = load_E(E, b + c.niy + 1, c.nn, c.guard);
+    }
+    double2 e;
+    e.x = f00.x * (1 - di) * (1 - dj) + f10.x * di * (1 - dj) + f01.x * (1 - di) * dj + f11.x * di * dj;
+    e.y = f00.y * (1 - di) * (1 - dj) + f10.y * di * (1 - dj) + f01.y * (1 - di) * dj + f11.y * di * dj;
+    return e;
+}
+
+__device__ __forceinline__ int tile_of(double x, double y, const PushConst &c) {
+    int ci = __double2int_rz(to_logical(x, c.dx)), cj = __double2int_rz(to_logical(y, c.dx));
+    int tx = ci / TILE, ty = cj / TILE;
+    tx = tx < 0 ? 0 : (tx >= c.ntx ? c.ntx - 1 : tx);
+    ty = ty < 0 ? 0 : (ty >= c.nty ? c.nty - 1 : ty);
+    return tx * c.nty + ty;
+}
+
+// ---------------------------------------------------------------------------
+// fixed-point CIC scatter of one particle (weights of src/main.cpp:664-667 without
+// the common factor spwt/(dx*dy), which k_deposit_finalize applies once per node)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void scatter_fixed(long long *__restrict__ acc, const PushConst &c, double x, double y,
+                                              double scale) {
+    double lx = to_logical(x, c.dx), ly = to_logical(y, c.dx);
+    int i = __double2int_rz(lx), j = __double2int_rz(ly);
+    double di = lx - i, dj = ly - j;
+    if (i < 0 || i > c.nix - 2 || j < 0 || j > c.niy - 2) return;   // cannot happen for 0 <= pos < xl (main.cpp:807-824 guarantees it)
+    long long b = (long long)i * c.niy + j;
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(acc);
+    atomicAdd(&a[b],             (unsigned long long)__double2ll_rn((1 - di) * (1 - dj) * scale));
+    atomicAdd(&a[b + c.niy],     (unsigned long long)__double2ll_rn(di * (1 - dj) * scale));
+    atomicAdd(&a[b + 1],         (unsigned long long)__double2ll_rn((1 - di) * dj * scale));
+    atomicAdd(&a[b + c.niy + 1], (unsigned long long)__double2ll_rn(di * dj * scale));
+}
+
+// ---------------------------------------------------------------------------
+// per-tile particle histogram and the fixed-point scale derived from it
+// ---------------------------------------------------------------------------
+__global__ void k_tile_hist(const double *__restrict__ x, const double *__restrict__ y, long long n,
+                            PushConst c, unsigned int *__restrict__ hist) {
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&hist[tile_of(x[p], y[p], c)], 1u);
+}
+
+// frac = 62 - bits(max over tiles of the periodic 5x5 neighbourhood population).
+// A node receives weight only from particles in the <= 2x2 tiles around it; the
+// fused mover deposits positions one step after the histogram was taken, and a
+// particle may move by at most one tile per step (checked by the mover), so the
+// 5x5 neighbourhood bounds every node sum by pop * 2^frac < 2^62.
+__global__ void k_frac_from_hist(const unsigned int *__restrict__ hist, int ntx, int nty, int *__restrict__ frac) {
+    __shared__ unsigned long long s_max[32];
+    unsigned long long m = 0;
+    int wx = ntx < 5 ? ntx : 5, wy = nty < 5 ? nty : 5;
+    for (int t = threadIdx.x; t < ntx * nty; t += blockDim.x) {
+        int tx = t / nty, ty = t % nty;
+        unsigned long long s = 0;
+        for (int a = 0; a < wx; a++)
+            for (int b = 0; b < wy; b++) {
+                int ux = (tx - wx / 2 + a + 2 * ntx) % ntx, uy = (ty - wy / 2 + b + 2 * nty) % nty;
+                s += hist[ux * nty + uy];
+            }
+        m = s > m ? s : m;
+    }
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < (blockDim.x + 31) / 32; w++) m = s_max[w] > m ? s_max[w] : m;
+        int bits = 64 - __clzll((long long)(m | 1ull));
+        int f = 62 - bits;
+        *frac = f > 60 ? 60 : (f < 0 ? 0 : f);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// standalone deposit (scatter loop of scatterSpecies, src/main.cpp:695-700)
+// ---------------------------------------------------------------------------
+__global__ void k_deposit(const double *__restrict__ x, const double *__restrict__ y, long long n, PushConst c,
+                          long long *__restrict__ acc, const int *__restrict__ frac) {
+    const double scale = exp2((double)*frac);
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x)
+        scatter_fixed(acc, c, x[p], y[p], scale);
+}
+
+// ---------------------------------------------------------------------------
+// mover: pushSpecies + gather (src/main.cpp:772-847, :671-681), optionally fused
+// with the NEXT step's scatter (the positions written here are exactly the ones
+// scatterSpecies reads next, src/main.cpp:482-483), which makes one particle-step
+// cost 32 B read + 32 B written.
+//
+// The reference's wrap is an if/else-if chain whose trailing `else it++` is the
+// only place the list iterator advances (:807-845): a particle that wrapped is
+// pushed AGAIN from its wrapped position, until a push ends inside the box (Q4).
+// ---------------------------------------------------------------------------
+constexpr int ERR_BIT_DISPLACEMENT = 1;
+constexpr int ERR_BIT_RUNAWAY = 2;
+
+template <bool FUSE_DEPOSIT>
+__global__ void __launch_bounds__(256)
+k_push(double *__restrict__ x, double *__restrict__ y, double *__restrict__ vx, double *__restrict__ vy,
+       long long n, PushConst c, const double2 *__restrict__ E, long long *__restrict__ acc,
+       const int *__restrict__ frac, unsigned int *__restrict__ hist_next,
+       unsigned long long *__restrict__ repush, int *__restrict__ err) {
+    const double scale = FUSE_DEPOSIT ? exp2((double)*frac) : 0.0;
+    unsigned int extra = 0;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        double px = x[p], py = y[p], pvx = vx[p], pvy = vy[p];
+        const int t0 = tile_of(px, py, c);
+        int wrapped, guard_iter = 0;
+        do {
+            double lx = to_logical(px, c.dx), ly = to_logical(py, c.dx);
+            double2 e = gather_E(E, c, lx, ly);
+            pvx += c.dtqm * e.x;
+            pvy += c.dtqm * e.y;
+            px += c.dt * pvx;
+            py += c.dt * pvy;
+            wrapped = 1;
+            if (px < 0.0) px += c.xl;
+            else if (px >= c.xl) px -= c.xl;
+            else if (py < 0.0) py += c.yl;
+            else if (py >= c.yl) py -= c.yl;
+            else wrapped = 0;
+            extra += wrapped;
+            if (++guard_iter > 64) { atomicOr(err, ERR_BIT_RUNAWAY); break; }   // +-inf / absurd speeds: the reference would spin forever
+        } while (wrapped);
+        x[p] = px; y[p] = py; vx[p] = pvx; vy[p] = pvy;
+        if (FUSE_DEPOSIT) {
+            const int t1 = tile_of(px, py, c);
+            int dtx = abs(t1 / c.nty - t0 / c.nty), dty = abs(t1 % c.nty - t0 % c.nty);
+            dtx = min(dtx, c.ntx - dtx); dty = min(dty, c.nty - dty);
+            if (dtx > 1 || dty > 1) atomicOr(err, ERR_BIT_DISPLACEMENT);
+            atomicAdd(&hist_next[t1], 1u);
+            scatter_fixed(acc, c, px, py, scale);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) extra += __shfl_xor_sync(0xffffffffu, extra, o);
+    if ((threadIdx.x & 31) == 0 && extra) atomicAdd(repush, (unsigned long long)extra);
+}
+
+// rewindSpecies, src/main.cpp:850-866 (no move, no wrap)
+__global__ void k_rewind(const double *__restrict__ x, const double *__restrict__ y, double *__restrict__ vx,
+                         double *__restrict__ vy, long long n, PushConst c, const double2 *__restrict__ E) {
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        double lx = to_logical(x[p], c.dx), ly = to_logical(y[p], c.dx);
+        double2 e = gather_E(E, c, lx, ly);
+        vx[p] -= c.hdtqm * e.x;
+        vy[p] -= c.hdtqm * e.y;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// bench-only synthetic loader (NOT reference behaviour): counter-based RNG
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double u01(uint64_t seed, uint64_t idx, uint32_t draw) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx * 8ull + draw + 1ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void k_fill_synthetic(double *__restrict__ x, double *__restrict__ y, double *__restrict__ vx,
+                                 double *__restrict__ vy, long long n, long long first, uint64_t seed,
+                                 double xl, double yl, double vth, double xdrift) {
+    const double s2 = 1.4142135623730951;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        uint64_t g = (uint64_t)(first + p);
+        x[p] = u01(seed, g, 0) * xl;
+        y[p] = u01(seed, g, 4) * yl;
+        double sgn = (g & 1ull) ? -1.0 : 1.0;
+        vx[p] = vth * s2 * (u01(seed, g, 1) + u01(seed, g, 2) + u01(seed, g, 3) - 1.5) + sgn * xdrift;
+        vy[p] = vth * s2 * (u01(seed, g, 5) + u01(seed, g, 6) + u01(seed, g, 7) - 1.5);
+    }
+}
+
+// un-permute for downloads: out[id[slot]] = in[slot]
+__global__ void k_unpermute(const double *__restrict__ in, const uint32_t *__restrict__ id, double *__restrict__ out,
+                            long long n) {
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x)
+        out[id[p]] = in[p];
+}
+
+}  // namespace picsp

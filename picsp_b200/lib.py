@@ -1,0 +1,93 @@
+"""ctypes binding of include/picsp_b200.h (one function per ABI entry point)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+LIB_PATH = os.path.join(PKG, "libpicsp_b200.so")
+HEADER = os.path.join(ROOT, "include", "picsp_b200.h")
+
+_dp = C.POINTER(C.c_double)
+_i64p = C.POINTER(C.c_int64)
+
+
+class PicspError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"picsp_b200 error {code}: {msg}")
+        self.code = code
+
+
+class CParams(C.Structure):
+    _fields_ = [("numxCells", C.c_int32), ("numyCells", C.c_int32), ("stepSize", C.c_double), ("timeStep", C.c_double),
+                ("solverType", C.c_int32), ("flags", C.c_int32), ("charge", C.c_double * 2), ("mass", C.c_double * 2),
+                ("spwt", C.c_double * 2), ("capacity", C.c_int64 * 2), ("device", C.c_int32), ("reserved", C.c_int32)]
+
+
+def abi_symbols():
+    """Every function name declared in include/picsp_b200.h."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(picsp_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def load_library():
+    """Loads the in-tree CUDA library.  No fallback: a missing library is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} is missing: build it with `python -m picsp_b200.build` "
+                                "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    ctx = C.c_void_p
+    sig = {
+        "picsp_abi_version": ([], C.c_int),
+        "picsp_create": ([C.POINTER(CParams), C.POINTER(ctx)], C.c_int),
+        "picsp_destroy": ([ctx], None),
+        "picsp_last_error": ([], C.c_char_p),
+        "picsp_sync": ([ctx], C.c_int),
+        "picsp_species_upload": ([ctx, C.c_int, _dp, _dp, _dp, _dp, C.c_int64], C.c_int),
+        "picsp_species_download": ([ctx, C.c_int, _dp, _dp, _dp, _dp], C.c_int),
+        "picsp_species_count": ([ctx, C.c_int, _i64p], C.c_int),
+        "picsp_species_download_rows": ([ctx, C.c_int, _dp], C.c_int),
+        "picsp_grid_upload": ([ctx, C.c_int, _dp], C.c_int),
+        "picsp_grid_download": ([ctx, C.c_int, _dp], C.c_int),
+        "picsp_deposit": ([ctx, C.c_int], C.c_int),
+        "picsp_compute_rho": ([ctx], C.c_int),
+        "picsp_solve": ([ctx], C.c_int),
+        "picsp_solve_spectral": ([ctx], C.c_int),
+        "picsp_solve_sor": ([ctx, _i64p, _dp], C.c_int),
+        "picsp_compute_ef": ([ctx], C.c_int),
+        "picsp_push": ([ctx, C.c_int], C.c_int),
+        "picsp_rewind": ([ctx, C.c_int], C.c_int),
+        "picsp_bootstrap": ([ctx], C.c_int),
+        "picsp_step": ([ctx, C.c_int], C.c_int),
+        "picsp_compute_ke": ([ctx, C.c_int, _dp], C.c_int),
+        "picsp_delta_phi": ([ctx, _dp, _dp], C.c_int),
+        "picsp_repush_count": ([ctx, C.c_int, _i64p], C.c_int),
+        "picsp_comm_unique_id": ([C.c_void_p], C.c_int),
+        "picsp_comm_attach": ([ctx, C.c_void_p, C.c_int, C.c_int], C.c_int),
+        "picsp_species_fill_synthetic": ([ctx, C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_double], C.c_int),
+        "picsp_profile_enable": ([ctx, C.c_int], C.c_int),
+        "picsp_profile_get": ([ctx, C.c_int, _dp, _i64p], C.c_int),
+        "picsp_profile_reset": ([ctx], C.c_int),
+        "picsp_kernel_launches": ([ctx, _i64p], C.c_int),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = res
+    L._picsp_signatures = sig
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise PicspError(rc, load_library().picsp_last_error().decode(errors="replace"))

@@ -1,0 +1,70 @@
+"""CPU: the C-ABI library loads, exports every symbol include/picsp_b200.h declares, and fails
+loudly (no CPU fallback) when there is no CUDA device.  No compute calls are made here."""
+import ctypes as C
+import os
+import subprocess
+
+import pytest
+
+import picsp_b200
+from picsp_b200 import lib as pl
+
+
+def test_library_is_in_tree_and_loads():
+    if not os.path.isfile(pl.LIB_PATH):
+        from picsp_b200 import build
+        build.build()
+    L = picsp_b200.load_library()
+    assert L.picsp_abi_version() == 1
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    L = picsp_b200.load_library()
+    declared = picsp_b200.abi_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/picsp_b200.h but not exported"
+    assert set(L._picsp_signatures) == set(declared), "python binding out of sync with the header"
+    out = subprocess.run(["nm", "-D", "--defined-only", pl.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert set(declared) <= exported
+
+
+def test_header_has_no_foreign_types():
+    import re
+    text = re.sub(r"/\*.*?\*/", "", open(pl.HEADER).read(), flags=re.S)   # declarations only, comments stripped
+    for bad in ("torch", "at::", "cudaStream_t", "#include <cuda"):
+        assert bad not in text
+
+
+def test_params_struct_layout_matches_header():
+    # int32 x2, f64 x2, int32 x2, f64[2] x3, int64[2], int32 x2  ->  104 bytes, natural alignment
+    assert C.sizeof(pl.CParams) == 104
+    assert pl.CParams.stepSize.offset == 8 and pl.CParams.charge.offset == 32 and pl.CParams.capacity.offset == 80
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback():
+    with pytest.raises(picsp_b200.PicspError) as ei:
+        picsp_b200.Simulation(picsp_b200.Params(16, 16, 0.017, 0.005, 1836.0, 10, 10))
+    assert ei.value.code == -2          # PICSP_ERR_NO_DEVICE
+
+
+def test_product_never_touches_the_oracle():
+    """The product tree must not import, link or mention oracle/ (it is test infrastructure)."""
+    pkg = os.path.dirname(pl.LIB_PATH)
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                src = open(os.path.join(d, f), errors="replace").read()
+                assert "oracle" not in src.lower(), os.path.join(d, f)
+    out = subprocess.run(["ldd", pl.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "picsp_ref" not in out

@@ -1,0 +1,204 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the reference.
+
+Checkers: the golden vectors produced by the unmodified reference TU (tests/golden/) and the
+C restatement (oracle/), which is bit-identical to that TU.  Tolerance: the north_star's
+1e-12 relative (max-norm) for density, potential, fields and phase space in double precision;
+interior and edge nodes are normalised separately (see tests/helpers.assert_grid_close).
+"""
+import numpy as np
+import pytest
+
+import picsp_b200
+from oracle.oracle import ELECTRON, ION, Oracle, normalise
+from picsp_b200 import Params, Simulation
+from tests.helpers import GRIDS, RTOL, assert_grid_close, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+LOOPS = ["loop_sor_65_load2_O0", "loop_sor_33_load1", "loop_spectral_33_load1", "loop_spectral_48x_load1"]
+PART = {ION: "i", ELECTRON: "e"}
+
+
+def sim_from_golden(g, flags=0):
+    numx, n, solver, load_type, nsteps = (int(v) for v in g["meta"])
+    dx, dt, mass_i = g["params"][:3]
+    return Simulation(Params(numx, numx, float(dx), float(dt), float(mass_i), n, n, solverType=solver, flags=flags)), nsteps
+
+
+def put_state(sim, g, tag, particles_tag=None):
+    for name in GRIDS:
+        sim.set_grid(name, g[f"{tag}/{name}"])
+    pt = particles_tag or tag
+    for s in (ION, ELECTRON):
+        sim.set_species(s, *g[f"{pt}/part_{PART[s]}"])
+
+
+def check_grids(sim, g, tag, names=GRIDS, tol=RTOL):
+    for name in names:
+        assert_grid_close(sim.grid(name), g[f"{tag}/{name}"], sim.nix, sim.niy, tol, f"{tag}/{name}")
+
+
+def check_particles(sim, g, tag, tol=RTOL):
+    for s in (ION, ELECTRON):
+        got = sim.get_species(s)
+        want = g[f"{tag}/part_{PART[s]}"]
+        for k, nm in enumerate("x y vx vy".split()):
+            e = relerr(got[k], want[k])
+            assert e <= tol, f"{tag} species {s} {nm}: rel err {e:.3e}"
+
+
+@pytest.mark.parametrize("name", LOOPS)
+def test_single_ops_against_reference_golden(name):
+    """Each hot-path function on the reference's own input state for that phase."""
+    g = load_golden(name)
+    sim, _ = sim_from_golden(g)
+    with sim:
+        put_state(sim, g, "loaded")
+        sim.scatterSpecies(ION); sim.scatterSpecies(ELECTRON)
+        check_grids(sim, g, "boot_deposit", ("den_i", "den_e"))
+        put_state(sim, g, "boot_deposit", "loaded"); sim.computeRho()
+        check_grids(sim, g, "boot_rho", ("rho",))
+        put_state(sim, g, "boot_rho", "loaded"); sim.solve()
+        check_grids(sim, g, "boot_solve", ("phi",))
+        put_state(sim, g, "boot_solve", "loaded"); sim.computeEF()
+        check_grids(sim, g, "boot_ef", ("efx", "efy"))
+        put_state(sim, g, "boot_ef", "loaded"); sim.rewindSpecies(ION); sim.rewindSpecies(ELECTRON)
+        check_particles(sim, g, "boot_rewind")
+        # one full loop body from the reference's state after the bootstrap
+        put_state(sim, g, "boot_rewind")
+        sim.step(1)
+        check_grids(sim, g, "step0"); check_particles(sim, g, "step0")
+        for s in (ION, ELECTRON):
+            assert abs(sim.computeKE(s) - g["step0/ke"][s]) <= RTOL * abs(g["step0/ke"][s])
+
+
+@pytest.mark.parametrize("name", LOOPS)
+@pytest.mark.parametrize("flags", [0, 4], ids=["fused", "nofuse"])
+def test_chained_loop_against_reference_golden(name, flags):
+    """bootstrap + several steps with no resynchronisation (fused and unfused mover)."""
+    g = load_golden(name)
+    sim, nsteps = sim_from_golden(g, flags)
+    with sim:
+        put_state(sim, g, "loaded")
+        sim.bootstrap()
+        check_grids(sim, g, "boot_rewind"); check_particles(sim, g, "boot_rewind")
+        for st in range(nsteps):
+            sim.step(1)
+            check_grids(sim, g, f"step{st}", tol=10 * RTOL)
+            check_particles(sim, g, f"step{st}", tol=10 * RTOL)
+
+
+def test_edge_push_and_rewind():
+    """Wrap / re-push chain (main.cpp:807-845), corners, fast particles, guard-band gathers."""
+    g = load_golden("edge_push")
+    numx, n = (int(v) for v in g["meta"])
+    dx, dt, mass_i = (float(v) for v in g["params"])
+    cin = g["in"]
+    with Simulation(Params(numx, numx, dx, dt, mass_i, n, n, solverType=2, capacity=(cin.shape[1],) * 2)) as sim:
+        for name in GRIDS:
+            sim.set_grid(name, g["field/" + name])
+        for s in (ION, ELECTRON):
+            sim.set_species(s, *cin)
+            sim.pushSpecies(s)
+            got = sim.get_species(s)
+            want = g["push_" + PART[s]]
+            for k in range(4):
+                assert relerr(got[k], want[k]) <= RTOL, (s, k)
+            assert sim.repush_count(s) > 50
+            sim.set_species(s, *cin)
+            sim.rewindSpecies(s)
+            got = sim.get_species(s)
+            want = g["rewind_" + PART[s]]
+            for k in range(4):
+                assert relerr(got[k], want[k]) <= RTOL, (s, k)
+
+
+@pytest.mark.parametrize("solver,numx,n", [(1, 128, 300_000), (2, 128, 300_000), (1, 256, 400_000), (2, 100, 50_000)])
+def test_step_against_oracle_midsize(solver, numx, n):
+    """Seeded Maxwellian plasma, bootstrap + 2 steps, CUDA path vs the C restatement."""
+    nm = normalise()
+    o = Oracle(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, vth_i=nm["vth_i"], solver=solver)
+    o.seed(3); o.init(ION, 1); o.init(ELECTRON, 1)
+    with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, solverType=solver)) as sim:
+        for s in (ION, ELECTRON):
+            sim.set_species(s, *o.get_species(s))
+        o.bootstrap(); sim.bootstrap()
+        for st in range(2):
+            o.step(1); sim.step(1)
+            for name in GRIDS:
+                assert_grid_close(sim.grid(name), o.grid(name), sim.nix, sim.niy, 10 * RTOL, f"step{st}/{name}")
+            for s in (ION, ELECTRON):
+                got, want = sim.get_species(s), o.get_species(s)
+                for k in range(4):
+                    assert relerr(got[k], want[k]) <= 10 * RTOL
+
+
+def test_density_is_deterministic_and_order_independent():
+    """Fixed-point accumulation: bit-identical density for any particle order and on repeat."""
+    nm = normalise()
+    numx, n = 96, 200_000
+    rng = np.random.default_rng(5)
+    xl = numx * nm["dx"]
+    x, y = rng.random(n) * xl, rng.random(n) * xl
+    v = np.zeros(n)
+    outs = []
+    for trial in range(3):
+        perm = np.arange(n) if trial == 0 else rng.permutation(n)
+        with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n)) as sim:
+            sim.set_species(ION, x[perm], y[perm], v, v)
+            sim.scatterSpecies(ION)
+            outs.append(sim.grid("den_i"))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+def test_charge_conservation_large():
+    """Size-independent property at a BASELINE-scale grid: the deposited weights sum to N*spwt/dx^2."""
+    nm = normalise()
+    numx, n = 1024, 20_000_000
+    with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n)) as sim:
+        sim.fill_synthetic(ELECTRON, n, seed=11)
+        sim.scatterSpecies(ELECTRON)
+        den = sim.grid("den_e").reshape(numx + 1, numx + 1)
+        total = den[:-1, :-1].sum()            # unique periodic nodes after the fold
+        want = n * sim.p.spwt[1] / nm["dx"] ** 2
+        assert abs(total - want) <= 1e-12 * want
+        # the mover keeps every particle inside the box and conserves the count
+        sim.scatterSpecies(ION); sim.computeRho(); sim.solve(); sim.computeEF()
+        sim.pushSpecies(ELECTRON)
+        x, y, _, _ = sim.get_species(ELECTRON)
+        xl = numx * nm["dx"]
+        assert x.min() >= 0 and x.max() < xl and y.min() >= 0 and y.max() < xl
+
+
+def test_clear_density_extension_and_accumulate_default():
+    nm = normalise()
+    numx, n = 32, 5000
+    rng = np.random.default_rng(9)
+    xl = numx * nm["dx"]
+    x, y, v = rng.random(n) * xl, rng.random(n) * xl, np.zeros(n)
+    res = {}
+    for flags in (0, 1):
+        with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, flags=flags)) as sim:
+            sim.set_species(ION, x, y, v, v)
+            sim.scatterSpecies(ION); a = sim.grid("den_i")
+            sim.scatterSpecies(ION); b = sim.grid("den_i")
+            res[flags] = (a, b)
+    a, b = res[0]
+    assert b.reshape(numx + 1, -1)[1:-1, 1:-1].sum() > 1.99 * a.reshape(numx + 1, -1)[1:-1, 1:-1].sum()   # Q1: accumulates
+    a, b = res[1]
+    assert np.array_equal(a, b)
+
+
+def test_error_codes():
+    nm = normalise()
+    with Simulation(Params(16, 16, nm["dx"], nm["dt"], nm["mass_i"], 10, 10, solverType=2)) as sim:
+        with pytest.raises(picsp_b200.PicspError) as ei:
+            sim.scatterSpecies(2)
+        assert ei.value.code == -1
+        with pytest.raises(picsp_b200.PicspError):
+            sim.set_species(ION, *(np.zeros(11),) * 4)       # exceeds capacity
+        with pytest.raises(picsp_b200.PicspError) as ei:
+            sim.spectralPotentialSolver()                     # SOR context has no FFT plans
+        assert ei.value.code == -6
+    with pytest.raises(picsp_b200.PicspError):
+        Simulation(Params(16, 16, nm["dx"], nm["dt"], nm["mass_i"], 10, 10, solverType=3))
