@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the PICSP particle loop (deposit + solve + E field + gather/push).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): particle-steps/s over the full step, both species.
+Workload: BASELINE.json config "1024x1024 periodic spectral, 1e9 particles" (two-stream
+electrons + cold ions, synthetic Maxwellian state from the bench-only device loader); the
+1e9 particles are sharded across the N ranks by index range (strong scaling), the grid is
+replicated and the per-rank partial charge densities are summed with one NCCL all-reduce.
+
+One JSON line on stdout (rank 0).  `value` = particle-steps/s with the state resident in
+HBM, timed with CUDA events on the library's stream (max over ranks).  `e2e` = the same
+metric through the C ABI with HOST buffers: upload of the particle state from pinned host
+memory, one dump period (50 steps, the reference's diagnostic cadence, main.cpp:507) and the
+download of everything the reference dumps (phase space, den, phi).  `roofline` is for the
+dominant kernel (the mover fused with the next step's deposit): 64 algorithmic bytes per
+particle-step.  `cpu_baseline` / `--impl reference` time the UNMODIFIED reference
+translation unit (oracle/_ref) on one host core (the reference is single-threaded).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALGO_BYTES_PER_PARTICLE_STEP = 64   # read + write {x, y, vx, vy} f64, deposit fused into the mover
+METRIC = "particle_steps_per_sec"
+UNIT = "particle-steps/s"
+
+
+def physical_normalisation():
+    """The reference's normalisation (main.cpp:279-291) of its shipped physical values (input.ini)."""
+    EPS_un, K, EV_TO_K = 8.85418782e-12, 1.38065e-23, 11604.52
+    q, me, mi, n0, vthE, vthI, driftE = 1.602e-19, 9.109e-31, 1.673e-27, 1e12, 0.9, 0.026, 0.2
+    omega_pe = np.sqrt((q * q * n0) / (me * EPS_un))
+    lambda_d = np.sqrt((EPS_un * K * vthE * EV_TO_K) / (n0 * q * q))
+    return dict(dt=float(1e-10 * omega_pe), dx=float(1.2e-4 / lambda_d), mass_i=mi / me,
+                vth_i=vthI / vthE, vth_e=1.0, drift_e=driftE / vthE)
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        bits = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                0x80: "hw_power_brake_slowdown"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for b, name in bits.items():
+                    if r & b:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the UNMODIFIED reference TU on one host core
+# ------------------------------------------------------------------------------------------
+def run_reference_cpu(cells, n_per_species, steps, warmup):
+    """Times the reference's own loop body (main.cpp:481-504) on a bounded sample of the workload.
+
+    Returns (value, info).  value = particle-steps/s over deposit + rho + EF + push, i.e. the
+    reference's own functions; the Poisson solve is timed but reported separately because
+    FFTW3 is absent from this image and the shim FFT that stands in for it is not FFTW (at
+    the full workload the solve is <0.1% of the reference's step).  The dead velocity-moment
+    deposit the reference also runs every step (scatterSpeciesVel, outputs never consumed) is
+    timed and reported but NOT charged to the reference."""
+    from oracle import oracle as orc
+    nm = physical_normalisation()
+    kind = "reference" if orc.have_reference() else "port"
+    t0 = time.perf_counter()
+    if kind == "reference":
+        r = orc.Reference(cells, cells, nm["dx"], nm["dt"], nm["mass_i"], n_per_species, n_per_species,
+                          vth_i=nm["vth_i"], vth_e=nm["vth_e"], solver=1)
+        r.L.picsp_ref_set_fft_mode(3)
+        r.seed(0)
+        r.init_both(1)
+        r.bootstrap()
+        if warmup:
+            r.step(warmup, with_dead_vel=True)
+        r.phase_seconds(reset=True)
+        r.step(steps, with_dead_vel=True)
+        ph = r.phase_seconds(reset=True)
+        r.close()
+    else:
+        o = orc.Oracle(cells, cells, nm["dx"], nm["dt"], nm["mass_i"], n_per_species, n_per_species,
+                       vth_i=nm["vth_i"], vth_e=nm["vth_e"], solver=1)
+        orc.Oracle.lib().oracle_set_fft_mode(3)
+        o.seed(0); o.init(0, 1); o.init(1, 1)
+        o.bootstrap()
+        ph = dict(deposit=0.0, dead_vel_deposit=0.0, rho=0.0, solve=0.0, ef=0.0, push=0.0)
+
+        def timed(key, fn, *a):
+            t = time.perf_counter(); fn(*a); ph[key] += time.perf_counter() - t
+        for it in range(warmup + steps):
+            if it == warmup:
+                for k in ph:
+                    ph[k] = 0.0
+            timed("deposit", o.scatterSpecies, 0); timed("deposit", o.scatterSpecies, 1)
+            timed("rho", o.computeRho); timed("solve", o.solve); timed("ef", o.computeEF)
+            timed("push", o.pushSpecies, 0); timed("push", o.pushSpecies, 1)
+    path_s = ph["deposit"] + ph["rho"] + ph["ef"] + ph["push"]
+    psteps = 2.0 * n_per_species * steps
+    value = psteps / path_s
+    info = {
+        "value": value, "unit": UNIT, "cores": 1, "kind": kind,
+        "sample": (f"{cells}x{cells} cells, {n_per_species} particles/species (Maxwellian, reference loader seed 0), "
+                   f"{steps} steps after {warmup} warm-up, 1 of {os.cpu_count()} host cores (reference is single-threaded), "
+                   f"g++ -O2 (the reference's own makefile uses -O0, ~3x slower); value counts deposit+rho+EF+push; "
+                   f"per-step seconds: deposit {ph['deposit'] / steps:.3f}, push {ph['push'] / steps:.3f}, "
+                   f"rho+EF {(ph['rho'] + ph['ef']) / steps:.4f}; excluded: Poisson solve {ph['solve'] / steps:.3f} s/step "
+                   f"(shim FFT, not FFTW) and the reference's dead velocity deposit {ph['dead_vel_deposit'] / steps:.3f} s/step"),
+        "ms_per_step": 1e3 * path_s / steps, "wall_s": time.perf_counter() - t0,
+    }
+    return value, info
+
+
+def main_reference(args, rank):
+    if rank != 0:
+        return 0
+    value, info = run_reference_cpu(args.cells, args.cpu_particles, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, None),
+        "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, n_local):
+    cfg = {
+        "workload": (f"two-stream electrons + cold ions, {args.cells}x{args.cells} cells periodic "
+                     f"({args.cells + 1}^2 nodes), spectral solver, {args.particles:.3g} particles total "
+                     f"({args.particles // 2} per species), BASELINE.json configs[3]"),
+        "cells": args.cells, "particles_total": int(args.particles), "solver": "spectral (cuFFT D2Z/Z2D)",
+        "sharding": f"particles by index range over {args.gpus} rank(s), grid replicated, 1 NCCL all-reduce of rho per step",
+        "l2_policy": "inputs exceed L2 (particle state per rank >> 126 MB); no explicit flush",
+    }
+    if n_local is not None:
+        cfg["particles_per_rank_per_species"] = int(n_local)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def main_ours(args, rank, world, local_rank):
+    import torch
+    from picsp_b200 import ELECTRON, ION, Params, Simulation
+    from picsp_b200.sim import shard_range
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: picsp_b200 has no CPU path"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    nm = physical_normalisation()
+    n_species = int(args.particles) // 2
+    lo, hi = shard_range(n_species, rank, world)
+    n_local = hi - lo
+    sim = Simulation(Params(args.cells, args.cells, nm["dx"], nm["dt"], nm["mass_i"], n_species, n_species,
+                            solverType=1, device=local_rank, capacity=(n_local, n_local)))
+    sim.fill_synthetic(ION, n_local, first_index=lo, seed=1, vth=nm["vth_i"], xdrift=0.0)
+    sim.fill_synthetic(ELECTRON, n_local, first_index=lo, seed=2, vth=nm["vth_e"], xdrift=nm["drift_e"])
+    if world > 1:
+        uid = [Simulation.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        sim.comm_attach(uid[0], rank, world)
+    sim.bootstrap()
+    sim.profile_enable(True)
+    sim.step(args.warmup)
+    sim.sync()
+    sim.profile_reset()
+
+    sampler = ClockSampler(local_rank)
+    launches0 = sim.kernel_launches()
+    barrier()
+    sampler.start()
+    t_wall = time.perf_counter()
+    sim.step(args.steps)
+    sim.sync()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.result()
+    launches = sim.kernel_launches() - launches0
+    prof = sim.profile()
+    ms_total = max_over_ranks(prof["step"][0])
+    ms_per_step = ms_total / args.steps
+    value = float(args.particles) * args.steps / (ms_total * 1e-3)
+
+    # roofline of the dominant kernel (fused mover+deposit): per-launch average over the timed region
+    push_ms, push_calls = prof["push"]
+    peak, peak_src = measured_peak_gbs()
+    per_launch_s = push_ms * 1e-3 / max(push_calls, 1)
+    achieved = ALGO_BYTES_PER_PARTICLE_STEP * n_local / per_launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": args.traffic_bytes_per_launch,
+                "kernel": "k_push<fused> (leapfrog mover + CIC gather + next-step CIC deposit)",
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE_STEP * n_local,
+                "avg_launch_ms": per_launch_s * 1e3, "launches_timed": push_calls, "peak_source": peak_src,
+                "share_of_step": push_ms / prof["step"][0] if prof["step"][0] else None}
+    phases_ms = {k: v[0] / args.steps for k, v in prof.items()}
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(sim, args, n_local, barrier, max_over_ranks, torch)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _, info = run_reference_cpu(args.cells, args.cpu_particles, 2, 1)
+        cpu_baseline = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    sim.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_local),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "phases_ms_per_step": phases_ms, "wall_ms_per_step": 1e3 * t_wall / args.steps,
+        }
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_e2e(sim, args, n_local, barrier, max_over_ranks, torch):
+    """Upload the particle state from pinned host memory, run one dump period, read back what the
+    reference dumps (phase space of both species, den.i, den.e, phi) — all through the C ABI."""
+    import ctypes as C
+    from picsp_b200.lib import check
+    dp = C.POINTER(C.c_double)
+    nn = sim.nix * sim.niy
+    pinned = True
+    try:
+        host = [[torch.empty(n_local, dtype=torch.float64, pin_memory=True) for _ in range(4)] for _ in range(2)]
+        grids = [torch.empty(nn, dtype=torch.float64, pin_memory=True) for _ in range(3)]
+    except RuntimeError:
+        pinned = False
+        host = [[torch.empty(n_local, dtype=torch.float64) for _ in range(4)] for _ in range(2)]
+        grids = [torch.empty(nn, dtype=torch.float64) for _ in range(3)]
+    ptr = lambda t: C.cast(t.data_ptr(), dp)  # noqa: E731
+    for s in range(2):   # untimed: seed the host buffers with the current device state
+        check(sim.L.picsp_species_download(sim.ctx, s, *(ptr(t) for t in host[s])))
+    steps = args.e2e_steps
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(2):
+        check(sim.L.picsp_species_upload(sim.ctx, s, *(ptr(t) for t in host[s]), n_local))
+    check(sim.L.picsp_step(sim.ctx, steps))
+    for s in range(2):
+        check(sim.L.picsp_species_download(sim.ctx, s, *(ptr(t) for t in host[s])))
+    for gid, t in zip((0, 1, 3), grids):
+        check(sim.L.picsp_grid_download(sim.ctx, gid, ptr(t)))
+    ke = [sim.computeKE(0), sim.computeKE(1)]
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    h2d = 2 * 4 * 8 * n_local
+    d2h = 2 * 4 * 8 * n_local + 3 * 8 * nn + 16
+    return {"value": float(args.particles) * steps / dt, "unit": UNIT,
+            "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps,
+            "steps_per_call": steps, "seconds": dt, "pinned_host_memory": pinned,
+            "what": "picsp_species_upload x2 -> picsp_step(50) -> picsp_species_download x2 + den.i, den.e, phi + KE "
+                    "(bytes are per rank, amortised over the dump period)", "ke_finite": bool(np.isfinite(ke).all())}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--cells", type=int, default=1024)
+    ap.add_argument("--particles", type=float, default=1e9, help="total particles (both species, all ranks)")
+    ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-particles", type=int, default=4_000_000, help="particles/species of the CPU sample")
+    ap.add_argument("--traffic-bytes-per-launch", type=float, default=None,
+                    help="dram bytes per launch of the dominant kernel from the committed ncu --set full capture")
+    args = ap.parse_args()
+    args.particles = int(args.particles)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return main_reference(args, rank)
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            # convenience: re-launch under torchrun
+            import subprocess
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+            return subprocess.call(cmd)
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    return main_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -143,7 +143,8 @@ enum {
     PICSP_PHASE_EF = 4,
     PICSP_PHASE_PUSH = 5,      /* the mover (fused with the next deposit unless NO_FUSE) */
     PICSP_PHASE_SORT = 6,
-    PICSP_PHASE_COUNT = 7
+    PICSP_PHASE_STEP = 7,      /* one whole picsp_step() call, first launch to last */
+    PICSP_PHASE_COUNT = 8
 };
 int picsp_profile_enable(picsp_ctx *ctx, int on);                       /* CUDA events around every phase on the library's stream */
 int picsp_profile_get(picsp_ctx *ctx, int phase, double *ms, int64_t *calls); /* synchronises; accumulates since last reset */

@@ -524,13 +524,13 @@ int picsp_step(picsp_ctx *c, int nsteps) {   // src/main.cpp:481-504
     check_ctx(c);
     PICSP_REQUIRE(nsteps >= 0, PICSP_ERR_INVALID, "negative step count");
     PICSP_CUDA(cudaSetDevice(c->prm.device));
+    PhaseScope whole(c, PICSP_PHASE_STEP);
     for (int it = 0; it < nsteps; it++) {
         op_deposit(c, 0); op_deposit(c, 1);
         op_compute_rho(c);
         op_solve(c);
         op_compute_ef(c);
         op_push(c, 0); op_push(c, 1);
-        if (c->profiling && c->timers[PICSP_PHASE_PUSH].used > 2048) profile_collect(c);
     }
     PICSP_API_END
 }
