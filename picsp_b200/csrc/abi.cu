@@ -12,6 +12,7 @@
 #include "ctx.cuh"
 #include "grid_kernels.cuh"
 #include "particle_kernels.cuh"
+#include "tile_kernels.cuh"
 
 using namespace picsp;
 
@@ -78,9 +79,74 @@ void ensure_hist(picsp_ctx *c, int s) {
         PICSP_LAUNCH(c, k_tile_hist, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, (long long)sp.n, push_const(c, s), sp.hist);
     sp.hist_valid = true;
 }
+bool tiled(const picsp_ctx *c) { return !(c->prm.flags & PICSP_FLAG_NO_SORT); }
+
 void compute_frac(picsp_ctx *c, int s) {
     Species &sp = c->sp[s];
-    PICSP_LAUNCH(c, k_frac_from_hist, 1, 1024, 0, sp.hist, c->g.ntx, c->g.nty, sp.frac);
+    // the shared-memory limbs of the tiled path carry at most MAX_FRAC_TILED fraction bits
+    PICSP_LAUNCH(c, k_frac_from_hist, 1, 1024, 0, sp.hist, c->g.ntx, c->g.nty, sp.frac, tiled(c) ? MAX_FRAC_TILED : 60);
+}
+
+// -- tile binning -------------------------------------------------------------------------
+void op_sort(picsp_ctx *c, int s) {
+    PhaseScope ph(c, PICSP_PHASE_SORT);
+    Species &sp = c->sp[s];
+    const Geom &g = c->g;
+    const int nt = g.ntx * g.nty;
+    ensure_hist(c, s);
+    PICSP_LAUNCH(c, k_scan_tiles, 1, 1024, 0, sp.hist, nt, sp.tile_off, (Chunk *)sp.chunks, sp.nchunks, sp.cursor);
+    if (!sp.x2) {
+        dalloc(&sp.x2, sp.cap); dalloc(&sp.y2, sp.cap); dalloc(&sp.vx2, sp.cap); dalloc(&sp.vy2, sp.cap);
+        dalloc(&sp.id, sp.cap); dalloc(&sp.id2, sp.cap);
+    }
+    if (sp.n > 0)
+        PICSP_LAUNCH(c, k_sort_scatter, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy,
+                     sp.has_perm ? sp.id : (const uint32_t *)nullptr, (long long)sp.n, push_const(c, s), sp.tile_off,
+                     sp.cursor, sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2);
+    std::swap(sp.x, sp.x2); std::swap(sp.y, sp.y2); std::swap(sp.vx, sp.vx2); std::swap(sp.vy, sp.vy2);
+    std::swap(sp.id, sp.id2);
+    sp.has_perm = true; sp.sorted = true; sp.steps_since_sort = 0;
+}
+
+int mover_grid(const Species &sp) {
+    long long b = sp.n / CHUNK + sp.max_chunks - sp.cap / CHUNK;   // n/CHUNK + ntiles + 1 (upper bound on chunks)
+    return (int)std::max<long long>(1, b);
+}
+
+template <int MODE> void launch_tile_mover(picsp_ctx *c, int s) {
+    Species &sp = c->sp[s];
+    CUtensorMap tm;
+    memcpy(&tm, c->tmapE, sizeof(tm));
+    PICSP_LAUNCH(c, (k_tile_mover<MODE>), mover_grid(sp), MOVER_THREADS, 0, tm, sp.x, sp.y, sp.vx, sp.vy,
+                 (const Chunk *)sp.chunks, sp.nchunks, push_const(c, s), c->E, sp.acc, sp.frac, sp.hist_next,
+                 sp.counters, c->d_error);
+}
+
+// -- TMA descriptor of the E field -------------------------------------------------------
+// E is [nix][niy] of {efx, efy}; seen by TMA as a 2-D tensor of doubles, inner extent 2*niy.
+// The encoder lives in libcuda; it is fetched through the runtime so that the library has
+// no link-time dependency on the driver (it must load on a box without one).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+void make_tensor_map(picsp_ctx *c) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PICSP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    PICSP_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, PICSP_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+    const Geom &g = c->g;
+    cuuint64_t dims[2] = {(cuuint64_t)(2 * g.niy), (cuuint64_t)g.nix};
+    cuuint64_t strides[1] = {(cuuint64_t)(2 * g.niy) * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)(2 * WIN), (cuuint32_t)WIN};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap tm;
+    CUresult r = ((EncodeTiledFn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)c->E, dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PICSP_REQUIRE(r == CUDA_SUCCESS, PICSP_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+    memcpy(c->tmapE, &tm, sizeof(tm));
+    c->have_tmap = true;
 }
 
 // -- operations ---------------------------------------------------------------------
@@ -89,11 +155,17 @@ void op_deposit(picsp_ctx *c, int s) {
     Species &sp = c->sp[s];
     const Geom &g = c->g;
     if (!sp.acc_valid) {
+        if (tiled(c) && !sp.sorted) op_sort(c, s);
         ensure_hist(c, s);
         compute_frac(c, s);
-        if (sp.n > 0)
-            PICSP_LAUNCH(c, k_deposit, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, (long long)sp.n,
-                         push_const(c, s), sp.acc, sp.frac);
+        PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
+        if (sp.n > 0) {
+            if (tiled(c))
+                launch_tile_mover<1>(c, s);
+            else
+                PICSP_LAUNCH(c, k_deposit, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, (long long)sp.n,
+                             push_const(c, s), sp.acc, sp.frac);
+        }
     }
     const double weight = sp.spwt / (g.dx * g.dx);   // value/dxdy, src/main.cpp:657,664
     const int clear = (c->prm.flags & PICSP_FLAG_CLEAR_DENSITY) ? 1 : 0;
@@ -149,35 +221,37 @@ void op_compute_ef(picsp_ctx *c) {
 void op_push(picsp_ctx *c, int s) {
     Species &sp = c->sp[s];
     const bool fuse = !(c->prm.flags & PICSP_FLAG_NO_FUSE);
-    if (fuse) {
-        ensure_hist(c, s);           // histogram of the positions about to be pushed -> bound for acc
-        compute_frac(c, s);
-    }
+    const bool tile = tiled(c);
+    if (tile && (!sp.sorted || sp.steps_since_sort >= sp.sort_period)) op_sort(c, s);
+    if (fuse || tile) ensure_hist(c, s);   // histogram of the positions about to be pushed -> bound for acc
+    if (fuse) compute_frac(c, s);
     PhaseScope ph(c, PICSP_PHASE_PUSH);
-    PICSP_CUDA(cudaMemsetAsync(sp.repush, 0, sizeof(unsigned long long), c->stream));
+    PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
     const int nt = c->g.ntx * c->g.nty;
-    if (fuse) {
-        PICSP_CUDA(cudaMemsetAsync(sp.hist_next, 0, sizeof(unsigned int) * nt, c->stream));
-        if (sp.acc_valid)   // a previous fused push was never consumed by a deposit: drop it
-            PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
-    }
+    if (fuse || tile) PICSP_CUDA(cudaMemsetAsync(sp.hist_next, 0, sizeof(unsigned int) * nt, c->stream));
+    if (fuse && sp.acc_valid)   // a previous fused push was never consumed by a deposit: drop it
+        PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
     if (sp.n > 0) {
-        const int blocks = particle_blocks(c, sp.n, 256);
-        if (fuse)
-            PICSP_LAUNCH(c, (k_push<true>), blocks, 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n, push_const(c, s),
-                         c->E, sp.acc, sp.frac, sp.hist_next, sp.repush, c->d_error);
-        else
-            PICSP_LAUNCH(c, (k_push<false>), blocks, 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n, push_const(c, s),
-                         c->E, sp.acc, sp.frac, sp.hist_next, sp.repush, c->d_error);
+        if (tile) {
+            if (fuse) launch_tile_mover<0>(c, s); else launch_tile_mover<2>(c, s);
+        } else {
+            const int blocks = particle_blocks(c, sp.n, 256);
+            if (fuse)
+                PICSP_LAUNCH(c, (k_push<true>), blocks, 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n, push_const(c, s),
+                             c->E, sp.acc, sp.frac, sp.hist_next, sp.counters, c->d_error);
+            else
+                PICSP_LAUNCH(c, (k_push<false>), blocks, 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n, push_const(c, s),
+                             c->E, sp.acc, sp.frac, sp.hist_next, sp.counters, c->d_error);
+        }
     }
-    if (fuse) {
+    if (fuse || tile) {
         std::swap(sp.hist, sp.hist_next);
         sp.hist_valid = true;
-        sp.acc_valid = true;
     } else {
         sp.hist_valid = false;
-        sp.acc_valid = false;
     }
+    sp.acc_valid = fuse;
+    sp.steps_since_sort++;
 }
 
 void op_rewind(picsp_ctx *c, int s) {
@@ -287,11 +361,18 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
             dalloc(&sp.x, sp.cap); dalloc(&sp.y, sp.cap); dalloc(&sp.vx, sp.cap); dalloc(&sp.vy, sp.cap);
             dalloc(&sp.den, g.nn); dalloc(&sp.acc, g.nn); dalloc(&sp.frac, 1);
             dalloc(&sp.hist, (size_t)g.ntx * g.nty); dalloc(&sp.hist_next, (size_t)g.ntx * g.nty);
-            dalloc(&sp.repush, 1);
+            dalloc(&sp.counters, 2);
+            sp.sort_period = (s == 0) ? 64 : 8;
+            sp.max_chunks = sp.cap / CHUNK + (long long)g.ntx * g.nty + 1;
+            dalloc(&sp.tile_off, (size_t)g.ntx * g.nty + 1);
+            dalloc((Chunk **)&sp.chunks, (size_t)sp.max_chunks);
+            dalloc(&sp.nchunks, 1);
+            dalloc(&sp.cursor, (size_t)g.ntx * g.nty);
+            PICSP_CUDA(cudaMemsetAsync(sp.nchunks, 0, sizeof(int), c->stream));
             PICSP_CUDA(cudaMemsetAsync(sp.den, 0, sizeof(double) * g.nn, c->stream));      // src/main.cpp:427,431
             PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * g.nn, c->stream));
             PICSP_CUDA(cudaMemsetAsync(sp.frac, 0, sizeof(int), c->stream));
-            PICSP_CUDA(cudaMemsetAsync(sp.repush, 0, sizeof(unsigned long long), c->stream));
+            PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
         }
         dalloc(&c->rho, g.nn); dalloc(&c->phi, g.nn);
         dalloc(&c->E_alloc, (size_t)(g.nn + 2 * g.guard));
@@ -299,6 +380,7 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
         PICSP_CUDA(cudaMemsetAsync(c->rho, 0, sizeof(double) * g.nn, c->stream));          // src/main.cpp:392-395
         PICSP_CUDA(cudaMemsetAsync(c->phi, 0, sizeof(double) * g.nn, c->stream));
         PICSP_CUDA(cudaMemsetAsync(c->E_alloc, 0, sizeof(double2) * (g.nn + 2 * g.guard), c->stream));
+        make_tensor_map(c);
         dalloc(&c->d_red, RED_BLOCKS); dalloc(&c->d_scalars, 8); dalloc(&c->d_sor_status, 2); dalloc(&c->d_error, 1);
         PICSP_CUDA(cudaMemsetAsync(c->d_scalars, 0, sizeof(double) * 8, c->stream));
         PICSP_CUDA(cudaMemsetAsync(c->d_sor_status, 0, sizeof(long long) * 2, c->stream));
@@ -335,7 +417,9 @@ void picsp_destroy(picsp_ctx *c) {
     for (int s = 0; s < 2; s++) {
         Species &sp = c->sp[s];
         cudaFree(sp.x); cudaFree(sp.y); cudaFree(sp.vx); cudaFree(sp.vy); cudaFree(sp.id);
-        cudaFree(sp.den); cudaFree(sp.acc); cudaFree(sp.frac); cudaFree(sp.hist); cudaFree(sp.hist_next); cudaFree(sp.repush);
+        cudaFree(sp.den); cudaFree(sp.acc); cudaFree(sp.frac); cudaFree(sp.hist); cudaFree(sp.hist_next); cudaFree(sp.counters);
+        cudaFree(sp.x2); cudaFree(sp.y2); cudaFree(sp.vx2); cudaFree(sp.vy2); cudaFree(sp.id2);
+        cudaFree(sp.tile_off); cudaFree(sp.chunks); cudaFree(sp.nchunks); cudaFree(sp.cursor);
     }
     cudaFree(c->rho); cudaFree(c->phi); cudaFree(c->E_alloc); cudaFree(c->rhok); cudaFree(c->phik);
     cudaFree(c->d_red); cudaFree(c->d_scalars); cudaFree(c->d_sor_status); cudaFree(c->d_error); cudaFree(c->stage);
@@ -369,7 +453,7 @@ int picsp_species_upload(picsp_ctx *c, int s, const double *x, const double *y, 
     if (sp.acc_valid) PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
     PICSP_CUDA(cudaStreamSynchronize(c->stream));
     sp.n = n; sp.hist_valid = false; sp.acc_valid = false;
-    if (sp.id) { cudaFree(sp.id); sp.id = nullptr; }
+    sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0;
     PICSP_API_END
 }
 
@@ -390,7 +474,7 @@ int picsp_species_download(picsp_ctx *c, int s, double *x, double *y, double *vx
     double *dst[4] = {x, y, vx, vy};
     for (int k = 0; k < 4; k++) {
         if (!dst[k] || sp.n == 0) continue;
-        if (sp.id) {
+        if (sp.has_perm) {
             ensure_stage(c, sp.n);
             PICSP_LAUNCH(c, k_unpermute, particle_blocks(c, sp.n, 256), 256, 0, src[k], sp.id, c->stage, (long long)sp.n);
             PICSP_CUDA(cudaMemcpyAsync(dst[k], c->stage, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -571,9 +655,28 @@ int picsp_repush_count(picsp_ctx *c, int s, int64_t *n) {
     PICSP_REQUIRE(n != nullptr, PICSP_ERR_INVALID, "null output");
     PICSP_CUDA(cudaSetDevice(c->prm.device));
     unsigned long long *h = reinterpret_cast<unsigned long long *>(c->h_pinned + 24);
-    PICSP_CUDA(cudaMemcpyAsync(h, c->sp[s].repush, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    PICSP_CUDA(cudaMemcpyAsync(h, c->sp[s].counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     PICSP_CUDA(cudaStreamSynchronize(c->stream));
     *n = (int64_t)*h;
+    PICSP_API_END
+}
+
+int picsp_straggler_count(picsp_ctx *c, int s, int64_t *n) {
+    PICSP_API_BEGIN
+    check_ctx(c); check_species(s);
+    PICSP_REQUIRE(n != nullptr, PICSP_ERR_INVALID, "null output");
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    unsigned long long *h = reinterpret_cast<unsigned long long *>(c->h_pinned + 24);
+    PICSP_CUDA(cudaMemcpyAsync(h, c->sp[s].counters + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    PICSP_CUDA(cudaStreamSynchronize(c->stream));
+    *n = (int64_t)*h;
+    PICSP_API_END
+}
+
+int picsp_set_sort_period(picsp_ctx *c, int s, int period) {
+    PICSP_API_BEGIN
+    check_ctx(c); check_species(s);
+    c->sp[s].sort_period = period > 0 ? period : (s == 0 ? 64 : 8);
     PICSP_API_END
 }
 
@@ -613,7 +716,7 @@ int picsp_species_fill_synthetic(picsp_ctx *c, int s, int64_t n, int64_t first_i
                      (long long)first_index, seed, c->g.xl, c->g.yl, vth, xdrift);
     if (sp.acc_valid) PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
     sp.n = n; sp.hist_valid = false; sp.acc_valid = false;
-    if (sp.id) { cudaFree(sp.id); sp.id = nullptr; }
+    sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0;
     PICSP_CUDA(cudaStreamSynchronize(c->stream));
     PICSP_API_END
 }

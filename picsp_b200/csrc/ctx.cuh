@@ -74,7 +74,20 @@ struct Species {
     unsigned int *hist_next = nullptr; // filled by the mover for the positions it writes
     bool hist_valid = false;
     bool acc_valid = false;        // acc holds the deposit of the stored positions (filled by the fused mover)
-    unsigned long long *repush = nullptr; // device counter of extra pushes in the last push
+    unsigned long long *counters = nullptr; // device: [0] extra pushes of the last push, [1] out-of-window deposits
+
+    // tile binning (fast path)
+    double *x2 = nullptr, *y2 = nullptr, *vx2 = nullptr, *vy2 = nullptr;   // sort destination (lazily allocated)
+    uint32_t *id2 = nullptr;
+    bool has_perm = false;         // id[] holds a permutation (otherwise identity)
+    bool sorted = false;           // particles are binned by tile and chunks/tile_off describe them
+    int steps_since_sort = 0;
+    int sort_period = 8;
+    long long *tile_off = nullptr; // ntiles+1
+    void *chunks = nullptr;        // picsp::Chunk[max_chunks]
+    int *nchunks = nullptr;        // device scalar
+    unsigned int *cursor = nullptr;// ntiles
+    long long max_chunks = 0;
 };
 
 struct PhaseTimer {
@@ -104,6 +117,10 @@ struct picsp_ctx {
     long long *d_sor_status = nullptr;
     int *d_error = nullptr;         // sticky device-side error flag
     double *h_pinned = nullptr;     // small pinned staging for scalar read-backs
+
+    // TMA descriptor of E viewed as [nix][2*niy] doubles (128 bytes, CUtensorMap)
+    alignas(64) unsigned char tmapE[128];
+    bool have_tmap = false;
 
     // staging for un-permuted downloads
     double *stage = nullptr; int64_t stage_cap = 0;

@@ -55,12 +55,41 @@ __device__ __forceinline__ double2 gather_E(const double2 *__restrict__ E, const
     return e;
 }
 
+// x/dx without the division sequence: one multiply by the rounded reciprocal and one
+// Newton correction (error <= 1 ulp of the quotient; CIC weights are continuous across a
+// cell boundary, so an index that differs by one at an exact boundary gives the same sums).
+__device__ __forceinline__ double to_logical_fast(double pos, double dx, double inv_dx) {
+    double q = pos * inv_dx;
+    double r = fma(-q, dx, pos);
+    return fma(r, inv_dx, q);
+}
+
+// floor of a non-negative double < 2^31 without a conversion instruction:
+// l + 2^52 rounded toward zero leaves floor(l) in the low mantissa bits.
+__device__ __forceinline__ int floor_nonneg(double l, double &fl) {
+    const double magic = 4503599627370496.0;   // 2^52
+    double t = __dadd_rz(l, magic);
+    fl = t - magic;
+    return __double2loint(t);
+}
+
+__device__ __forceinline__ bool in_box(double px, double py, const PushConst &c) {
+    return px >= 0.0 && px < c.xl && py >= 0.0 && py < c.yl;
+}
+
+// Bin of a position.  ONE definition shared by the histogram, the sort and the mover, so
+// that bin populations and bin contents always agree bit for bit.  Positions outside the
+// box (only possible for caller-supplied garbage; the mover keeps particles inside) go to bin 0.
+__device__ __forceinline__ int tile_of_cell(int ci, int cj, const PushConst &c) {
+    return min(ci / TILE, c.ntx - 1) * c.nty + min(cj / TILE, c.nty - 1);
+}
 __device__ __forceinline__ int tile_of(double x, double y, const PushConst &c) {
-    int ci = __double2int_rz(to_logical(x, c.dx)), cj = __double2int_rz(to_logical(y, c.dx));
-    int tx = ci / TILE, ty = cj / TILE;
-    tx = tx < 0 ? 0 : (tx >= c.ntx ? c.ntx - 1 : tx);
-    ty = ty < 0 ? 0 : (ty >= c.nty ? c.nty - 1 : ty);
-    return tx * c.nty + ty;
+    if (!in_box(x, y, c)) return 0;
+    const double inv_dx = 1.0 / c.dx;
+    double fi, fj;
+    int ci = floor_nonneg(to_logical_fast(x, c.dx, inv_dx), fi);
+    int cj = floor_nonneg(to_logical_fast(y, c.dx, inv_dx), fj);
+    return tile_of_cell(ci, cj, c);
 }
 
 // ---------------------------------------------------------------------------
@@ -95,7 +124,7 @@ __global__ void k_tile_hist(const double *__restrict__ x, const double *__restri
 // fused mover deposits positions one step after the histogram was taken, and a
 // particle may move by at most one tile per step (checked by the mover), so the
 // 5x5 neighbourhood bounds every node sum by pop * 2^frac < 2^62.
-__global__ void k_frac_from_hist(const unsigned int *__restrict__ hist, int ntx, int nty, int *__restrict__ frac) {
+__global__ void k_frac_from_hist(const unsigned int *__restrict__ hist, int ntx, int nty, int *__restrict__ frac, int cap) {
     __shared__ unsigned long long s_max[32];
     unsigned long long m = 0;
     int wx = ntx < 5 ? ntx : 5, wy = nty < 5 ? nty : 5;
@@ -116,7 +145,7 @@ __global__ void k_frac_from_hist(const unsigned int *__restrict__ hist, int ntx,
         for (int w = 0; w < (blockDim.x + 31) / 32; w++) m = s_max[w] > m ? s_max[w] : m;
         int bits = 64 - __clzll((long long)(m | 1ull));
         int f = 62 - bits;
-        *frac = f > 60 ? 60 : (f < 0 ? 0 : f);
+        *frac = f > cap ? cap : (f < 0 ? 0 : f);
     }
 }
 
@@ -148,7 +177,7 @@ __global__ void __launch_bounds__(256)
 k_push(double *__restrict__ x, double *__restrict__ y, double *__restrict__ vx, double *__restrict__ vy,
        long long n, PushConst c, const double2 *__restrict__ E, long long *__restrict__ acc,
        const int *__restrict__ frac, unsigned int *__restrict__ hist_next,
-       unsigned long long *__restrict__ repush, int *__restrict__ err) {
+       unsigned long long *__restrict__ counters, int *__restrict__ err) {
     const double scale = FUSE_DEPOSIT ? exp2((double)*frac) : 0.0;
     unsigned int extra = 0;
     for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
@@ -182,7 +211,7 @@ k_push(double *__restrict__ x, double *__restrict__ y, double *__restrict__ vx, 
         }
     }
     for (int o = 16; o > 0; o >>= 1) extra += __shfl_xor_sync(0xffffffffu, extra, o);
-    if ((threadIdx.x & 31) == 0 && extra) atomicAdd(repush, (unsigned long long)extra);
+    if ((threadIdx.x & 31) == 0 && extra) atomicAdd(&counters[0], (unsigned long long)extra);
 }
 
 // rewindSpecies, src/main.cpp:850-866 (no move, no wrap)

@@ -1,0 +1,351 @@
+// picsp_b200/csrc/tile_kernels.cuh — the tile-binned fast path of the particle loop.
+//
+// Particles are kept binned by TILE x TILE-cell tile (periodic counting sort, every few
+// steps).  One CTA processes one CHUNK (<= 2048 consecutive particles of one bin):
+//   * the E field of the tile plus a HALO-cell ring is staged in shared memory by ONE TMA
+//     tensor copy (cp.async.bulk.tensor.2d, zero-filled outside the grid),
+//   * the mover (pushSpecies + gather, src/main.cpp:772-847, :671-681) gathers from that
+//     window, writes the particle back in place (32 B read + 32 B written),
+//   * the next step's CIC deposit (scatterSpecies, src/main.cpp:684-700) of the position just
+//     written goes into a shared-memory window of FIXED-POINT accumulators held as two
+//     32-bit limbs, so that every update is one native 32-bit shared atomic (64-bit shared
+//     atomics are CAS loops on sm_100a) and needs no carry: a limb receives at most
+//     CHUNK = 2^11 addends of < 2^21, which cannot overflow 32 bits,
+//   * the window is flushed to the global int64 accumulator grid with native 64-bit
+//     integer REDs.  Integer addition commutes, so the density is bit-identical for any
+//     particle order, chunking or launch order.
+// Particles that drifted out of their bin's window since the last sort ("stragglers"), or
+// that wrap through the periodic boundary, take the global path (same arithmetic).
+#pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched at run time)
+
+#include "ctx.cuh"
+#include "particle_kernels.cuh"
+
+namespace picsp {
+
+constexpr int HALO = 4;                       // cells of drift a window tolerates on each side
+constexpr int WIN = TILE + 1 + 2 * HALO;      // window edge in nodes (25)
+constexpr int CHUNK = 2048;                   // particles per CTA work item
+constexpr int LIMB_BITS = 21;                 // 32 - log2(CHUNK)
+constexpr int MAX_FRAC_TILED = 2 * LIMB_BITS; // fraction bits the two limbs can carry (42)
+constexpr int MOVER_THREADS = 256;
+
+struct __align__(16) Chunk {
+    long long start;   // first particle (index into the species arrays)
+    int count;         // <= CHUNK
+    int tile;          // bin (tx * nty + ty)
+};
+
+// ---------------------------------------------------------------------------
+// binning: exclusive scan of the tile histogram -> tile offsets + chunk table
+// (single CTA; ntiles <= 128*128)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+k_scan_tiles(const unsigned int *__restrict__ hist, int ntiles, long long *__restrict__ tile_off,
+             Chunk *__restrict__ chunks, int *__restrict__ nchunks, unsigned int *__restrict__ cursor) {
+    __shared__ long long s_part[1024];
+    __shared__ int s_chunk[1024];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int per = (ntiles + nt - 1) / nt;
+    const int lo = tid * per, hi = min(lo + per, ntiles);
+    long long sum = 0; int csum = 0;
+    for (int t = lo; t < hi; t++) { unsigned int h = hist[t]; sum += h; csum += (int)((h + CHUNK - 1) / CHUNK); }
+    s_part[tid] = sum; s_chunk[tid] = csum;
+    __syncthreads();
+    if (tid == 0) {
+        long long a = 0; int b = 0;
+        for (int k = 0; k < nt; k++) { long long v = s_part[k]; int w = s_chunk[k]; s_part[k] = a; s_chunk[k] = b; a += v; b += w; }
+        tile_off[ntiles] = a;
+        *nchunks = b;
+    }
+    __syncthreads();
+    long long off = s_part[tid]; int coff = s_chunk[tid];
+    for (int t = lo; t < hi; t++) {
+        unsigned int h = hist[t];
+        tile_off[t] = off;
+        cursor[t] = 0u;
+        for (unsigned int done = 0; done < h; done += CHUNK) {
+            Chunk ck; ck.start = off + done; ck.count = (int)min((unsigned int)CHUNK, h - done); ck.tile = t;
+            chunks[coff++] = ck;
+        }
+        off += h;
+    }
+}
+
+// out-of-place scatter into the bins.  Slots inside a bin are handed out by an atomic
+// cursor (warp-aggregated per destination tile), so the order inside a bin is arbitrary —
+// harmless: the mover is per-particle and the deposit is order-independent.
+__global__ void __launch_bounds__(256)
+k_sort_scatter(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ vx,
+               const double *__restrict__ vy, const uint32_t *__restrict__ id, long long n, PushConst c,
+               const long long *__restrict__ tile_off, unsigned int *__restrict__ cursor,
+               double *__restrict__ x2, double *__restrict__ y2, double *__restrict__ vx2, double *__restrict__ vy2,
+               uint32_t *__restrict__ id2) {
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = blockIdx.x * (long long)blockDim.x + threadIdx.x - lane; base < n; base += stride) {
+        const long long p = base + lane;
+        const bool live = p < n;
+        double px = 0, py = 0;
+        int t = -1;
+        if (live) { px = x[p]; py = y[p]; t = tile_of(px, py, c); }
+        const unsigned int peers = __match_any_sync(0xffffffffu, t);
+        const int leader = __ffs(peers) - 1;
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        unsigned int first = 0;
+        if (live && lane == leader) first = atomicAdd(&cursor[t], (unsigned int)__popc(peers));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        if (live) {
+            const long long dst = tile_off[t] + first + rank;
+            x2[dst] = px; y2[dst] = py; vx2[dst] = vx[p]; vy2[dst] = vy[p];
+            id2[dst] = id ? id[p] : (uint32_t)p;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA tensor load
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 2-D tiled TMA load: box (c0 fastest, c1) of the tensor described by tmap -> dst, completes on bar
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, int c0, int c1, unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+struct TileCtx {
+    int wx0, wy0;        // window origin (node indices, may be negative)
+    int ilo, jlo;        // cells whose four nodes lie inside window AND grid: [ilo, ilo+ispan] x [jlo, jlo+jspan]
+    unsigned ispan, jspan;
+};
+
+// mover body for one particle (pushSpecies, src/main.cpp:779-846); returns the number of extra pushes
+__device__ __forceinline__ int push_one(double &px, double &py, double &pvx, double &pvy, const PushConst &c,
+                                        double inv_dx, const TileCtx &tc, const double2 *sE,
+                                        const double2 *__restrict__ E, int *err) {
+    int extra = 0;
+    for (int iter = 0;; iter++) {
+        double2 e;
+        bool done_fast = false;
+        if (in_box(px, py, c)) {
+            double lx = to_logical_fast(px, c.dx, inv_dx), ly = to_logical_fast(py, c.dx, inv_dx);
+            double fi, fj;
+            int i = floor_nonneg(lx, fi), j = floor_nonneg(ly, fj);
+            if ((unsigned)(i - tc.ilo) <= tc.ispan && (unsigned)(j - tc.jlo) <= tc.jspan) {
+                double di = lx - fi, dj = ly - fj;
+                const double2 *w = sE + (i - tc.wx0) * WIN + (j - tc.wy0);
+                double2 f00 = w[0], f01 = w[1], f10 = w[WIN], f11 = w[WIN + 1];
+                double a = 1 - di, b = 1 - dj;
+                double w00 = a * b, w10 = di * b, w01 = a * dj, w11 = di * dj;
+                e.x = f00.x * w00 + f10.x * w10 + f01.x * w01 + f11.x * w11;
+                e.y = f00.y * w00 + f10.y * w10 + f01.y * w01 + f11.y * w11;
+                done_fast = true;
+            }
+        }
+        if (!done_fast)   // straggler, wrapped or out-of-box position: the reference's flat-index gather
+            e = gather_E(E, c, to_logical(px, c.dx), to_logical(py, c.dx));
+        pvx += c.dtqm * e.x;
+        pvy += c.dtqm * e.y;
+        px += c.dt * pvx;
+        py += c.dt * pvy;
+        // src/main.cpp:807-845: exactly one wrap per push, then push again
+        if (px < 0.0) px += c.xl;
+        else if (px >= c.xl) px -= c.xl;
+        else if (py < 0.0) py += c.yl;
+        else if (py >= c.yl) py -= c.yl;
+        else break;
+        extra++;
+        if (iter >= 64) { atomicOr(err, ERR_BIT_RUNAWAY); break; }
+    }
+    return extra;
+}
+
+// fixed-point CIC deposit of one particle into the window limbs, or the global grid.
+// ci/cj return the particle's cell (or -1 when the position is outside the box: skipped).
+// returns true when the deposit stayed inside the shared-memory window.
+__device__ __forceinline__ bool deposit_one(double px, double py, const PushConst &c, double inv_dx, const TileCtx &tc,
+                                            unsigned *sLo, unsigned *sHi, long long *__restrict__ acc, double scale,
+                                            int &ci, int &cj) {
+    ci = cj = -1;
+    if (!in_box(px, py, c)) return false;
+    double lx = to_logical_fast(px, c.dx, inv_dx), ly = to_logical_fast(py, c.dx, inv_dx);
+    double fi, fj;
+    int i = floor_nonneg(lx, fi), j = floor_nonneg(ly, fj);
+    ci = i; cj = j;
+    double di = lx - fi, dj = ly - fj;
+    double a = (1 - di) * scale, d = di * scale, b = 1 - dj;
+    const double magic = 4503599627370496.0;   // 2^52: the mantissa of (w + 2^52) is w rounded to nearest-even
+    const unsigned long long mm = 0xFFFFFFFFFFFFFull;
+    unsigned long long w00 = (unsigned long long)__double_as_longlong(fma(a, b, magic)) & mm;
+    unsigned long long w10 = (unsigned long long)__double_as_longlong(fma(d, b, magic)) & mm;
+    unsigned long long w01 = (unsigned long long)__double_as_longlong(fma(a, dj, magic)) & mm;
+    unsigned long long w11 = (unsigned long long)__double_as_longlong(fma(d, dj, magic)) & mm;
+    if ((unsigned)(i - tc.ilo) <= tc.ispan && (unsigned)(j - tc.jlo) <= tc.jspan) {
+        const int k = (i - tc.wx0) * WIN + (j - tc.wy0);
+        const unsigned m = (1u << LIMB_BITS) - 1u;
+        atomicAdd(&sLo[k], (unsigned)w00 & m);           atomicAdd(&sHi[k], (unsigned)(w00 >> LIMB_BITS));
+        atomicAdd(&sLo[k + WIN], (unsigned)w10 & m);     atomicAdd(&sHi[k + WIN], (unsigned)(w10 >> LIMB_BITS));
+        atomicAdd(&sLo[k + 1], (unsigned)w01 & m);       atomicAdd(&sHi[k + 1], (unsigned)(w01 >> LIMB_BITS));
+        atomicAdd(&sLo[k + WIN + 1], (unsigned)w11 & m); atomicAdd(&sHi[k + WIN + 1], (unsigned)(w11 >> LIMB_BITS));
+        return true;
+    }
+    if (i <= c.nix - 2 && j <= c.niy - 2) {
+        unsigned long long *g = reinterpret_cast<unsigned long long *>(acc) + ((long long)i * c.niy + j);
+        atomicAdd(g, w00); atomicAdd(g + c.niy, w10); atomicAdd(g + 1, w01); atomicAdd(g + c.niy + 1, w11);
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------
+// the fused chunk kernel.  MODE 0: push + deposit(next step); 1: deposit only
+// (standalone scatterSpecies); 2: push only (PICSP_FLAG_NO_FUSE)
+// counters[0] = extra pushes, counters[1] = particles that deposited outside their window
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(MOVER_THREADS, 4)
+k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, double *__restrict__ y,
+             double *__restrict__ vx, double *__restrict__ vy, const Chunk *__restrict__ chunks,
+             const int *__restrict__ nchunks, PushConst c, const double2 *__restrict__ E,
+             long long *__restrict__ acc, const int *__restrict__ frac, unsigned int *__restrict__ hist_next,
+             unsigned long long *__restrict__ counters, int *__restrict__ err) {
+    __shared__ __align__(128) double2 sE[WIN * WIN];
+    __shared__ unsigned sLo[WIN * WIN];
+    __shared__ unsigned sHi[WIN * WIN];
+    __shared__ unsigned sCnt[9];
+    __shared__ __align__(8) unsigned long long sBar;
+
+    if ((int)blockIdx.x >= *nchunks) return;
+    const Chunk ck = chunks[blockIdx.x];
+    const int tid = threadIdx.x;
+    const int tx = ck.tile / c.nty, ty = ck.tile - tx * c.nty;
+    TileCtx tc;
+    tc.wx0 = tx * TILE - HALO; tc.wy0 = ty * TILE - HALO;
+    tc.ilo = max(tc.wx0, 0); tc.jlo = max(tc.wy0, 0);
+    tc.ispan = (unsigned)(min(tc.wx0 + WIN - 2, c.nix - 2) - tc.ilo);
+    tc.jspan = (unsigned)(min(tc.wy0 + WIN - 2, c.niy - 2) - tc.jlo);
+
+    if (MODE != 1 && tid == 0) {
+        mbar_init(&sBar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(&sBar, (uint32_t)(WIN * WIN * sizeof(double2)));
+        // tensor = E viewed as [nix][2*niy] doubles; box = [WIN][2*WIN]; out-of-grid elements arrive as 0
+        tma_load_2d(sE, &tmapE, 2 * tc.wy0, tc.wx0, &sBar);
+    }
+    if (MODE != 2)
+        for (int k = tid; k < WIN * WIN; k += MOVER_THREADS) { sLo[k] = 0u; sHi[k] = 0u; }
+    if (tid < 9) sCnt[tid] = 0u;
+
+    // first particle of this thread in flight while the window lands
+    const bool nbr_ok = (c.ntx >= 3 && c.nty >= 3);
+    int k = tid;
+    double px = 0, py = 0, pvx = 0, pvy = 0;
+    if (k < ck.count) {
+        const long long p = ck.start + k;
+        px = x[p]; py = y[p];
+        if (MODE != 1) { pvx = vx[p]; pvy = vy[p]; }
+    }
+    __syncthreads();
+    if (MODE != 1) mbar_wait(&sBar, 0);
+
+    const double inv_dx = 1.0 / c.dx;
+    const double scale = (MODE != 2) ? exp2((double)*frac) : 0.0;
+    unsigned extra = 0, outside = 0, same = 0;
+
+    while (k < ck.count) {
+        const long long p = ck.start + k;
+        const int kn = k + MOVER_THREADS;
+        double nx = 0, ny = 0, nvx = 0, nvy = 0;
+        if (kn < ck.count) {            // software prefetch of the next particle
+            nx = x[p + MOVER_THREADS]; ny = y[p + MOVER_THREADS];
+            if (MODE != 1) { nvx = vx[p + MOVER_THREADS]; nvy = vy[p + MOVER_THREADS]; }
+        }
+        if (MODE != 1) {
+            extra += push_one(px, py, pvx, pvy, c, inv_dx, tc, sE, E, err);
+            x[p] = px; y[p] = py; vx[p] = pvx; vy[p] = pvy;
+        }
+        int ci = -1, cj = -1;
+        if (MODE != 2) {
+            if (!deposit_one(px, py, c, inv_dx, tc, sLo, sHi, acc, scale, ci, cj)) outside++;
+        } else if (in_box(px, py, c)) {
+            double fi, fj;
+            ci = floor_nonneg(to_logical_fast(px, c.dx, inv_dx), fi);
+            cj = floor_nonneg(to_logical_fast(py, c.dx, inv_dx), fj);
+        }
+        if (MODE != 1) {
+            // histogram of the positions just written (bins of the next sort, bound of the next
+            // scale); same bin function as tile_of(): out-of-box positions count in bin 0
+            const int tnew = ci >= 0 ? tile_of_cell(ci, cj, c) : 0;
+            const int ux = tnew / c.nty, uy = tnew - ux * c.nty;
+            if (tnew == ck.tile) {
+                same++;
+            } else {
+                int ddx = ux - tx, ddy = uy - ty;
+                if (ddx > 1) ddx -= c.ntx; else if (ddx < -1) ddx += c.ntx;      // periodic neighbours
+                if (ddy > 1) ddy -= c.nty; else if (ddy < -1) ddy += c.nty;
+                if (nbr_ok && ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1) {
+                    atomicAdd(&sCnt[(ddx + 1) * 3 + (ddy + 1)], 1u);
+                } else {
+                    atomicAdd(&hist_next[ux * c.nty + uy], 1u);
+                    int ax = abs(ux - tx), ay = abs(uy - ty);
+                    ax = min(ax, c.ntx - ax); ay = min(ay, c.nty - ay);
+                    if (ax > 1 || ay > 1) atomicOr(err, ERR_BIT_DISPLACEMENT);
+                }
+            }
+        }
+        k = kn; px = nx; py = ny; pvx = nvx; pvy = nvy;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        extra += __shfl_xor_sync(0xffffffffu, extra, o);
+        outside += __shfl_xor_sync(0xffffffffu, outside, o);
+        same += __shfl_xor_sync(0xffffffffu, same, o);
+    }
+    if ((tid & 31) == 0) {
+        if (same) atomicAdd(&sCnt[4], same);
+        if (extra) atomicAdd(&counters[0], (unsigned long long)extra);
+        if (outside) atomicAdd(&counters[1], (unsigned long long)outside);
+    }
+    __syncthreads();
+
+    // flush the window: limbs -> one native 64-bit integer RED per touched node
+    if (MODE != 2) {
+        for (int q = tid; q < WIN * WIN; q += MOVER_THREADS) {
+            unsigned long long v = ((unsigned long long)sHi[q] << LIMB_BITS) + (unsigned long long)sLo[q];
+            if (v) {
+                int li = q / WIN, lj = q - li * WIN;
+                long long gi = tc.wx0 + li, gj = tc.wy0 + lj;
+                atomicAdd(reinterpret_cast<unsigned long long *>(acc) + (gi * c.niy + gj), v);
+            }
+        }
+    }
+    if (MODE != 1 && tid < 9 && sCnt[tid]) {
+        if (tid == 4) {
+            atomicAdd(&hist_next[ck.tile], sCnt[4]);
+        } else {
+            int ux = (tx + tid / 3 - 1 + c.ntx) % c.ntx, uy = (ty + tid % 3 - 1 + c.nty) % c.nty;
+            atomicAdd(&hist_next[ux * c.nty + uy], sCnt[tid]);
+        }
+    }
+}
+
+}  // namespace picsp

@@ -148,6 +148,13 @@ class Simulation:
         check(self.L.picsp_repush_count(self.ctx, s, C.byref(n)))
         return n.value
 
+    def straggler_count(self, s):
+        n = C.c_int64()
+        check(self.L.picsp_straggler_count(self.ctx, s, C.byref(n)))
+        return n.value
+
+    def set_sort_period(self, s, period): check(self.L.picsp_set_sort_period(self.ctx, s, period))
+
     # -- multi-GPU ------------------------------------------------------------------------------
     @staticmethod
     def comm_unique_id():

@@ -73,7 +73,7 @@ def test_single_ops_against_reference_golden(name):
 
 
 @pytest.mark.parametrize("name", LOOPS)
-@pytest.mark.parametrize("flags", [0, 4], ids=["fused", "nofuse"])
+@pytest.mark.parametrize("flags", [0, 4, 2, 6], ids=["tiled-fused", "tiled-nofuse", "unsorted-fused", "unsorted-nofuse"])
 def test_chained_loop_against_reference_golden(name, flags):
     """bootstrap + several steps with no resynchronisation (fused and unfused mover)."""
     g = load_golden(name)
@@ -133,6 +133,32 @@ def test_step_against_oracle_midsize(solver, numx, n):
                     assert relerr(got[k], want[k]) <= 10 * RTOL
 
 
+@pytest.mark.parametrize("period", [1, 3, 1000], ids=["sort-every-step", "sort-every-3", "never-resort"])
+def test_sort_period_does_not_change_results(period):
+    """The tile sort only reorders storage: results after 12 steps are identical to 1e-12 whatever the
+    sort cadence, including 'never re-sort' where fast electrons leave their window (straggler path)."""
+    nm = normalise()
+    numx, n, solver = 64, 60_000, 1
+    o = Oracle(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, vth_i=nm["vth_i"], solver=solver)
+    o.seed(21); o.init(ION, 1); o.init(ELECTRON, 1)
+    x, y, vx, vy = o.get_species(ELECTRON)
+    o.set_species(ELECTRON, x, y, vx * 2.5, vy * 2.5)          # up to ~2 cells per step
+    with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, solverType=solver)) as sim:
+        sim.set_sort_period(ION, period); sim.set_sort_period(ELECTRON, period)
+        for s in (ION, ELECTRON):
+            sim.set_species(s, *o.get_species(s))
+        o.bootstrap(); sim.bootstrap()
+        o.step(12); sim.step(12)
+        if period == 1000:
+            assert sim.straggler_count(ELECTRON) > 0, "fixture must exercise the straggler path"
+        for name in GRIDS:
+            assert_grid_close(sim.grid(name), o.grid(name), sim.nix, sim.niy, 100 * RTOL, name)
+        for s in (ION, ELECTRON):
+            got, want = sim.get_species(s), o.get_species(s)
+            for k in range(4):
+                assert relerr(got[k], want[k]) <= 100 * RTOL
+
+
 def test_density_is_deterministic_and_order_independent():
     """Fixed-point accumulation: bit-identical density for any particle order and on repeat."""
     nm = normalise()
@@ -144,7 +170,7 @@ def test_density_is_deterministic_and_order_independent():
     outs = []
     for trial in range(3):
         perm = np.arange(n) if trial == 0 else rng.permutation(n)
-        with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n)) as sim:
+        with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, flags=2 if trial == 2 else 0)) as sim:
             sim.set_species(ION, x[perm], y[perm], v, v)
             sim.scatterSpecies(ION)
             outs.append(sim.grid("den_i"))
