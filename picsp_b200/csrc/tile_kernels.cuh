@@ -7,10 +7,9 @@
 //   * the mover (pushSpecies + gather, src/main.cpp:772-847, :671-681) gathers from that
 //     window, writes the particle back in place (32 B read + 32 B written),
 //   * the next step's CIC deposit (scatterSpecies, src/main.cpp:684-700) of the position just
-//     written goes into a shared-memory window of FIXED-POINT accumulators held as two
-//     32-bit limbs, so that every update is one native 32-bit shared atomic (64-bit shared
-//     atomics are CAS loops on sm_100a) and needs no carry: a limb receives at most
-//     CHUNK = 2^11 addends of < 2^21, which cannot overflow 32 bits,
+//     written goes into a shared-memory window of 64-bit FIXED-POINT accumulators held as two
+//     32-bit limbs and updated with native 32-bit shared atomics plus an exact carry
+//     (64-bit shared atomics are CAS loops on sm_100a; see add64_limbs),
 //   * the window is flushed to the global int64 accumulator grid with native 64-bit
 //     integer REDs.  Integer addition commutes, so the density is bit-identical for any
 //     particle order, chunking or launch order.
@@ -27,8 +26,7 @@ namespace picsp {
 constexpr int HALO = 4;                       // cells of drift a window tolerates on each side
 constexpr int WIN = TILE + 1 + 2 * HALO;      // window edge in nodes (25)
 constexpr int CHUNK = 2048;                   // particles per CTA work item
-constexpr int LIMB_BITS = 21;                 // 32 - log2(CHUNK)
-constexpr int MAX_FRAC_TILED = 2 * LIMB_BITS; // fraction bits the two limbs can carry (42)
+constexpr int MAX_FRAC_TILED = 51;            // w*2^frac <= 2^51 keeps (w*2^frac + 2^52) below 2^53: the magic-number conversion is exact
 constexpr int MOVER_THREADS = 256;
 
 struct __align__(16) Chunk {
@@ -181,6 +179,18 @@ __device__ __forceinline__ int push_one(double &px, double &py, double &pvx, dou
     return extra;
 }
 
+// Exact 64-bit accumulation out of two native 32-bit shared atomics: the low-limb add
+// returns the previous value, which tells THIS add whether it wrapped the limb; the wrap is
+// then carried into the high limb together with the high half of the addend.  Every carry is
+// accounted exactly once, by the add that produced it, so the (hi, lo) pair equals the
+// 64-bit sum for any interleaving of adds (64-bit shared atomics are CAS loops on sm_100a).
+__device__ __forceinline__ void add64_limbs(unsigned *sLo, unsigned *sHi, int k, unsigned long long w) {
+    const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
+    const unsigned old = atomicAdd(&sLo[k], lo);
+    const unsigned carry = (old + lo) < lo ? 1u : 0u;
+    if (hi | carry) atomicAdd(&sHi[k], hi + carry);
+}
+
 // fixed-point CIC deposit of one particle into the window limbs, or the global grid.
 // ci/cj return the particle's cell (or -1 when the position is outside the box: skipped).
 // returns true when the deposit stayed inside the shared-memory window.
@@ -203,11 +213,10 @@ __device__ __forceinline__ bool deposit_one(double px, double py, const PushCons
     unsigned long long w11 = (unsigned long long)__double_as_longlong(fma(d, dj, magic)) & mm;
     if ((unsigned)(i - tc.ilo) <= tc.ispan && (unsigned)(j - tc.jlo) <= tc.jspan) {
         const int k = (i - tc.wx0) * WIN + (j - tc.wy0);
-        const unsigned m = (1u << LIMB_BITS) - 1u;
-        atomicAdd(&sLo[k], (unsigned)w00 & m);           atomicAdd(&sHi[k], (unsigned)(w00 >> LIMB_BITS));
-        atomicAdd(&sLo[k + WIN], (unsigned)w10 & m);     atomicAdd(&sHi[k + WIN], (unsigned)(w10 >> LIMB_BITS));
-        atomicAdd(&sLo[k + 1], (unsigned)w01 & m);       atomicAdd(&sHi[k + 1], (unsigned)(w01 >> LIMB_BITS));
-        atomicAdd(&sLo[k + WIN + 1], (unsigned)w11 & m); atomicAdd(&sHi[k + WIN + 1], (unsigned)(w11 >> LIMB_BITS));
+        add64_limbs(sLo, sHi, k, w00);
+        add64_limbs(sLo, sHi, k + WIN, w10);
+        add64_limbs(sLo, sHi, k + 1, w01);
+        add64_limbs(sLo, sHi, k + WIN + 1, w11);
         return true;
     }
     if (i <= c.nix - 2 && j <= c.niy - 2) {
@@ -330,7 +339,7 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
     // flush the window: limbs -> one native 64-bit integer RED per touched node
     if (MODE != 2) {
         for (int q = tid; q < WIN * WIN; q += MOVER_THREADS) {
-            unsigned long long v = ((unsigned long long)sHi[q] << LIMB_BITS) + (unsigned long long)sLo[q];
+            unsigned long long v = ((unsigned long long)sHi[q] << 32) | (unsigned long long)sLo[q];
             if (v) {
                 int li = q / WIN, lj = q - li * WIN;
                 long long gi = tc.wx0 + li, gj = tc.wy0 + lj;
