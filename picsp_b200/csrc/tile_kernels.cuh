@@ -141,8 +141,9 @@ struct TileCtx {
 // mover body for one particle (pushSpecies, src/main.cpp:779-846); returns the number of extra pushes
 __device__ __forceinline__ int push_one(double &px, double &py, double &pvx, double &pvy, const PushConst &c,
                                         double inv_dx, const TileCtx &tc, const double2 *sE,
-                                        const double2 *__restrict__ E, int *err) {
+                                        const double2 *__restrict__ E, int *err, int &oi, int &oj) {
     int extra = 0;
+    oi = oj = -1;   // cell of the position the push starts from (-1: outside the box)
     for (int iter = 0;; iter++) {
         double2 e;
         bool done_fast = false;
@@ -150,6 +151,7 @@ __device__ __forceinline__ int push_one(double &px, double &py, double &pvx, dou
             double lx = to_logical_fast(px, c.dx, inv_dx), ly = to_logical_fast(py, c.dx, inv_dx);
             double fi, fj;
             int i = floor_nonneg(lx, fi), j = floor_nonneg(ly, fj);
+            if (iter == 0) { oi = i; oj = j; }
             if ((unsigned)(i - tc.ilo) <= tc.ispan && (unsigned)(j - tc.jlo) <= tc.jspan) {
                 double di = lx - fi, dj = ly - fj;
                 const double2 *w = sE + (i - tc.wx0) * WIN + (j - tc.wy0);
@@ -289,8 +291,9 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
             nx = x[p + MOVER_THREADS]; ny = y[p + MOVER_THREADS];
             if (MODE != 1) { nvx = vx[p + MOVER_THREADS]; nvy = vy[p + MOVER_THREADS]; }
         }
+        int oi = -1, oj = -1;
         if (MODE != 1) {
-            extra += push_one(px, py, pvx, pvy, c, inv_dx, tc, sE, E, err);
+            extra += push_one(px, py, pvx, pvy, c, inv_dx, tc, sE, E, err, oi, oj);
             x[p] = px; y[p] = py; vx[p] = pvx; vy[p] = pvy;
         }
         int ci = -1, cj = -1;
@@ -316,10 +319,14 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
                     atomicAdd(&sCnt[(ddx + 1) * 3 + (ddy + 1)], 1u);
                 } else {
                     atomicAdd(&hist_next[ux * c.nty + uy], 1u);
-                    int ax = abs(ux - tx), ay = abs(uy - ty);
-                    ax = min(ax, c.ntx - ax); ay = min(ay, c.nty - ay);
-                    if (ax > 1 || ay > 1) atomicOr(err, ERR_BIT_DISPLACEMENT);
                 }
+            }
+            // the fixed-point scale assumes no particle moves more than one tile in ONE step
+            const int told = oi >= 0 ? tile_of_cell(oi, oj, c) : 0;
+            if (tnew != told) {
+                int ax = abs(ux - told / c.nty), ay = abs(uy - told % c.nty);
+                ax = min(ax, c.ntx - ax); ay = min(ay, c.nty - ay);
+                if (ax > 1 || ay > 1) atomicOr(err, ERR_BIT_DISPLACEMENT);
             }
         }
         k = kn; px = nx; py = ny; pvx = nvx; pvy = nvy;
