@@ -28,6 +28,10 @@ constexpr int WIN = TILE + 1 + 2 * HALO;      // window edge in nodes (25)
 constexpr int CHUNK = 2048;                   // particles per CTA work item
 constexpr int MAX_FRAC_TILED = 51;            // w*2^frac <= 2^51 keeps (w*2^frac + 2^52) below 2^53: the magic-number conversion is exact
 constexpr int MOVER_THREADS = 256;
+#ifndef PICSP_MOVER_MIN_CTAS
+#define PICSP_MOVER_MIN_CTAS 4
+#endif
+constexpr int MOVER_MIN_CTAS = PICSP_MOVER_MIN_CTAS;
 
 struct __align__(16) Chunk {
     long long start;   // first particle (index into the species arrays)
@@ -136,25 +140,36 @@ struct TileCtx {
     int wx0, wy0;        // window origin (node indices, may be negative)
     int ilo, jlo;        // cells whose four nodes lie inside window AND grid: [ilo, ilo+ispan] x [jlo, jlo+jspan]
     unsigned ispan, jspan;
+    int tx, ty;          // this chunk's bin
+    int ntx1, nty1;      // ntx-1, nty-1
+    unsigned long long xl_bits, yl_bits;
 };
 
-// mover body for one particle (pushSpecies, src/main.cpp:779-846); returns the number of extra pushes
+// 0 <= v < limit for IEEE doubles, as ONE unsigned 64-bit integer compare: non-negative
+// doubles order like their bit patterns; negatives (sign bit), NaN and +inf compare high.
+// (-0.0 reports "outside"; the callers' slow paths treat it exactly like the reference.)
+__device__ __forceinline__ bool in_range_bits(double v, unsigned long long limit_bits) {
+    return (unsigned long long)__double_as_longlong(v) < limit_bits;
+}
+
+// mover body for one particle (pushSpecies, src/main.cpp:779-846); returns the number of extra pushes.
+// oi/oj: cell the push starts from (-1 if outside the box).
 __device__ __forceinline__ int push_one(double &px, double &py, double &pvx, double &pvy, const PushConst &c,
                                         double inv_dx, const TileCtx &tc, const double2 *sE,
                                         const double2 *__restrict__ E, int *err, int &oi, int &oj) {
     int extra = 0;
-    oi = oj = -1;   // cell of the position the push starts from (-1: outside the box)
+    oi = oj = -1;
     for (int iter = 0;; iter++) {
         double2 e;
         bool done_fast = false;
-        if (in_box(px, py, c)) {
+        if (in_range_bits(px, tc.xl_bits) && in_range_bits(py, tc.yl_bits)) {
             double lx = to_logical_fast(px, c.dx, inv_dx), ly = to_logical_fast(py, c.dx, inv_dx);
             double fi, fj;
             int i = floor_nonneg(lx, fi), j = floor_nonneg(ly, fj);
             if (iter == 0) { oi = i; oj = j; }
             if ((unsigned)(i - tc.ilo) <= tc.ispan && (unsigned)(j - tc.jlo) <= tc.jspan) {
                 double di = lx - fi, dj = ly - fj;
-                const double2 *w = sE + (i - tc.wx0) * WIN + (j - tc.wy0);
+                const double2 *w = sE + ((i - tc.wx0) * WIN + (j - tc.wy0));
                 double2 f00 = w[0], f01 = w[1], f10 = w[WIN], f11 = w[WIN + 1];
                 double a = 1 - di, b = 1 - dj;
                 double w00 = a * b, w10 = di * b, w01 = a * dj, w11 = di * dj;
@@ -169,12 +184,14 @@ __device__ __forceinline__ int push_one(double &px, double &py, double &pvx, dou
         pvy += c.dtqm * e.y;
         px += c.dt * pvx;
         py += c.dt * pvy;
-        // src/main.cpp:807-845: exactly one wrap per push, then push again
+        // src/main.cpp:807-845: exactly one wrap per push, then push again.  Common case first:
+        // both coordinates inside the box means none of the four tests fires.
+        if (in_range_bits(px, tc.xl_bits) && in_range_bits(py, tc.yl_bits)) break;
         if (px < 0.0) px += c.xl;
         else if (px >= c.xl) px -= c.xl;
         else if (py < 0.0) py += c.yl;
         else if (py >= c.yl) py -= c.yl;
-        else break;
+        else break;                       // -0.0 or NaN: no test fires in the reference either
         extra++;
         if (iter >= 64) { atomicOr(err, ERR_BIT_RUNAWAY); break; }
     }
@@ -190,7 +207,7 @@ __device__ __forceinline__ void add64_limbs(unsigned *sLo, unsigned *sHi, int k,
     const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
     const unsigned old = atomicAdd(&sLo[k], lo);
     const unsigned carry = (old + lo) < lo ? 1u : 0u;
-    if (hi | carry) atomicAdd(&sHi[k], hi + carry);
+    atomicAdd(&sHi[k], hi + carry);
 }
 
 // fixed-point CIC deposit of one particle into the window limbs, or the global grid.
@@ -200,7 +217,9 @@ __device__ __forceinline__ bool deposit_one(double px, double py, const PushCons
                                             unsigned *sLo, unsigned *sHi, long long *__restrict__ acc, double scale,
                                             int &ci, int &cj) {
     ci = cj = -1;
-    if (!in_box(px, py, c)) return false;
+    if (!(in_range_bits(px, tc.xl_bits) && in_range_bits(py, tc.yl_bits))) {
+        if (!in_box(px, py, c)) return false;    // -0.0 is inside the box; everything else here is not
+    }
     double lx = to_logical_fast(px, c.dx, inv_dx), ly = to_logical_fast(py, c.dx, inv_dx);
     double fi, fj;
     int i = floor_nonneg(lx, fi), j = floor_nonneg(ly, fj);
@@ -234,7 +253,7 @@ __device__ __forceinline__ bool deposit_one(double px, double py, const PushCons
 // counters[0] = extra pushes, counters[1] = particles that deposited outside their window
 // ---------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(MOVER_THREADS, 4)
+__global__ void __launch_bounds__(MOVER_THREADS, MOVER_MIN_CTAS)
 k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, double *__restrict__ y,
              double *__restrict__ vx, double *__restrict__ vy, const Chunk *__restrict__ chunks,
              const int *__restrict__ nchunks, PushConst c, const double2 *__restrict__ E,
@@ -249,12 +268,15 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
     if ((int)blockIdx.x >= *nchunks) return;
     const Chunk ck = chunks[blockIdx.x];
     const int tid = threadIdx.x;
-    const int tx = ck.tile / c.nty, ty = ck.tile - tx * c.nty;
     TileCtx tc;
-    tc.wx0 = tx * TILE - HALO; tc.wy0 = ty * TILE - HALO;
+    tc.tx = ck.tile / c.nty; tc.ty = ck.tile - tc.tx * c.nty;
+    tc.wx0 = tc.tx * TILE - HALO; tc.wy0 = tc.ty * TILE - HALO;
     tc.ilo = max(tc.wx0, 0); tc.jlo = max(tc.wy0, 0);
     tc.ispan = (unsigned)(min(tc.wx0 + WIN - 2, c.nix - 2) - tc.ilo);
     tc.jspan = (unsigned)(min(tc.wy0 + WIN - 2, c.niy - 2) - tc.jlo);
+    tc.ntx1 = c.ntx - 1; tc.nty1 = c.nty - 1;
+    tc.xl_bits = (unsigned long long)__double_as_longlong(c.xl);
+    tc.yl_bits = (unsigned long long)__double_as_longlong(c.yl);
 
     if (MODE != 1 && tid == 0) {
         mbar_init(&sBar, 1);
@@ -267,14 +289,22 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
         for (int k = tid; k < WIN * WIN; k += MOVER_THREADS) { sLo[k] = 0u; sHi[k] = 0u; }
     if (tid < 9) sCnt[tid] = 0u;
 
-    // first particle of this thread in flight while the window lands
+    // chunk-local pointers: 32-bit indexing inside the loop
+    double *__restrict__ cx = x + ck.start;
+    double *__restrict__ cy = y + ck.start;
+    double *__restrict__ cvx = vx + ck.start;
+    double *__restrict__ cvy = vy + ck.start;
+    const int count = ck.count;
+    const int last = count - 1;
     const bool nbr_ok = (c.ntx >= 3 && c.nty >= 3);
+
+    // first particle of this thread in flight while the window lands
     int k = tid;
-    double px = 0, py = 0, pvx = 0, pvy = 0;
-    if (k < ck.count) {
-        const long long p = ck.start + k;
-        px = x[p]; py = y[p];
-        if (MODE != 1) { pvx = vx[p]; pvy = vy[p]; }
+    double px, py, pvx = 0, pvy = 0;
+    {
+        const int k0 = min(k, last);
+        px = cx[k0]; py = cy[k0];
+        if (MODE != 1) { pvx = cvx[k0]; pvy = cvy[k0]; }
     }
     __syncthreads();
     if (MODE != 1) mbar_wait(&sBar, 0);
@@ -283,18 +313,18 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
     const double scale = (MODE != 2) ? exp2((double)*frac) : 0.0;
     unsigned extra = 0, outside = 0, same = 0;
 
-    while (k < ck.count) {
-        const long long p = ck.start + k;
+    while (k < count) {
+        // software prefetch of this thread's next particle (clamped: always a valid address)
         const int kn = k + MOVER_THREADS;
-        double nx = 0, ny = 0, nvx = 0, nvy = 0;
-        if (kn < ck.count) {            // software prefetch of the next particle
-            nx = x[p + MOVER_THREADS]; ny = y[p + MOVER_THREADS];
-            if (MODE != 1) { nvx = vx[p + MOVER_THREADS]; nvy = vy[p + MOVER_THREADS]; }
-        }
+        const int kp = min(kn, last);
+        const double nx = cx[kp], ny = cy[kp];
+        double nvx = 0, nvy = 0;
+        if (MODE != 1) { nvx = cvx[kp]; nvy = cvy[kp]; }
+
         int oi = -1, oj = -1;
         if (MODE != 1) {
             extra += push_one(px, py, pvx, pvy, c, inv_dx, tc, sE, E, err, oi, oj);
-            x[p] = px; y[p] = py; vx[p] = pvx; vy[p] = pvy;
+            cx[k] = px; cy[k] = py; cvx[k] = pvx; cvy[k] = pvy;
         }
         int ci = -1, cj = -1;
         if (MODE != 2) {
@@ -307,24 +337,24 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
         if (MODE != 1) {
             // histogram of the positions just written (bins of the next sort, bound of the next
             // scale); same bin function as tile_of(): out-of-box positions count in bin 0
-            const int tnew = ci >= 0 ? tile_of_cell(ci, cj, c) : 0;
-            const int ux = tnew / c.nty, uy = tnew - ux * c.nty;
-            if (tnew == ck.tile) {
+            const int ux = ci >= 0 ? min((int)((unsigned)ci / TILE), tc.ntx1) : 0;
+            const int uy = ci >= 0 ? min((int)((unsigned)cj / TILE), tc.nty1) : 0;
+            if (ux == tc.tx && uy == tc.ty) {
                 same++;
             } else {
-                int ddx = ux - tx, ddy = uy - ty;
+                int ddx = ux - tc.tx, ddy = uy - tc.ty;
                 if (ddx > 1) ddx -= c.ntx; else if (ddx < -1) ddx += c.ntx;      // periodic neighbours
                 if (ddy > 1) ddy -= c.nty; else if (ddy < -1) ddy += c.nty;
-                if (nbr_ok && ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1) {
+                if (nbr_ok && ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1)
                     atomicAdd(&sCnt[(ddx + 1) * 3 + (ddy + 1)], 1u);
-                } else {
+                else
                     atomicAdd(&hist_next[ux * c.nty + uy], 1u);
-                }
             }
             // the fixed-point scale assumes no particle moves more than one tile in ONE step
-            const int told = oi >= 0 ? tile_of_cell(oi, oj, c) : 0;
-            if (tnew != told) {
-                int ax = abs(ux - told / c.nty), ay = abs(uy - told % c.nty);
+            const int ox = oi >= 0 ? min((int)((unsigned)oi / TILE), tc.ntx1) : 0;
+            const int oy = oi >= 0 ? min((int)((unsigned)oj / TILE), tc.nty1) : 0;
+            if (ox != ux || oy != uy) {
+                int ax = abs(ux - ox), ay = abs(uy - oy);
                 ax = min(ax, c.ntx - ax); ay = min(ay, c.nty - ay);
                 if (ax > 1 || ay > 1) atomicOr(err, ERR_BIT_DISPLACEMENT);
             }
@@ -358,7 +388,7 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
         if (tid == 4) {
             atomicAdd(&hist_next[ck.tile], sCnt[4]);
         } else {
-            int ux = (tx + tid / 3 - 1 + c.ntx) % c.ntx, uy = (ty + tid % 3 - 1 + c.nty) % c.nty;
+            int ux = (tc.tx + tid / 3 - 1 + c.ntx) % c.ntx, uy = (tc.ty + tid % 3 - 1 + c.nty) % c.nty;
             atomicAdd(&hist_next[ux * c.nty + uy], sCnt[tid]);
         }
     }
