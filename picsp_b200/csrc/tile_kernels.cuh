@@ -314,12 +314,13 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
     unsigned extra = 0, outside = 0, same = 0;
 
     while (k < count) {
-        // software prefetch of this thread's next particle (clamped: always a valid address)
+        // software prefetch of this thread's next particle (predicated: no redundant traffic)
         const int kn = k + MOVER_THREADS;
-        const int kp = min(kn, last);
-        const double nx = cx[kp], ny = cy[kp];
-        double nvx = 0, nvy = 0;
-        if (MODE != 1) { nvx = cvx[kp]; nvy = cvy[kp]; }
+        double nx = px, ny = py, nvx = pvx, nvy = pvy;
+        if (kn < count) {
+            nx = cx[kn]; ny = cy[kn];
+            if (MODE != 1) { nvx = cvx[kn]; nvy = cvy[kn]; }
+        }
 
         int oi = -1, oj = -1;
         if (MODE != 1) {

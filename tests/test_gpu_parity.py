@@ -159,8 +159,10 @@ def test_sort_period_does_not_change_results(period):
                 assert relerr(got[k], want[k]) <= 100 * RTOL
 
 
-def test_density_is_deterministic_and_order_independent():
-    """Fixed-point accumulation: bit-identical density for any particle order and on repeat."""
+@pytest.mark.parametrize("flags", [0, 2], ids=["tiled", "unsorted"])
+def test_density_is_deterministic_and_order_independent(flags):
+    """Fixed-point accumulation: bit-identical density for any particle order and on repeat
+    (within one code path; the tiled and unsorted paths round weights at different scales)."""
     nm = normalise()
     numx, n = 96, 200_000
     rng = np.random.default_rng(5)
@@ -170,11 +172,27 @@ def test_density_is_deterministic_and_order_independent():
     outs = []
     for trial in range(3):
         perm = np.arange(n) if trial == 0 else rng.permutation(n)
-        with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, flags=2 if trial == 2 else 0)) as sim:
+        with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, flags=flags)) as sim:
             sim.set_species(ION, x[perm], y[perm], v, v)
             sim.scatterSpecies(ION)
             outs.append(sim.grid("den_i"))
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+def test_fused_mover_density_is_deterministic():
+    """Same state pushed twice in two contexts: the density accumulated by the fused mover and
+    the phase space are bit-identical (independent of chunk scheduling and atomic arrival order)."""
+    nm = normalise()
+    numx, n = 96, 150_000
+    res = []
+    for trial in range(2):
+        with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n)) as sim:
+            sim.fill_synthetic(ION, n, seed=3, vth=nm["vth_i"])
+            sim.fill_synthetic(ELECTRON, n, seed=4, vth=1.0, xdrift=nm["drift_e"])
+            sim.bootstrap(); sim.step(3)
+            res.append([sim.grid(g) for g in GRIDS] + list(sim.get_species(ELECTRON)))
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
 
 
 def test_charge_conservation_large():
