@@ -9,6 +9,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 LIB_PATH = os.path.join(PKG, "libpicsp_b200.so")
 HEADER = os.path.join(ROOT, "include", "picsp_b200.h")
+HOST_HEADER = os.path.join(ROOT, "include", "picsp_b200_host.h")
 
 _dp = C.POINTER(C.c_double)
 _i64p = C.POINTER(C.c_int64)
@@ -20,6 +21,13 @@ class PicspError(RuntimeError):
         self.code = code
 
 
+class CRunConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("nTimeSteps", "numxCells", "numyCells", "nParticlesI", "nParticlesE",
+                                         "dumpPeriod", "solverType", "loadType")] + \
+               [(n, C.c_double) for n in ("timeStep", "stepSize", "massI", "massE", "chargeE", "density", "vthE", "vthI",
+                                          "driftE", "driftI", "ion_spwt", "electron_spwt", "omega_pe", "Lambda_D")]
+
+
 class CParams(C.Structure):
     _fields_ = [("numxCells", C.c_int32), ("numyCells", C.c_int32), ("stepSize", C.c_double), ("timeStep", C.c_double),
                 ("solverType", C.c_int32), ("flags", C.c_int32), ("charge", C.c_double * 2), ("mass", C.c_double * 2),
@@ -27,10 +35,12 @@ class CParams(C.Structure):
 
 
 def abi_symbols():
-    """Every function name declared in include/picsp_b200.h."""
-    text = open(HEADER).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(picsp_[a-z0-9_]+)\s*\(", text)))
+    """Every function name declared in include/*.h."""
+    names = set()
+    for h in (HEADER, HOST_HEADER):
+        text = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        names |= set(re.findall(r"\b(picsp_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 _lib = None
@@ -80,6 +90,17 @@ def load_library():
         "picsp_profile_get": ([ctx, C.c_int, _dp, _i64p], C.c_int),
         "picsp_profile_reset": ([ctx], C.c_int),
         "picsp_kernel_launches": ([ctx, _i64p], C.c_int),
+        "picsp_host_parse_ini": ([C.c_char_p, C.POINTER(CRunConfig), C.c_int], C.c_int),
+        "picsp_host_loader_create": ([C.c_uint32], C.c_void_p),
+        "picsp_host_loader_destroy": ([C.c_void_p], None),
+        "picsp_host_loader_fill": ([C.c_void_p, C.POINTER(CRunConfig), C.c_int, _dp, _dp, _dp, _dp], C.c_int),
+        "picsp_host_run": ([C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int], C.c_int),
+        "picsp_host_h5_open": ([C.c_char_p], C.c_void_p),
+        "picsp_host_h5_group": ([C.c_void_p, C.c_char_p], C.c_int),
+        "picsp_host_h5_dataset_f64": ([C.c_void_p, C.c_char_p, _dp, C.c_uint64, C.c_uint64], C.c_int),
+        "picsp_host_h5_attr_f64": ([C.c_void_p, C.c_char_p, C.c_double], C.c_int),
+        "picsp_host_h5_attr_i32": ([C.c_void_p, C.c_char_p, C.c_int32], C.c_int),
+        "picsp_host_h5_close": ([C.c_void_p], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)

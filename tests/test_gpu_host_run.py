@@ -1,0 +1,54 @@
+"""GPU: the whole drop-in program (`picsp_host_run` == `picsp_b200_run <input.ini>`) on BASELINE config 1,
+the shipped input.ini, against the reference's own main() on the same file (tests/golden/whole_run_input_ini.npz,
+produced at the reference's -O0 build): HDF5 names/shapes/attribute types, first dumps, energy rows."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from picsp_b200 import host
+from picsp_b200.lib import PKG
+from tests import h5mini
+from tests.helpers import GOLDEN, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+INI = os.path.join(GOLDEN, "input_ini_shipped.ini")
+
+
+def test_whole_program_first_100_steps(tmp_path):
+    g = load_golden("whole_run_input_ini")
+    out = str(tmp_path / "data.h5")
+    host.run(INI, out, max_steps=100, quiet=True)
+    f = h5mini.File(out)
+    # layout contract: root attributes with the reference's types, six groups
+    a = f.attrs()
+    for k in ("Lx", "Ly"):
+        assert a[k].dtype == np.float64 and a[k] == g["attr_" + k][0]
+    for k in ("dp", "Nt", "Nx", "Ny"):
+        assert a[k].dtype == np.int32 and a[k] == g["attr_" + k][0]
+    assert sorted("/" + n for n in f.groups()) == sorted(g["groups"].tolist())
+    assert f.datasets("phi") == sorted(["0", "50", "100"])
+    assert f.read("/particle.e/0").shape == (10000, 4) and f.read("/den.i/50").shape == (65, 65)
+    assert f.read("/timedata/energy").shape == g["energy"].shape
+    # numbers: first dump is one step after the bootstrap; the 50-step dump has 51 steps of round-off growth
+    assert relerr(f.read("/phi/0"), g["phi_0"]) < 1e-11
+    assert relerr(f.read("/particle.e/0"), g["particle_e_0"]) < 1e-12
+    assert relerr(f.read("/particle.i/0"), g["particle_i_0"]) < 1e-12
+    assert relerr(f.read("/den.e/0")[1:-1, 1:-1], g["den_e_0"][1:-1, 1:-1]) < 1e-12
+    assert relerr(f.read("/den.i/50")[1:-1, 1:-1], g["den_i_50"][1:-1, 1:-1]) < 1e-9
+    assert relerr(f.read("/phi/50"), g["phi_50"]) < 1e-7
+    e = f.read("/timedata/energy")
+    assert np.allclose(e[:3], g["energy"][:3], rtol=1e-8, atol=0)
+
+
+def test_cli_executable_prints_the_reference_banner(tmp_path):
+    exe = os.path.join(PKG, "picsp_b200_run")
+    out = str(tmp_path / "cli.h5")
+    r = subprocess.run([exe, INI, "--out", out, "--steps", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    for line in ("********** IMPORTANT PLASMA QUANTITIES ***********", "STATUS, Input parameters are compatible.",
+                 "Ion mass: 1836.65 charge: 1 spwt: 0.000118562 Num of particles: 10000", "vdriftE: 0.222222 vdriftI: 0",
+                 "Nx: 64 Ny: 64", "Total timesteps: 10000", "TS: 0 \t delta_phi:", "Total time taken by PICSP:"):
+        assert line in r.stdout, line
+    assert subprocess.run([exe], capture_output=True, text=True).returncode != 0
