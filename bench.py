@@ -49,6 +49,16 @@ def physical_normalisation():
                 vth_i=vthI / vthE, vth_e=1.0, drift_e=driftE / vthE)
 
 
+def ncu_traffic_bytes_per_particle():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full
+    capture (profiles/ncu_traffic.json), per particle; None if no capture is recorded."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return float(json.load(f)["k_tile_mover<0>"]["dram_bytes_per_particle"])
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -254,9 +264,13 @@ def main_ours(args, rank, world, local_rank):
     peak, peak_src = measured_peak_gbs()
     per_launch_s = push_ms * 1e-3 / max(push_calls, 1)
     achieved = ALGO_BYTES_PER_PARTICLE_STEP * n_local / per_launch_s / 1e9
+    traffic = args.traffic_bytes_per_launch
+    if traffic is None and ncu_traffic_bytes_per_particle() is not None:
+        traffic = ncu_traffic_bytes_per_particle() * n_local     # per launch, like `achieved`
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": args.traffic_bytes_per_launch,
-                "kernel": "k_push<fused> (leapfrog mover + CIC gather + next-step CIC deposit)",
+                "traffic": traffic,
+                "kernel": "k_tile_mover<0> (leapfrog mover + CIC gather from a TMA-staged E tile + next-step CIC deposit)",
+                "traffic_source": "profiles/ncu_traffic.json: ncu --set full dram bytes per particle x particles per launch",
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE_STEP * n_local,
                 "avg_launch_ms": per_launch_s * 1e3, "launches_timed": push_calls, "peak_source": peak_src,
                 "share_of_step": push_ms / prof["step"][0] if prof["step"][0] else None}
