@@ -237,6 +237,10 @@ def main_ours(args, rank, world, local_rank):
         uid = [Simulation.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         sim.comm_attach(uid[0], rank, world)
+    if args.sort_period_e > 0:
+        sim.set_sort_period(ELECTRON, args.sort_period_e)
+    if args.sort_period_i > 0:
+        sim.set_sort_period(ION, args.sort_period_i)
     sim.bootstrap()
     sim.profile_enable(True)
     sim.step(args.warmup)
@@ -351,6 +355,8 @@ def main():
     ap.add_argument("--cells", type=int, default=1024)
     ap.add_argument("--particles", type=float, default=1e9, help="total particles (both species, all ranks)")
     ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--sort-period-e", type=int, default=0, help="steps between electron tile sorts (0: library default)")
+    ap.add_argument("--sort-period-i", type=int, default=0, help="steps between ion tile sorts (0: library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-particles", type=int, default=4_000_000, help="particles/species of the CPU sample")

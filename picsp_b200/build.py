@@ -49,7 +49,8 @@ def _stale(target):
 def build(force: bool = False, verbose: bool = False) -> str:
     cu, cpp = _sources()
     if force or _stale(LIB):
-        cmd = [NVCC, *ARCH, *COMMON, "-shared", "-o", LIB, *cu, *cpp, "-lcufft", "-ldl",
+        extra = os.environ.get("PICSP_NVCC_DEFINES", "").split()     # e.g. "-DPICSP_CHUNK=4096" for tuning sweeps
+        cmd = [NVCC, *ARCH, *COMMON, *extra, "-shared", "-o", LIB, *cu, *cpp, "-lcufft", "-ldl",
                "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

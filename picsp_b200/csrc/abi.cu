@@ -362,7 +362,7 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
             dalloc(&sp.den, g.nn); dalloc(&sp.acc, g.nn); dalloc(&sp.frac, 1);
             dalloc(&sp.hist, (size_t)g.ntx * g.nty); dalloc(&sp.hist_next, (size_t)g.ntx * g.nty);
             dalloc(&sp.counters, 2);
-            sp.sort_period = (s == 0) ? 64 : 8;
+            sp.sort_period = (s == 0) ? 96 : 12;
             sp.max_chunks = sp.cap / CHUNK + (long long)g.ntx * g.nty + 1;
             dalloc(&sp.tile_off, (size_t)g.ntx * g.nty + 1);
             dalloc((Chunk **)&sp.chunks, (size_t)sp.max_chunks);
@@ -676,7 +676,7 @@ int picsp_straggler_count(picsp_ctx *c, int s, int64_t *n) {
 int picsp_set_sort_period(picsp_ctx *c, int s, int period) {
     PICSP_API_BEGIN
     check_ctx(c); check_species(s);
-    c->sp[s].sort_period = period > 0 ? period : (s == 0 ? 64 : 8);
+    c->sp[s].sort_period = period > 0 ? period : (s == 0 ? 96 : 12);
     PICSP_API_END
 }
 

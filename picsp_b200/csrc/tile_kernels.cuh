@@ -1,7 +1,7 @@
 // picsp_b200/csrc/tile_kernels.cuh — the tile-binned fast path of the particle loop.
 //
 // Particles are kept binned by TILE x TILE-cell tile (periodic counting sort, every few
-// steps).  One CTA processes one CHUNK (<= 2048 consecutive particles of one bin):
+// steps).  One CTA processes one CHUNK (<= 4096 consecutive particles of one bin):
 //   * the E field of the tile plus a HALO-cell ring is staged in shared memory by ONE TMA
 //     tensor copy (cp.async.bulk.tensor.2d, zero-filled outside the grid),
 //   * the mover (pushSpecies + gather, src/main.cpp:772-847, :671-681) gathers from that
@@ -23,11 +23,20 @@
 
 namespace picsp {
 
-constexpr int HALO = 4;                       // cells of drift a window tolerates on each side
-constexpr int WIN = TILE + 1 + 2 * HALO;      // window edge in nodes (25)
-constexpr int CHUNK = 2048;                   // particles per CTA work item
+#ifndef PICSP_HALO
+#define PICSP_HALO 6
+#endif
+#ifndef PICSP_CHUNK
+#define PICSP_CHUNK 4096
+#endif
+constexpr int HALO = PICSP_HALO;              // cells of drift a window tolerates on each side
+constexpr int WIN = TILE + 1 + 2 * HALO;      // window edge in nodes (29)
+constexpr int CHUNK = PICSP_CHUNK;            // particles per CTA work item
 constexpr int MAX_FRAC_TILED = 51;            // w*2^frac <= 2^51 keeps (w*2^frac + 2^52) below 2^53: the magic-number conversion is exact
-constexpr int MOVER_THREADS = 256;
+#ifndef PICSP_MOVER_THREADS
+#define PICSP_MOVER_THREADS 256
+#endif
+constexpr int MOVER_THREADS = PICSP_MOVER_THREADS;
 #ifndef PICSP_MOVER_MIN_CTAS
 #define PICSP_MOVER_MIN_CTAS 4
 #endif
