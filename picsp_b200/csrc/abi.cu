@@ -204,7 +204,18 @@ void op_solve_spectral(picsp_ctx *c) {
 void op_solve_sor(picsp_ctx *c) {
     PhaseScope ph(c, PICSP_PHASE_SOLVE);
     const Geom &g = c->g;
-    PICSP_LAUNCH(c, k_sor_solve, 1, 1024, 0, c->phi, c->rho, g.nix, g.niy, g.dx, g.dx, c->d_sor_status, c->d_scalars + 3, 200000);
+    const int bands = (g.nix + SOR_ROWS - 1) / SOR_ROWS;
+    if (bands <= c->num_sms && !(c->prm.flags & PICSP_FLAG_SOR_SINGLE_CTA)) {
+        // sweep 0 pipelined over co-resident bands, then the reference's convergence test; further sweeps
+        // (never needed in practice) fall through to the single-CTA kernel
+        PICSP_CUDA(cudaMemsetAsync(c->d_sor_progress, 0, sizeof(int) * bands, c->stream));
+        PICSP_LAUNCH(c, k_sor_sweep_pipelined, bands, SOR_ROWS, 0, c->phi, c->rho, g.nix, g.niy, g.dx, g.dx, c->d_sor_progress);
+        PICSP_LAUNCH(c, k_sor_residual_partial, RED_BLOCKS, RED_THREADS, 0, c->phi, c->rho, g.nix, g.niy, g.dx, c->d_red);
+        PICSP_LAUNCH(c, k_sor_residual_final, 1, 1024, 0, c->d_red, RED_BLOCKS, g.nix, g.niy, c->d_sor_status, c->d_scalars + 3);
+        PICSP_LAUNCH(c, k_sor_solve, 1, 1024, 0, c->phi, c->rho, g.nix, g.niy, g.dx, g.dx, c->d_sor_status, c->d_scalars + 3, 200000, 1);
+    } else {
+        PICSP_LAUNCH(c, k_sor_solve, 1, 1024, 0, c->phi, c->rho, g.nix, g.niy, g.dx, g.dx, c->d_sor_status, c->d_scalars + 3, 200000, 0);
+    }
 }
 
 void op_solve(picsp_ctx *c) {
@@ -381,7 +392,7 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
         PICSP_CUDA(cudaMemsetAsync(c->phi, 0, sizeof(double) * g.nn, c->stream));
         PICSP_CUDA(cudaMemsetAsync(c->E_alloc, 0, sizeof(double2) * (g.nn + 2 * g.guard), c->stream));
         make_tensor_map(c);
-        dalloc(&c->d_red, RED_BLOCKS); dalloc(&c->d_scalars, 8); dalloc(&c->d_sor_status, 2); dalloc(&c->d_error, 1);
+        dalloc(&c->d_red, RED_BLOCKS); dalloc(&c->d_scalars, 8); dalloc(&c->d_sor_status, 2); dalloc(&c->d_sor_progress, (size_t)(g.nix + SOR_ROWS - 1) / SOR_ROWS + 1); dalloc(&c->d_error, 1);
         PICSP_CUDA(cudaMemsetAsync(c->d_scalars, 0, sizeof(double) * 8, c->stream));
         PICSP_CUDA(cudaMemsetAsync(c->d_sor_status, 0, sizeof(long long) * 2, c->stream));
         PICSP_CUDA(cudaMemsetAsync(c->d_error, 0, sizeof(int), c->stream));
@@ -422,7 +433,7 @@ void picsp_destroy(picsp_ctx *c) {
         cudaFree(sp.tile_off); cudaFree(sp.chunks); cudaFree(sp.nchunks); cudaFree(sp.cursor);
     }
     cudaFree(c->rho); cudaFree(c->phi); cudaFree(c->E_alloc); cudaFree(c->rhok); cudaFree(c->phik);
-    cudaFree(c->d_red); cudaFree(c->d_scalars); cudaFree(c->d_sor_status); cudaFree(c->d_error); cudaFree(c->stage);
+    cudaFree(c->d_red); cudaFree(c->d_scalars); cudaFree(c->d_sor_status); cudaFree(c->d_sor_progress); cudaFree(c->d_error); cudaFree(c->stage);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto &t : c->timers) for (auto e : t.pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);

@@ -115,6 +115,7 @@ struct picsp_ctx {
     double *d_red = nullptr;        // reduction partials
     double *d_scalars = nullptr;    // [0..7] results (ke, maxphi, phi0, sor l2, ...)
     long long *d_sor_status = nullptr;
+    int *d_sor_progress = nullptr;  // per-band column progress of the pipelined SOR sweep
     int *d_error = nullptr;         // sticky device-side error flag
     double *h_pinned = nullptr;     // small pinned staging for scalar read-backs
 

@@ -111,18 +111,32 @@ __global__ void k_kspace_green(const cufftDoubleComplex *__restrict__ rhok, cuff
 // reference does (in practice the first test passes: one sweep per call, Q6).
 // status[0] = sweeps done (negative: cap hit), d_l2 = last L2.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double *s_red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (blockDim.x + 31) / 32; w++) t += s_red[w];
+    return t;   // valid on thread 0
+}
+
 __device__ __forceinline__ double ldcg(const double *p) { return __ldcg(p); }
 
 __global__ void __launch_bounds__(1024, 1)
 k_sor_solve(double *phi, const double *__restrict__ rho, int nix, int niy, double dx, double dy,
-            long long *status, double *d_l2, int max_sweeps) {
+            long long *status, double *d_l2, int max_sweeps, int first_sweep) {
     __shared__ double s_red[32];
     __shared__ double s_l2;
     const double dx2 = dx * dx, dy2 = dy * dy, eps = 1.0;
     const double coef = 0.5 * (1 / ((1 / dx2) + (1 / dy2)));
     const int tid = threadIdx.x, nt = blockDim.x;
     double L2 = 0.0;
-    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+    if (first_sweep > 0) {            // sweep 0 and its convergence test were done by the pipelined kernels
+        if (status[0] == 1) return;   // converged after one sweep (the usual case)
+        L2 = *d_l2;
+    }
+    for (int sweep = first_sweep; sweep < max_sweeps; sweep++) {
         for (int d = 0; d <= nix + niy - 2; d++) {
             int i_lo = d - (niy - 1); if (i_lo < 0) i_lo = 0;
             int i_hi = d < nix - 1 ? d : nix - 1;
@@ -176,6 +190,124 @@ k_sor_solve(double *phi, const double *__restrict__ rho, int nix, int niy, doubl
 }
 
 // ---------------------------------------------------------------------------
+// SOR sweep 0, pipelined across CTAs (same lexicographic iterate as k_sor_solve).
+//
+// One thread per grid row i; thread t of band b owns row i = b*SOR_ROWS + t and visits the
+// columns j = s - t at band step s, so the threads of a band form a skewed wavefront.  What a
+// node needs (src/main.cpp:916-924):
+//   new phi(i-1, j)  - produced ONE step earlier by thread t-1: handed over in shared memory;
+//                      for t == 0 it comes from the previous band through global memory, gated by
+//                      that band's published progress (checked once per 32 columns);
+//                      for i == 0 it is the OLD phi(nix-2, j) (periodic wrap), read before the last
+//                      band can overwrite it (that band transitively waits on this one)
+//   new phi(i, j-1)  - this thread's previous result (register); OLD phi(i, niy-2) for j == 0
+//   old phi(i+1, j), old phi(i, j+1), rho(i, j) - not yet written this sweep: plain (L1-cached,
+//                      software-prefetched) global loads; NEW phi(1, j) for i == nix-1 and this
+//                      thread's saved NEW phi(i, 1) for j == niy-1 (periodic wraps)
+// so a step costs one shared-memory hand-over and one block barrier instead of L2 round trips.
+// Bands must be co-resident (grid = ceil(nix/SOR_ROWS) <= #SMs, enforced by the launcher).
+// ---------------------------------------------------------------------------
+constexpr int SOR_ROWS = 64;
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+__global__ void __launch_bounds__(SOR_ROWS, 1)
+k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int niy, double dx, double dy,
+                      int *progress) {
+    __shared__ double s_new[2][SOR_ROWS];
+    const int t = threadIdx.x, b = blockIdx.x;
+    const int i = b * SOR_ROWS + t;
+    const bool active = i < nix;
+    const int rows_here = min(SOR_ROWS, nix - b * SOR_ROWS);
+    const bool last_row_of_band = (t == rows_here - 1);
+    const double dx2 = dx * dx, dy2 = dy * dy, eps = 1.0;
+    const double coef = 0.5 * (1 / ((1 / dx2) + (1 / dy2)));
+    const int q_row = (i + 1 > nix - 1) ? 1 : i + 1;          // src/main.cpp:917
+    const int p_row = (i - 1 < 0) ? nix - 2 : i - 1;          // src/main.cpp:916
+    const double *row = phi + (long long)i * niy;
+    const double *row_q = phi + (long long)q_row * niy;
+    const double *row_p = phi + (long long)p_row * niy;
+    const double *rrho = rho + (long long)i * niy;
+    const bool q_is_new = (i == nix - 1);                     // wraps to row 1, already swept
+    const bool p_from_global = (t == 0);                      // previous band's last row, or the i == 0 wrap (old)
+
+    double left = 0.0, center = 0.0, saved_col1 = 0.0;
+    if (active) { left = __ldcg(&row[niy - 2]); center = __ldcg(&row[0]); }   // r wrap for j == 0 (old), phi_old(i,0)
+    int granted = (b == 0) ? niy : 0;                         // columns of the previous band known to be complete
+    const int nsteps = niy + rows_here - 1;
+    for (int s = 0; s < nsteps; s++) {
+        const int j = s - t;
+        const bool work = active && j >= 0 && j < niy;
+        double v = 0.0;
+        if (work) {
+            if (j + 8 < niy) { prefetch_l1(&row[j + 8]); prefetch_l1(&rrho[j + 8]); if (!q_is_new) prefetch_l1(&row_q[j + 8]); }
+            // independent operands first (old values / own registers)
+            const int sj = (j + 1 > niy - 1) ? 1 : j + 1;                           // src/main.cpp:919
+            const double right = (j == niy - 1) ? saved_col1 : row[sj];             // old phi(i,j+1) | new phi(i,1)
+            const double down = q_is_new ? __ldcg(&row_q[j]) : row_q[j];            // new phi(1,j) | old phi(i+1,j)
+            const double rh = rrho[j];
+            double up;
+            if (p_from_global) {
+                if (b > 0 && j >= granted) {      // wait for the previous band, 32 columns at a time
+                    const int want = min(j + 32, niy);
+                    while ((granted = *(volatile int *)&progress[b - 1]) < want) { }
+                    __threadfence();
+                }
+                up = __ldcg(&row_p[j]);
+            } else {
+                up = s_new[(s + 1) & 1][t - 1];   // written at step s-1 by thread t-1
+            }
+            const double g = coef * (((up + down) / dx2) + ((left + right) / dy2) + (rh / eps));
+            v = center + 1.4 * (g - center);
+            __stcg(&phi[(long long)i * niy + j], v);
+            s_new[s & 1][t] = v;
+            if (j == 1) saved_col1 = v;
+            left = v;
+            center = right;                       // phi_old(i, j+1) is the next centre
+            if (last_row_of_band && ((j & 15) == 15 || j == niy - 1)) {
+                __threadfence();
+                *(volatile int *)&progress[b] = j + 1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// residual of the reference's convergence test (src/main.cpp:930-950), multi-CTA, fixed tree
+__global__ void k_sor_residual_partial(const double *__restrict__ phi, const double *__restrict__ rho, int nix, int niy,
+                                       double dx, double *__restrict__ partial) {
+    __shared__ double s_red[32];
+    const double dx2 = dx * dx, eps = 1.0;
+    const long long nn = (long long)nix * niy;
+    double sum = 0.0;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nn; k += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(k / niy), j = (int)(k % niy);
+        int p = i - 1; if (p < 0) p = nix - 2;
+        int q = i + 1; if (q > nix - 1) q = 1;
+        int r = j - 1; if (r < 0) r = niy - 2;
+        int s = j + 1; if (s > niy - 1) s = 1;
+        double R = 0.25 * (phi[(long long)p * niy + j] + phi[(long long)q * niy + j] + phi[(long long)i * niy + r] +
+                           phi[(long long)i * niy + s] + (dx2 * rho[k] / eps)) - phi[k];
+        sum = sum + (R * R);
+    }
+    double tsum = block_sum(sum, s_red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = tsum;
+}
+// status[0] = 1 (converged after 1 sweep) or 0 (keep sweeping); d_l2 = L2
+__global__ void k_sor_residual_final(const double *__restrict__ partial, int n, int nix, int niy, long long *status,
+                                     double *d_l2) {
+    __shared__ double s_red[32];
+    double s = 0.0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) s += partial[k];
+    double t = block_sum(s, s_red);
+    if (threadIdx.x == 0) {
+        double L2 = sqrt(t) / (nix * niy);
+        *d_l2 = L2;
+        status[0] = (L2 < 1e-2) ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // E field (src/main.cpp:1111-1139).  Interior: central differences.  Rows i = 0 and
 // i = nix-1 get the one-sided efx (divided by 2*dx as the reference does), columns
 // j = 0 and j = niy-1 the one-sided efy.  efx[i][0], efx[i][niy-1] for interior i
@@ -219,16 +351,6 @@ __global__ void k_ef_set_component(double2 *__restrict__ E, const double *__rest
 // ---------------------------------------------------------------------------
 constexpr int RED_BLOCKS = 592;   // 4 per SM on 148 SMs
 constexpr int RED_THREADS = 256;
-
-__device__ __forceinline__ double block_sum(double v, double *s_red) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-    if (threadIdx.x == 0)
-        for (int w = 0; w < (blockDim.x + 31) / 32; w++) t += s_red[w];
-    return t;   // valid on thread 0
-}
 
 __global__ void k_ke_partial(const double *__restrict__ vx, const double *__restrict__ vy, long long n,
                              double *__restrict__ partial) {

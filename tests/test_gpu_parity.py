@@ -160,6 +160,71 @@ def test_sort_period_does_not_change_results(period):
 
 
 @pytest.mark.parametrize("flags", [0, 2], ids=["tiled", "unsorted"])
+@pytest.mark.parametrize("solver", [1, 2])
+@pytest.mark.parametrize("numx,numy", [(40, 72), (130, 33), (200, 64)])
+def test_rectangular_grids(solver, numx, numy):
+    """numxCells != numyCells (the reference allows it): bootstrap + 3 steps vs the oracle."""
+    nm = normalise()
+    n = 30_000
+    o = Oracle(numx, numy, nm["dx"], nm["dt"], nm["mass_i"], n, n, vth_i=nm["vth_i"], solver=solver)
+    o.seed(5); o.init(ION, 1); o.init(ELECTRON, 1)
+    with Simulation(Params(numx, numy, nm["dx"], nm["dt"], nm["mass_i"], n, n, solverType=solver)) as sim:
+        for s in (ION, ELECTRON):
+            sim.set_species(s, *o.get_species(s))
+        o.bootstrap(); sim.bootstrap()
+        o.step(3); sim.step(3)
+        for name in GRIDS:
+            assert_grid_close(sim.grid(name), o.grid(name), sim.nix, sim.niy, 10 * RTOL, name)
+        for s in (ION, ELECTRON):
+            got, want = sim.get_species(s), o.get_species(s)
+            for k in range(4):
+                assert relerr(got[k], want[k]) <= 10 * RTOL
+
+
+@pytest.mark.parametrize("numx,numy", [(24, 24), (64, 64), (150, 70), (512, 512)])
+def test_sor_pipelined_equals_single_cta_and_oracle(numx, numy):
+    """One SOR call (solvePotential, main.cpp:904-957) from a warm-start phi: the pipelined multi-CTA sweep,
+    the single-CTA anti-diagonal sweep and the oracle's lexicographic loop give the same iterate."""
+    nm = normalise()
+    rng = np.random.default_rng(12)
+    nix, niy = numx + 1, numy + 1
+    rho = np.zeros((nix, niy)); rho[1:-1, 1:-1] = rng.standard_normal((nix - 2, niy - 2))
+    phi0 = 1e-3 * rng.standard_normal((nix, niy))
+    o = Oracle(numx, numy, nm["dx"], nm["dt"], nm["mass_i"], 8, 8, solver=2)
+    o.set_grid("rho", rho); o.set_grid("phi", phi0)
+    assert o.solvePotential() and o.last_sweeps == 1
+    res = []
+    for flags in (0, 8):
+        with Simulation(Params(numx, numy, nm["dx"], nm["dt"], nm["mass_i"], 8, 8, solverType=2, flags=flags)) as sim:
+            sim.set_grid("rho", rho); sim.set_grid("phi", phi0)
+            sim.solvePotential()
+            assert sim.last_sweeps == 1
+            assert abs(sim.last_l2 - o.last_l2) <= 1e-9 * o.last_l2
+            res.append(sim.grid("phi"))
+    assert relerr(res[0], o.phi) <= RTOL and relerr(res[1], o.phi) <= RTOL
+    assert np.array_equal(res[0], res[1]), "pipelined and single-CTA sweeps must be the same arithmetic"
+
+
+def test_sor_multiple_sweeps_when_first_test_fails():
+    """A source large enough that the reference's L2 < 1e-2 test fails after sweep 0: 101 sweeps, then converged."""
+    nm = normalise()
+    numx = 20
+    nix = numx + 1
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((nix - 2, nix - 2)); base -= base.mean()
+    rho = np.zeros((nix, nix)); rho[1:-1, 1:-1] = 3e4 * base
+    o = Oracle(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], 8, 8, solver=2)
+    o.set_grid("rho", rho)
+    assert o.solvePotential()
+    assert o.last_sweeps == 101, o.last_sweeps
+    for flags in (0, 8):
+        with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], 8, 8, solverType=2, flags=flags)) as sim:
+            sim.set_grid("rho", rho)
+            sim.solvePotential()
+            assert sim.last_sweeps == o.last_sweeps
+            assert relerr(sim.grid("phi"), o.phi) <= 1e-10
+
+
 def test_density_is_deterministic_and_order_independent(flags):
     """Fixed-point accumulation: bit-identical density for any particle order and on repeat
     (within one code path; the tiled and unsorted paths round weights at different scales)."""
