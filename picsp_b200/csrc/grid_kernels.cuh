@@ -208,13 +208,17 @@ k_sor_solve(double *phi, const double *__restrict__ rho, int nix, int niy, doubl
 // Bands must be co-resident (grid = ceil(nix/SOR_ROWS) <= #SMs, enforced by the launcher).
 // ---------------------------------------------------------------------------
 constexpr int SOR_ROWS = 64;
+constexpr int SOR_DEPTH = 8;     // columns each thread keeps in flight in registers
 
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
+// A store to phi(i,j) invalidates the L1 line that also holds phi(i,j+1..), so "old" operands
+// cannot be served from L1; instead every thread keeps the operands of its next SOR_DEPTH columns
+// in a register ring (slot = step % SOR_DEPTH, a compile-time index after unrolling), loaded
+// SOR_DEPTH steps before use, which hides the L2 latency.
 __global__ void __launch_bounds__(SOR_ROWS, 1)
 k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int niy, double dx, double dy,
                       int *progress) {
     __shared__ double s_new[2][SOR_ROWS];
+    constexpr int D = SOR_DEPTH;
     const int t = threadIdx.x, b = blockIdx.x;
     const int i = b * SOR_ROWS + t;
     const bool active = i < nix;
@@ -224,52 +228,66 @@ k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int 
     const double coef = 0.5 * (1 / ((1 / dx2) + (1 / dy2)));
     const int q_row = (i + 1 > nix - 1) ? 1 : i + 1;          // src/main.cpp:917
     const int p_row = (i - 1 < 0) ? nix - 2 : i - 1;          // src/main.cpp:916
-    const double *row = phi + (long long)i * niy;
-    const double *row_q = phi + (long long)q_row * niy;
-    const double *row_p = phi + (long long)p_row * niy;
-    const double *rrho = rho + (long long)i * niy;
-    const bool q_is_new = (i == nix - 1);                     // wraps to row 1, already swept
-    const bool p_from_global = (t == 0);                      // previous band's last row, or the i == 0 wrap (old)
+    const double *row = phi + (long long)(active ? i : 0) * niy;
+    const double *row_q = phi + (long long)(active ? q_row : 0) * niy;
+    const double *row_p = phi + (long long)(active ? p_row : 0) * niy;
+    const double *rrho = rho + (long long)(active ? i : 0) * niy;
+    // row nix-1 reads the NEW phi(1, j); it may be fetched ahead only if row 1 is far enough in front
+    const bool q_is_new = (i == nix - 1);
+    const bool q_prefetch_ok = !q_is_new || (nix > D + 8);
+    const bool up_from_global = (t == 0);   // previous band's last row (b > 0), or the i == 0 wrap (old values)
+
+    double r_right[D], r_down[D], r_rho[D], r_up[D];
+    int granted = (b == 0) ? niy : 0;       // columns of the previous band known to be complete (thread 0 only)
+
+    // operands of column jj into ring slot k
+    auto fetch = [&](int k, int jj) {
+        if (!active || jj < 0 || jj >= niy) return;
+        if (up_from_global && b > 0 && jj >= granted) {                 // wait for the previous band, >= 32 columns at a time
+            const int want = min(jj + 32, niy);
+            while ((granted = *(volatile int *)&progress[b - 1]) < want) { }
+            __threadfence();                                            // acquire: also orders the loads below
+        }
+        const int sj = (jj + 1 > niy - 1) ? 1 : jj + 1;                 // src/main.cpp:919
+        r_right[k] = (jj == niy - 1) ? 0.0 : __ldcg(&row[sj]);          // old phi(i,jj+1); the j == niy-1 wrap uses saved_col1
+        r_down[k] = q_prefetch_ok ? __ldcg(&row_q[jj]) : 0.0;           // old phi(i+1,jj) | new phi(1,jj)
+        r_rho[k] = rrho[jj];
+        if (up_from_global) r_up[k] = __ldcg(&row_p[jj]);
+    };
 
     double left = 0.0, center = 0.0, saved_col1 = 0.0;
     if (active) { left = __ldcg(&row[niy - 2]); center = __ldcg(&row[0]); }   // r wrap for j == 0 (old), phi_old(i,0)
-    int granted = (b == 0) ? niy : 0;                         // columns of the previous band known to be complete
+#pragma unroll
+    for (int k = 0; k < D; k++) fetch(k, k - t);
+
     const int nsteps = niy + rows_here - 1;
-    for (int s = 0; s < nsteps; s++) {
-        const int j = s - t;
-        const bool work = active && j >= 0 && j < niy;
-        double v = 0.0;
-        if (work) {
-            if (j + 8 < niy) { prefetch_l1(&row[j + 8]); prefetch_l1(&rrho[j + 8]); if (!q_is_new) prefetch_l1(&row_q[j + 8]); }
-            // independent operands first (old values / own registers)
-            const int sj = (j + 1 > niy - 1) ? 1 : j + 1;                           // src/main.cpp:919
-            const double right = (j == niy - 1) ? saved_col1 : row[sj];             // old phi(i,j+1) | new phi(i,1)
-            const double down = q_is_new ? __ldcg(&row_q[j]) : row_q[j];            // new phi(1,j) | old phi(i+1,j)
-            const double rh = rrho[j];
-            double up;
-            if (p_from_global) {
-                if (b > 0 && j >= granted) {      // wait for the previous band, 32 columns at a time
-                    const int want = min(j + 32, niy);
-                    while ((granted = *(volatile int *)&progress[b - 1]) < want) { }
-                    __threadfence();
+    for (int s0 = 0; s0 < nsteps; s0 += D) {
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const int s = s0 + k;
+            if (s < nsteps) {               // uniform across the CTA
+                const int j = s - t;
+                const bool work = active && j >= 0 && j < niy;
+                if (work) {
+                    const double right = (j == niy - 1) ? saved_col1 : r_right[k];
+                    const double down = q_prefetch_ok ? r_down[k] : __ldcg(&row_q[j]);
+                    const double up = up_from_global ? r_up[k] : s_new[(s + 1) & 1][t - 1];   // written at step s-1 by thread t-1
+                    const double g = coef * (((up + down) / dx2) + ((left + right) / dy2) + (r_rho[k] / eps));
+                    const double v = center + 1.4 * (g - center);
+                    __stcg(&phi[(long long)i * niy + j], v);
+                    s_new[s & 1][t] = v;
+                    if (j == 1) saved_col1 = v;
+                    left = v;
+                    center = right;         // phi_old(i, j+1) is the next centre
+                    if (last_row_of_band && ((j & 15) == 15 || j == niy - 1)) {
+                        __threadfence();
+                        *(volatile int *)&progress[b] = j + 1;
+                    }
                 }
-                up = __ldcg(&row_p[j]);
-            } else {
-                up = s_new[(s + 1) & 1][t - 1];   // written at step s-1 by thread t-1
-            }
-            const double g = coef * (((up + down) / dx2) + ((left + right) / dy2) + (rh / eps));
-            v = center + 1.4 * (g - center);
-            __stcg(&phi[(long long)i * niy + j], v);
-            s_new[s & 1][t] = v;
-            if (j == 1) saved_col1 = v;
-            left = v;
-            center = right;                       // phi_old(i, j+1) is the next centre
-            if (last_row_of_band && ((j & 15) == 15 || j == niy - 1)) {
-                __threadfence();
-                *(volatile int *)&progress[b] = j + 1;
+                fetch(k, j + D);            // refill this slot for step s + D
+                __syncthreads();
             }
         }
-        __syncthreads();
     }
 }
 

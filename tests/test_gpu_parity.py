@@ -159,7 +159,6 @@ def test_sort_period_does_not_change_results(period):
                 assert relerr(got[k], want[k]) <= 100 * RTOL
 
 
-@pytest.mark.parametrize("flags", [0, 2], ids=["tiled", "unsorted"])
 @pytest.mark.parametrize("solver", [1, 2])
 @pytest.mark.parametrize("numx,numy", [(40, 72), (130, 33), (200, 64)])
 def test_rectangular_grids(solver, numx, numy):
@@ -225,6 +224,7 @@ def test_sor_multiple_sweeps_when_first_test_fails():
             assert relerr(sim.grid("phi"), o.phi) <= 1e-10
 
 
+@pytest.mark.parametrize("flags", [0, 2], ids=["tiled", "unsorted"])
 def test_density_is_deterministic_and_order_independent(flags):
     """Fixed-point accumulation: bit-identical density for any particle order and on repeat
     (within one code path; the tiled and unsorted paths round weights at different scales)."""
