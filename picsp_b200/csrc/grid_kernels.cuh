@@ -238,12 +238,15 @@ k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int 
     const bool up_from_global = (t == 0);   // previous band's last row (b > 0), or the i == 0 wrap (old values)
 
     double r_right[D], r_down[D], r_rho[D], r_up[D];
-    int granted = (b == 0) ? niy : 0;       // columns of the previous band known to be complete (thread 0 only)
+    int granted = (b == 0) ? niy : 0;       // columns of the previous band known to be complete (polling threads only)
 
     // operands of column jj into ring slot k
     auto fetch = [&](int k, int jj) {
         if (!active || jj < 0 || jj >= niy) return;
-        if (up_from_global && b > 0 && jj >= granted) {                 // wait for the previous band, >= 32 columns at a time
+        // Threads that read values ANOTHER band produces this sweep — thread 0 (new phi(i-1,.)) and the row
+        // nix-1 (new phi(1,.), implied by the previous band's progress) — wait for the previous band first,
+        // >= 32 columns at a time.  (This also covers the fetches issued before the first barrier.)
+        if ((up_from_global || q_is_new) && b > 0 && jj >= granted) {
             const int want = min(jj + 32, niy);
             while ((granted = *(volatile int *)&progress[b - 1]) < want) { }
             __threadfence();                                            // acquire: also orders the loads below

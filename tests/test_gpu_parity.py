@@ -180,7 +180,7 @@ def test_rectangular_grids(solver, numx, numy):
                 assert relerr(got[k], want[k]) <= 10 * RTOL
 
 
-@pytest.mark.parametrize("numx,numy", [(24, 24), (64, 64), (150, 70), (512, 512)])
+@pytest.mark.parametrize("numx,numy", [(24, 24), (64, 64), (65, 40), (130, 33), (150, 70), (197, 9), (512, 512)])
 def test_sor_pipelined_equals_single_cta_and_oracle(numx, numy):
     """One SOR call (solvePotential, main.cpp:904-957) from a warm-start phi: the pipelined multi-CTA sweep,
     the single-CTA anti-diagonal sweep and the oracle's lexicographic loop give the same iterate."""
