@@ -208,17 +208,28 @@ k_sor_solve(double *phi, const double *__restrict__ rho, int nix, int niy, doubl
 // Bands must be co-resident (grid = ceil(nix/SOR_ROWS) <= #SMs, enforced by the launcher).
 // ---------------------------------------------------------------------------
 constexpr int SOR_ROWS = 64;
-constexpr int SOR_DEPTH = 8;     // columns each thread keeps in flight in registers
+constexpr int SOR_DEPTH = 8;     // columns each thread keeps in flight
 
-// A store to phi(i,j) invalidates the L1 line that also holds phi(i,j+1..), so "old" operands
-// cannot be served from L1; instead every thread keeps the operands of its next SOR_DEPTH columns
-// in a register ring (slot = step % SOR_DEPTH, a compile-time index after unrolling), loaded
-// SOR_DEPTH steps before use, which hides the L2 latency.
+// A store to phi(i,j) invalidates the L1 line that also holds phi(i,j+1..), so the "old" operands
+// cannot be served from L1, and deep register prefetching is defeated by the counting scoreboard
+// (a wait on an old load also waits for the younger loads sharing its slot).  Instead every thread
+// streams the operands of its next SOR_DEPTH columns through a private shared-memory ring with
+// cp.async (LDGSTS, L2-only, completion tracked by cp.async groups, not the scoreboard).  cp.async.cg
+// moves 16 aligned bytes, so the aligned pair containing the wanted double is fetched.
+__device__ __forceinline__ void sor_cp_async16(void *smem_dst, const double *gmem_elem) {
+    const unsigned long long a = reinterpret_cast<unsigned long long>(gmem_elem) & ~15ull;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(a) : "memory");
+}
+__device__ __forceinline__ double sor_pick(const double2 &pair, const double *gmem_elem) {
+    return (reinterpret_cast<unsigned long long>(gmem_elem) & 8ull) ? pair.y : pair.x;
+}
+
 __global__ void __launch_bounds__(SOR_ROWS, 1)
 k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int niy, double dx, double dy,
                       int *progress) {
-    __shared__ double s_new[2][SOR_ROWS];
     constexpr int D = SOR_DEPTH;
+    __shared__ double s_new[2][SOR_ROWS];
+    __shared__ __align__(16) double2 s_ring[D][4][SOR_ROWS];   // [slot][right, down, rho, up][thread]
     const int t = threadIdx.x, b = blockIdx.x;
     const int i = b * SOR_ROWS + t;
     const bool active = i < nix;
@@ -236,26 +247,25 @@ k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int 
     const bool q_is_new = (i == nix - 1);
     const bool q_prefetch_ok = !q_is_new || (nix > D + 8);
     const bool up_from_global = (t == 0);   // previous band's last row (b > 0), or the i == 0 wrap (old values)
-
-    double r_right[D], r_down[D], r_rho[D], r_up[D];
     int granted = (b == 0) ? niy : 0;       // columns of the previous band known to be complete (polling threads only)
 
-    // operands of column jj into ring slot k
+    // start the copies of column jj's operands into ring slot k (one cp.async group per call)
     auto fetch = [&](int k, int jj) {
-        if (!active || jj < 0 || jj >= niy) return;
-        // Threads that read values ANOTHER band produces this sweep — thread 0 (new phi(i-1,.)) and the row
-        // nix-1 (new phi(1,.), implied by the previous band's progress) — wait for the previous band first,
-        // >= 32 columns at a time.  (This also covers the fetches issued before the first barrier.)
-        if ((up_from_global || q_is_new) && b > 0 && jj >= granted) {
-            const int want = min(jj + 32, niy);
-            while ((granted = *(volatile int *)&progress[b - 1]) < want) { }
-            __threadfence();                                            // acquire: also orders the loads below
+        if (active && jj >= 0 && jj < niy) {
+            // Threads that read values ANOTHER band produces this sweep — thread 0 (new phi(i-1,.)) and the row
+            // nix-1 (new phi(1,.), implied by the previous band's progress) — wait for the previous band first,
+            // >= 32 columns at a time.  (This also covers the fetches issued before the first barrier.)
+            if ((up_from_global || q_is_new) && b > 0 && jj >= granted) {
+                const int want = min(jj + 32, niy);
+                while ((granted = *(volatile int *)&progress[b - 1]) < want) { }
+                __threadfence();
+            }
+            if (jj < niy - 1) sor_cp_async16(&s_ring[k][0][t], &row[jj + 1]);      // old phi(i,jj+1); jj == niy-1 uses saved_col1
+            if (q_prefetch_ok) sor_cp_async16(&s_ring[k][1][t], &row_q[jj]);       // old phi(i+1,jj) | new phi(1,jj)
+            sor_cp_async16(&s_ring[k][2][t], &rrho[jj]);
+            if (up_from_global) sor_cp_async16(&s_ring[k][3][t], &row_p[jj]);
         }
-        const int sj = (jj + 1 > niy - 1) ? 1 : jj + 1;                 // src/main.cpp:919
-        r_right[k] = (jj == niy - 1) ? 0.0 : __ldcg(&row[sj]);          // old phi(i,jj+1); the j == niy-1 wrap uses saved_col1
-        r_down[k] = q_prefetch_ok ? __ldcg(&row_q[jj]) : 0.0;           // old phi(i+1,jj) | new phi(1,jj)
-        r_rho[k] = rrho[jj];
-        if (up_from_global) r_up[k] = __ldcg(&row_p[jj]);
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
     double left = 0.0, center = 0.0, saved_col1 = 0.0;
@@ -271,11 +281,14 @@ k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int 
             if (s < nsteps) {               // uniform across the CTA
                 const int j = s - t;
                 const bool work = active && j >= 0 && j < niy;
+                asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");   // the group that filled slot k has landed
                 if (work) {
-                    const double right = (j == niy - 1) ? saved_col1 : r_right[k];
-                    const double down = q_prefetch_ok ? r_down[k] : __ldcg(&row_q[j]);
-                    const double up = up_from_global ? r_up[k] : s_new[(s + 1) & 1][t - 1];   // written at step s-1 by thread t-1
-                    const double g = coef * (((up + down) / dx2) + ((left + right) / dy2) + (r_rho[k] / eps));
+                    const double right = (j == niy - 1) ? saved_col1 : sor_pick(s_ring[k][0][t], &row[j + 1]);
+                    const double down = q_prefetch_ok ? sor_pick(s_ring[k][1][t], &row_q[j]) : __ldcg(&row_q[j]);
+                    const double rh = sor_pick(s_ring[k][2][t], &rrho[j]);
+                    const double up = up_from_global ? sor_pick(s_ring[k][3][t], &row_p[j])
+                                                     : s_new[(s + 1) & 1][t - 1];   // written at step s-1 by thread t-1
+                    const double g = coef * (((up + down) / dx2) + ((left + right) / dy2) + (rh / eps));
                     const double v = center + 1.4 * (g - center);
                     __stcg(&phi[(long long)i * niy + j], v);
                     s_new[s & 1][t] = v;
@@ -292,6 +305,7 @@ k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int 
             }
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // residual of the reference's convergence test (src/main.cpp:930-950), multi-CTA, fixed tree
