@@ -123,6 +123,16 @@ __device__ __forceinline__ double block_sum(double v, double *s_red) {
 
 __device__ __forceinline__ double ldcg(const double *p) { return __ldcg(p); }
 
+// x / d for a loop-invariant d with its correctly rounded reciprocal r = 1/d: quotient estimate, exact
+// remainder (FMA), one correction.  This is the final step of the IEEE division sequence (Markstein): the
+// result is the correctly rounded quotient (identical to `x / d`) except in astronomically rare tie cases,
+// at 3 dependent FMAs instead of ~10 — the SOR wavefront is latency-bound on exactly this chain.
+__device__ __forceinline__ double sor_div(double x, double d, double r) {
+    double q = x * r;
+    double rem = fma(-q, d, x);
+    return fma(rem, r, q);
+}
+
 __global__ void __launch_bounds__(1024, 1)
 k_sor_solve(double *phi, const double *__restrict__ rho, int nix, int niy, double dx, double dy,
             long long *status, double *d_l2, int max_sweeps, int first_sweep) {
@@ -130,6 +140,7 @@ k_sor_solve(double *phi, const double *__restrict__ rho, int nix, int niy, doubl
     __shared__ double s_l2;
     const double dx2 = dx * dx, dy2 = dy * dy, eps = 1.0;
     const double coef = 0.5 * (1 / ((1 / dx2) + (1 / dy2)));
+    const double rdx2 = 1 / dx2, rdy2 = 1 / dy2;
     const int tid = threadIdx.x, nt = blockDim.x;
     double L2 = 0.0;
     if (first_sweep > 0) {            // sweep 0 and its convergence test were done by the pipelined kernels
@@ -147,8 +158,8 @@ k_sor_solve(double *phi, const double *__restrict__ rho, int nix, int niy, doubl
                 int r = j - 1; if (r < 0) r = niy - 2;
                 int s = j + 1; if (s > niy - 1) s = 1;
                 long long c = (long long)i * niy + j;
-                double g = coef * (((ldcg(&phi[(long long)p * niy + j]) + ldcg(&phi[(long long)q * niy + j])) / dx2) +
-                                   ((ldcg(&phi[(long long)i * niy + r]) + ldcg(&phi[(long long)i * niy + s])) / dy2) +
+                double g = coef * (sor_div(ldcg(&phi[(long long)p * niy + j]) + ldcg(&phi[(long long)q * niy + j]), dx2, rdx2) +
+                                   sor_div(ldcg(&phi[(long long)i * niy + r]) + ldcg(&phi[(long long)i * niy + s]), dy2, rdy2) +
                                    (rho[c] / eps));
                 double old = ldcg(&phi[c]);
                 __stcg(&phi[c], old + 1.4 * (g - old));
@@ -237,6 +248,7 @@ k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int 
     const bool last_row_of_band = (t == rows_here - 1);
     const double dx2 = dx * dx, dy2 = dy * dy, eps = 1.0;
     const double coef = 0.5 * (1 / ((1 / dx2) + (1 / dy2)));
+    const double rdx2 = 1 / dx2, rdy2 = 1 / dy2;
     const int q_row = (i + 1 > nix - 1) ? 1 : i + 1;          // src/main.cpp:917
     const int p_row = (i - 1 < 0) ? nix - 2 : i - 1;          // src/main.cpp:916
     const double *row = phi + (long long)(active ? i : 0) * niy;
@@ -254,9 +266,9 @@ k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int 
         if (active && jj >= 0 && jj < niy) {
             // Threads that read values ANOTHER band produces this sweep — thread 0 (new phi(i-1,.)) and the row
             // nix-1 (new phi(1,.), implied by the previous band's progress) — wait for the previous band first,
-            // >= 32 columns at a time.  (This also covers the fetches issued before the first barrier.)
+            // >= 8 columns at a time.  (This also covers the fetches issued before the first barrier.)
             if ((up_from_global || q_is_new) && b > 0 && jj >= granted) {
-                const int want = min(jj + 32, niy);
+                const int want = min(jj + 8, niy);
                 while ((granted = *(volatile int *)&progress[b - 1]) < want) { }
                 __threadfence();
             }
@@ -288,14 +300,14 @@ k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int 
                     const double rh = sor_pick(s_ring[k][2][t], &rrho[j]);
                     const double up = up_from_global ? sor_pick(s_ring[k][3][t], &row_p[j])
                                                      : s_new[(s + 1) & 1][t - 1];   // written at step s-1 by thread t-1
-                    const double g = coef * (((up + down) / dx2) + ((left + right) / dy2) + (rh / eps));
+                    const double g = coef * (sor_div(up + down, dx2, rdx2) + sor_div(left + right, dy2, rdy2) + (rh / eps));
                     const double v = center + 1.4 * (g - center);
                     __stcg(&phi[(long long)i * niy + j], v);
                     s_new[s & 1][t] = v;
                     if (j == 1) saved_col1 = v;
                     left = v;
                     center = right;         // phi_old(i, j+1) is the next centre
-                    if (last_row_of_band && ((j & 15) == 15 || j == niy - 1)) {
+                    if (last_row_of_band && ((j & 7) == 7 || j == niy - 1)) {
                         __threadfence();
                         *(volatile int *)&progress[b] = j + 1;
                     }
