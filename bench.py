@@ -180,7 +180,7 @@ def main_reference(args, rank):
         "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -302,7 +302,7 @@ def main_ours(args, rank, world, local_rank):
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "phases_ms_per_step": phases_ms, "wall_ms_per_step": 1e3 * t_wall / args.steps,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     return 0
 
 
@@ -346,7 +346,26 @@ def run_e2e(sim, args, n_local, barrier, max_over_ranks, torch):
                     "(bytes are per rank, amortised over the dump period)", "ke_finite": bool(np.isfinite(ke).all())}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to fd 1 from here on (NCCL's version
+    banner, library chatter, the reference's own banner in the CPU arm) goes to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
