@@ -637,7 +637,14 @@ int picsp_compute_ke(picsp_ctx *c, int s, double *ke) {
     PICSP_REQUIRE(ke != nullptr, PICSP_ERR_INVALID, "null output");
     PICSP_CUDA(cudaSetDevice(c->prm.device));
     Species &sp = c->sp[s];
-    PICSP_LAUNCH(c, k_ke_partial, RED_BLOCKS, RED_THREADS, 0, sp.vx, sp.vy, (long long)sp.n, c->d_red);
+    if (sp.has_perm && sp.n > 0) {
+        // sorted store: reduce in upload order so the sum is reproducible regardless of the storage order
+        ensure_stage(c, sp.n);
+        PICSP_LAUNCH(c, k_ke_terms, particle_blocks(c, sp.n, 256), 256, 0, sp.vx, sp.vy, sp.id, (long long)sp.n, c->stage);
+        PICSP_LAUNCH(c, k_sum_partial, RED_BLOCKS, RED_THREADS, 0, c->stage, (long long)sp.n, c->d_red);
+    } else {
+        PICSP_LAUNCH(c, k_ke_partial, RED_BLOCKS, RED_THREADS, 0, sp.vx, sp.vy, (long long)sp.n, c->d_red);
+    }
     PICSP_LAUNCH(c, k_sum_final, 1, 1024, 0, c->d_red, RED_BLOCKS, c->d_scalars + 0);
     if (c->comm) PICSP_NCCL(nccl().AllReduce(c->d_scalars, c->d_scalars, 1, ncclFloat64, ncclSum, c->comm, c->stream));
     double sum = read_scalar(c, c->d_scalars + 0);

@@ -408,6 +408,20 @@ __global__ void k_ke_partial(const double *__restrict__ vx, const double *__rest
     double t = block_sum(s, s_red);
     if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
+// KE terms written in UPLOAD order (stage[id[slot]]), so that the reduction tree — and the result, bit for
+// bit — does not depend on how the tile sort happened to arrange the particles in memory.
+__global__ void k_ke_terms(const double *__restrict__ vx, const double *__restrict__ vy, const unsigned int *__restrict__ id,
+                           long long n, double *__restrict__ terms) {
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x)
+        terms[id ? (long long)id[p] : p] = vx[p] * vx[p] + vy[p] * vy[p];
+}
+__global__ void k_sum_partial(const double *__restrict__ a, long long n, double *__restrict__ partial) {
+    __shared__ double s_red[32];
+    double s = 0.0;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) s += a[p];
+    double t = block_sum(s, s_red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
 __global__ void k_sum_final(const double *__restrict__ partial, int n, double *__restrict__ out) {
     __shared__ double s_red[32];
     double s = 0.0;
