@@ -324,6 +324,60 @@ def test_clear_density_extension_and_accumulate_default():
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("solver", [1, 2])
+@pytest.mark.parametrize("numx,numy", [(3, 3), (4, 7), (9, 5), (16, 16), (17, 31)])
+def test_tiny_grids(solver, numx, numy):
+    """Grids smaller than one particle tile / one SOR band, odd and even node counts."""
+    nm = normalise()
+    n = 700
+    o = Oracle(numx, numy, nm["dx"], nm["dt"], nm["mass_i"], n, n, vth_i=nm["vth_i"], solver=solver)
+    o.seed(17); o.init(ION, 1); o.init(ELECTRON, 1)
+    with Simulation(Params(numx, numy, nm["dx"], nm["dt"], nm["mass_i"], n, n, solverType=solver)) as sim:
+        for s in (ION, ELECTRON):
+            sim.set_species(s, *o.get_species(s))
+        o.bootstrap(); sim.bootstrap()
+        o.step(3); sim.step(3)
+        for name in GRIDS:
+            assert_grid_close(sim.grid(name), o.grid(name), sim.nix, sim.niy, 10 * RTOL, name)
+        for s in (ION, ELECTRON):
+            got, want = sim.get_species(s), o.get_species(s)
+            for k in range(4):
+                assert relerr(got[k], want[k]) <= 10 * RTOL
+
+
+def test_empty_species_and_single_particle():
+    nm = normalise()
+    numx = 32
+    with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], 1, 1, solverType=1, capacity=(4, 4))) as sim:
+        sim.set_species(ION, *(np.zeros(0),) * 4)                      # no ions at all
+        sim.set_species(ELECTRON, [0.2], [0.3], [0.5], [-0.25])
+        sim.bootstrap(); sim.step(2)
+        assert sim.count(ION) == 0 and sim.count(ELECTRON) == 1
+        o = Oracle(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], 1, 1, solver=1)
+        o.set_species(ION, *(np.zeros(0),) * 4); o.set_species(ELECTRON, [0.2], [0.3], [0.5], [-0.25])
+        o.bootstrap(); o.step(2)
+        for k in range(4):
+            assert relerr(sim.get_species(ELECTRON)[k], o.get_species(ELECTRON)[k]) <= RTOL
+        assert_grid_close(sim.grid("phi"), o.grid("phi"), numx + 1, numx + 1, RTOL, "phi")
+
+
+def test_displacement_guard_reports_an_error():
+    """The fixed-point scale assumes no particle crosses more than one 16-cell tile per step; a violation is not
+    silently wrong, it surfaces as PICSP_ERR_DISPLACEMENT at the next synchronising call."""
+    nm = normalise()
+    numx, n = 128, 1000
+    rng = np.random.default_rng(2)
+    xl = numx * nm["dx"]
+    x, y = rng.random(n) * xl, rng.random(n) * xl
+    vx = np.zeros(n); vx[0] = 40 * nm["dx"] / nm["dt"]                 # 40 cells in one step
+    with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n)) as sim:
+        sim.set_species(ION, x, y, np.zeros(n), np.zeros(n)); sim.set_species(ELECTRON, x, y, vx, np.zeros(n))
+        sim.bootstrap(); sim.step(1)
+        with pytest.raises(picsp_b200.PicspError) as ei:
+            sim.sync()
+        assert ei.value.code == -7
+
+
 def test_error_codes():
     nm = normalise()
     with Simulation(Params(16, 16, nm["dx"], nm["dt"], nm["mass_i"], 10, 10, solverType=2)) as sim:
