@@ -84,7 +84,9 @@ bool tiled(const picsp_ctx *c) { return !(c->prm.flags & PICSP_FLAG_NO_SORT); }
 void compute_frac(picsp_ctx *c, int s) {
     Species &sp = c->sp[s];
     // the shared-memory limbs of the tiled path carry at most MAX_FRAC_TILED fraction bits
-    PICSP_LAUNCH(c, k_frac_from_hist, 1, 1024, 0, sp.hist, c->g.ntx, c->g.nty, sp.frac, tiled(c) ? MAX_FRAC_TILED : 60);
+    const int nt = c->g.ntx * c->g.nty;
+    PICSP_LAUNCH(c, k_frac_from_hist, (nt + 255) / 256, 256, 0, sp.hist, c->g.ntx, c->g.nty, sp.frac,
+                 tiled(c) ? MAX_FRAC_TILED : 60, sp.frac_scratch);
 }
 
 // -- tile binning -------------------------------------------------------------------------
@@ -150,23 +152,31 @@ void make_tensor_map(picsp_ctx *c) {
 }
 
 // -- operations ---------------------------------------------------------------------
+void op_allreduce_rho(picsp_ctx *c);   // comm section below
+
+// makes sure acc_s holds the fixed-point deposit of the stored positions (scatter loop of scatterSpecies)
+void ensure_acc(picsp_ctx *c, int s) {
+    Species &sp = c->sp[s];
+    if (sp.acc_valid) return;
+    if (tiled(c) && !sp.sorted) op_sort(c, s);
+    ensure_hist(c, s);
+    compute_frac(c, s);
+    PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
+    if (sp.n > 0) {
+        if (tiled(c))
+            launch_tile_mover<1>(c, s);
+        else
+            PICSP_LAUNCH(c, k_deposit, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, (long long)sp.n,
+                         push_const(c, s), sp.acc, sp.frac);
+    }
+    sp.acc_valid = true;
+}
+
 void op_deposit(picsp_ctx *c, int s) {
     PhaseScope ph(c, PICSP_PHASE_DEPOSIT);
     Species &sp = c->sp[s];
     const Geom &g = c->g;
-    if (!sp.acc_valid) {
-        if (tiled(c) && !sp.sorted) op_sort(c, s);
-        ensure_hist(c, s);
-        compute_frac(c, s);
-        PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
-        if (sp.n > 0) {
-            if (tiled(c))
-                launch_tile_mover<1>(c, s);
-            else
-                PICSP_LAUNCH(c, k_deposit, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, (long long)sp.n,
-                             push_const(c, s), sp.acc, sp.frac);
-        }
-    }
+    ensure_acc(c, s);
     const double weight = sp.spwt / (g.dx * g.dx);   // value/dxdy, src/main.cpp:657,664
     const int clear = (c->prm.flags & PICSP_FLAG_CLEAR_DENSITY) ? 1 : 0;
     PICSP_LAUNCH(c, k_deposit_finalize, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, sp.den, sp.acc, sp.frac, weight, g.nn, clear);
@@ -174,7 +184,28 @@ void op_deposit(picsp_ctx *c, int s) {
     sp.acc_valid = false;
 }
 
-void op_allreduce_rho(picsp_ctx *c);   // comm section below
+// picsp_step's grid phase: scatterSpecies x2 (finalize + fold) and computeRho in ONE launch
+void op_grid_phase(picsp_ctx *c) {
+    const Geom &g = c->g;
+    {
+        PhaseScope ph(c, PICSP_PHASE_DEPOSIT);
+        ensure_acc(c, 0); ensure_acc(c, 1);
+    }
+    {
+        PhaseScope ph(c, PICSP_PHASE_RHO);
+        GridPhaseSpecies gs[2];
+        for (int s = 0; s < 2; s++) {
+            Species &sp = c->sp[s];
+            gs[s].den = sp.den; gs[s].acc = sp.acc; gs[s].frac = sp.frac;
+            gs[s].weight = sp.spwt / (g.dx * g.dx); gs[s].q = sp.q;
+            sp.acc_valid = false;
+        }
+        const int clear = (c->prm.flags & PICSP_FLAG_CLEAR_DENSITY) ? 1 : 0;
+        PICSP_LAUNCH(c, k_grid_phase, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, gs[0], gs[1], c->rho, g.nix, g.niy, clear);
+    }
+    if (c->comm) op_allreduce_rho(c);    // the folds are linear: folding the partial rho first commutes with the sum
+}
+
 
 void op_compute_rho(picsp_ctx *c) {
     const Geom &g = c->g;
@@ -370,7 +401,7 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
             Species &sp = c->sp[s];
             sp.cap = p->capacity[s]; sp.q = p->charge[s]; sp.m = p->mass[s]; sp.spwt = p->spwt[s];
             dalloc(&sp.x, sp.cap); dalloc(&sp.y, sp.cap); dalloc(&sp.vx, sp.cap); dalloc(&sp.vy, sp.cap);
-            dalloc(&sp.den, g.nn); dalloc(&sp.acc, g.nn); dalloc(&sp.frac, 1);
+            dalloc(&sp.den, g.nn); dalloc(&sp.acc, g.nn); dalloc(&sp.frac, 1); dalloc(&sp.frac_scratch, 2);
             dalloc(&sp.hist, (size_t)g.ntx * g.nty); dalloc(&sp.hist_next, (size_t)g.ntx * g.nty);
             dalloc(&sp.counters, 2);
             sp.sort_period = (s == 0) ? 96 : 12;
@@ -383,6 +414,7 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
             PICSP_CUDA(cudaMemsetAsync(sp.den, 0, sizeof(double) * g.nn, c->stream));      // src/main.cpp:427,431
             PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * g.nn, c->stream));
             PICSP_CUDA(cudaMemsetAsync(sp.frac, 0, sizeof(int), c->stream));
+            PICSP_CUDA(cudaMemsetAsync(sp.frac_scratch, 0, 2 * sizeof(unsigned long long), c->stream));
             PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
         }
         dalloc(&c->rho, g.nn); dalloc(&c->phi, g.nn);
@@ -428,7 +460,7 @@ void picsp_destroy(picsp_ctx *c) {
     for (int s = 0; s < 2; s++) {
         Species &sp = c->sp[s];
         cudaFree(sp.x); cudaFree(sp.y); cudaFree(sp.vx); cudaFree(sp.vy); cudaFree(sp.id);
-        cudaFree(sp.den); cudaFree(sp.acc); cudaFree(sp.frac); cudaFree(sp.hist); cudaFree(sp.hist_next); cudaFree(sp.counters);
+        cudaFree(sp.den); cudaFree(sp.acc); cudaFree(sp.frac); cudaFree(sp.frac_scratch); cudaFree(sp.hist); cudaFree(sp.hist_next); cudaFree(sp.counters);
         cudaFree(sp.x2); cudaFree(sp.y2); cudaFree(sp.vx2); cudaFree(sp.vy2); cudaFree(sp.id2);
         cudaFree(sp.tile_off); cudaFree(sp.chunks); cudaFree(sp.nchunks); cudaFree(sp.cursor);
     }
@@ -621,8 +653,7 @@ int picsp_step(picsp_ctx *c, int nsteps) {   // src/main.cpp:481-504
     PICSP_CUDA(cudaSetDevice(c->prm.device));
     PhaseScope whole(c, PICSP_PHASE_STEP);
     for (int it = 0; it < nsteps; it++) {
-        op_deposit(c, 0); op_deposit(c, 1);
-        op_compute_rho(c);
+        op_grid_phase(c);           // scatterSpecies x2 + computeRho (src/main.cpp:482-490)
         op_solve(c);
         op_compute_ef(c);
         op_push(c, 0); op_push(c, 1);

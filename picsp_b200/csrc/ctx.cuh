@@ -70,6 +70,7 @@ struct Species {
     double *den = nullptr;         // nn, accumulating
     long long *acc = nullptr;      // nn, fixed-point deposit accumulator (order-independent => deterministic)
     int *frac = nullptr;           // device scalar: fixed-point fraction bits acc was filled with
+    unsigned long long *frac_scratch = nullptr;   // [0] running max population, [1] CTA ticket (k_frac_from_hist)
     unsigned int *hist = nullptr;      // particles per tile at the positions currently stored
     unsigned int *hist_next = nullptr; // filled by the mover for the positions it writes
     bool hist_valid = false;

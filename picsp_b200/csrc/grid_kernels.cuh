@@ -59,6 +59,68 @@ __global__ void k_compute_rho(double *__restrict__ rho, const double *__restrict
 }
 
 // ---------------------------------------------------------------------------
+// One-launch grid phase of a time step (picsp_step): for BOTH species
+//   den += spwt/(dx*dy) * acc * 2^-frac ; acc = 0          (k_deposit_finalize)
+//   periodic fold of den, rows then columns                 (k_fold_periodic, src/main.cpp:702-712)
+// then rho = q_i*den_i + q_e*den_e on interior nodes        (k_compute_rho, src/main.cpp:874-878)
+// and the fold of rho's (never written) boundary            (src/main.cpp:880-890).
+// The folds only couple an edge node with its periodic partner, so they are done in place by giving
+// each partner pair (and the four corners together) to ONE thread: the result of the two ordered fold
+// loops is  edge (0,j)/(L,j): f0j + fLj;  edge (i,0)/(i,M): fi0 + fiM;  corners: (f00 + fL0) + (f0M + fLM).
+// ---------------------------------------------------------------------------
+struct GridPhaseSpecies { double *den; long long *acc; const int *frac; double weight, q; };
+
+__device__ __forceinline__ double finalize_node(const GridPhaseSpecies &sp, long long k, double scale, int clear) {
+    const long long a = sp.acc[k];
+    sp.acc[k] = 0;
+    return (clear ? 0.0 : sp.den[k]) + (double)a * scale;
+}
+
+__global__ void k_grid_phase(GridPhaseSpecies s0, GridPhaseSpecies s1, double *__restrict__ rho, int nix, int niy, int clear) {
+    const int L = nix - 1, M = niy - 1;
+    const double sc0 = s0.weight * exp2((double)(-*s0.frac)), sc1 = s1.weight * exp2((double)(-*s1.frac));
+    const long long n_int = (long long)(nix - 2) * (niy - 2);
+    const long long n_work = n_int + (M - 1) + (L - 1) + 1;   // interior nodes, row pairs, column pairs, corner group
+    for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < n_work; w += (long long)gridDim.x * blockDim.x) {
+        if (w < n_int) {
+            const int i = 1 + (int)(w / (niy - 2)), j = 1 + (int)(w % (niy - 2));
+            const long long k = (long long)i * niy + j;
+            const double di = finalize_node(s0, k, sc0, clear), de = finalize_node(s1, k, sc1, clear);
+            s0.den[k] = di; s1.den[k] = de;
+            rho[k] = s0.q * di + s1.q * de;
+            continue;
+        }
+        long long e = w - n_int;
+        if (e < M - 1) {                                   // rows 0 and L, column j in 1..M-1
+            const long long a = 1 + e, b = (long long)L * niy + 1 + e;
+            double v = finalize_node(s0, a, sc0, clear) + finalize_node(s0, b, sc0, clear); s0.den[a] = v; s0.den[b] = v;
+            v = finalize_node(s1, a, sc1, clear) + finalize_node(s1, b, sc1, clear); s1.den[a] = v; s1.den[b] = v;
+            v = rho[a] + rho[b]; rho[a] = v; rho[b] = v;
+            continue;
+        }
+        e -= M - 1;
+        if (e < L - 1) {                                   // columns 0 and M, row i in 1..L-1
+            const long long a = (1 + e) * niy, b = a + M;
+            double v = finalize_node(s0, a, sc0, clear) + finalize_node(s0, b, sc0, clear); s0.den[a] = v; s0.den[b] = v;
+            v = finalize_node(s1, a, sc1, clear) + finalize_node(s1, b, sc1, clear); s1.den[a] = v; s1.den[b] = v;
+            v = rho[a] + rho[b]; rho[a] = v; rho[b] = v;
+            continue;
+        }
+        {                                                  // the four corners
+            const long long c00 = 0, c0M = M, cL0 = (long long)L * niy, cLM = cL0 + M;
+            double v = (finalize_node(s0, c00, sc0, clear) + finalize_node(s0, cL0, sc0, clear)) +
+                       (finalize_node(s0, c0M, sc0, clear) + finalize_node(s0, cLM, sc0, clear));
+            s0.den[c00] = v; s0.den[c0M] = v; s0.den[cL0] = v; s0.den[cLM] = v;
+            v = (finalize_node(s1, c00, sc1, clear) + finalize_node(s1, cL0, sc1, clear)) +
+                (finalize_node(s1, c0M, sc1, clear) + finalize_node(s1, cLM, sc1, clear));
+            s1.den[c00] = v; s1.den[c0M] = v; s1.den[cL0] = v; s1.den[cLM] = v;
+            v = (rho[c00] + rho[cL0]) + (rho[c0M] + rho[cLM]);
+            rho[c00] = v; rho[c0M] = v; rho[cL0] = v; rho[cLM] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // k-space Green's function (src/main.cpp:996-1025) + 1/(Nx*Ny) (:1051-1055).
 //  * kx = 2*PI*i/Lx for i < Nx/2, 2*PI*(Nx-i)/Lx for i > Nx/2, Lx = xl (:999-1021)
 //  * row i == Nx/2 is never written by the reference -> defined as 0 (Q7)

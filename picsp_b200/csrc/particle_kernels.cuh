@@ -124,28 +124,39 @@ __global__ void k_tile_hist(const double *__restrict__ x, const double *__restri
 // fused mover deposits positions one step after the histogram was taken, and a
 // particle may move by at most one tile per step (checked by the mover), so the
 // 5x5 neighbourhood bounds every node sum by pop * 2^frac < 2^62.
-__global__ void k_frac_from_hist(const unsigned int *__restrict__ hist, int ntx, int nty, int *__restrict__ frac, int cap) {
-    __shared__ unsigned long long s_max[32];
+// Multi-CTA: every thread sums one tile's neighbourhood (25 independent L2 loads), the CTA maximum goes
+// to scratch[0] with atomicMax, and the last CTA to finish (ticket in scratch[1]) converts the maximum into
+// the fraction-bit count and resets the scratch for the next call.
+__global__ void __launch_bounds__(256)
+k_frac_from_hist(const unsigned int *__restrict__ hist, int ntx, int nty, int *__restrict__ frac, int cap,
+                 unsigned long long *__restrict__ scratch) {
+    __shared__ unsigned long long s_max[8];
     unsigned long long m = 0;
-    int wx = ntx < 5 ? ntx : 5, wy = nty < 5 ? nty : 5;
-    for (int t = threadIdx.x; t < ntx * nty; t += blockDim.x) {
-        int tx = t / nty, ty = t % nty;
-        unsigned long long s = 0;
+    const int wx = ntx < 5 ? ntx : 5, wy = nty < 5 ? nty : 5;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ntx * nty) {
+        const int tx = t / nty, ty = t % nty;
         for (int a = 0; a < wx; a++)
             for (int b = 0; b < wy; b++) {
                 int ux = (tx - wx / 2 + a + 2 * ntx) % ntx, uy = (ty - wy / 2 + b + 2 * nty) % nty;
-                s += hist[ux * nty + uy];
+                m += hist[ux * nty + uy];
             }
-        m = s > m ? s : m;
     }
-    for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long v = __shfl_xor_sync(0xffffffffu, m, o); m = v > m ? v : m; }
     if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 0; w < (blockDim.x + 31) / 32; w++) m = s_max[w] > m ? s_max[w] : m;
-        int bits = 64 - __clzll((long long)(m | 1ull));
-        int f = 62 - bits;
-        *frac = f > cap ? cap : (f < 0 ? 0 : f);
+        atomicMax(&scratch[0], m);
+        __threadfence();
+        if (atomicAdd(&scratch[1], 1ull) == (unsigned long long)gridDim.x - 1) {   // last CTA
+            __threadfence();
+            const unsigned long long mx = atomicExch(&scratch[0], 0ull);
+            scratch[1] = 0ull;
+            const int bits = 64 - __clzll((long long)(mx | 1ull));
+            const int f = 62 - bits;
+            *frac = f > cap ? cap : (f < 0 ? 0 : f);
+        }
     }
 }
 
