@@ -79,34 +79,24 @@ __device__ __forceinline__ double finalize_node(const GridPhaseSpecies &sp, long
 __global__ void k_grid_phase(GridPhaseSpecies s0, GridPhaseSpecies s1, double *__restrict__ rho, int nix, int niy, int clear) {
     const int L = nix - 1, M = niy - 1;
     const double sc0 = s0.weight * exp2((double)(-*s0.frac)), sc1 = s1.weight * exp2((double)(-*s1.frac));
-    const long long n_int = (long long)(nix - 2) * (niy - 2);
-    const long long n_work = n_int + (M - 1) + (L - 1) + 1;   // interior nodes, row pairs, column pairs, corner group
-    for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < n_work; w += (long long)gridDim.x * blockDim.x) {
-        if (w < n_int) {
-            const int i = 1 + (int)(w / (niy - 2)), j = 1 + (int)(w % (niy - 2));
-            const long long k = (long long)i * niy + j;
+    const unsigned nn = (unsigned)nix * (unsigned)niy;      // <= 2^31 by the capacity of int node counts
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < nn; k += gridDim.x * blockDim.x) {
+        const int i = (int)(k / (unsigned)niy), j = (int)(k - (unsigned)i * (unsigned)niy);
+        if (i > 0 && i < L && j > 0 && j < M) {              // interior node
             const double di = finalize_node(s0, k, sc0, clear), de = finalize_node(s1, k, sc1, clear);
             s0.den[k] = di; s1.den[k] = de;
             rho[k] = s0.q * di + s1.q * de;
-            continue;
-        }
-        long long e = w - n_int;
-        if (e < M - 1) {                                   // rows 0 and L, column j in 1..M-1
-            const long long a = 1 + e, b = (long long)L * niy + 1 + e;
+        } else if (i == 0 && j > 0 && j < M) {               // rows 0 and L: the (0,j) thread owns the pair
+            const long long a = k, b = (long long)L * niy + j;
             double v = finalize_node(s0, a, sc0, clear) + finalize_node(s0, b, sc0, clear); s0.den[a] = v; s0.den[b] = v;
             v = finalize_node(s1, a, sc1, clear) + finalize_node(s1, b, sc1, clear); s1.den[a] = v; s1.den[b] = v;
             v = rho[a] + rho[b]; rho[a] = v; rho[b] = v;
-            continue;
-        }
-        e -= M - 1;
-        if (e < L - 1) {                                   // columns 0 and M, row i in 1..L-1
-            const long long a = (1 + e) * niy, b = a + M;
+        } else if (j == 0 && i > 0 && i < L) {               // columns 0 and M: the (i,0) thread owns the pair
+            const long long a = k, b = a + M;
             double v = finalize_node(s0, a, sc0, clear) + finalize_node(s0, b, sc0, clear); s0.den[a] = v; s0.den[b] = v;
             v = finalize_node(s1, a, sc1, clear) + finalize_node(s1, b, sc1, clear); s1.den[a] = v; s1.den[b] = v;
             v = rho[a] + rho[b]; rho[a] = v; rho[b] = v;
-            continue;
-        }
-        {                                                  // the four corners
+        } else if (i == 0 && j == 0) {                       // the four corners
             const long long c00 = 0, c0M = M, cL0 = (long long)L * niy, cLM = cL0 + M;
             double v = (finalize_node(s0, c00, sc0, clear) + finalize_node(s0, cL0, sc0, clear)) +
                        (finalize_node(s0, c0M, sc0, clear) + finalize_node(s0, cLM, sc0, clear));
@@ -116,7 +106,7 @@ __global__ void k_grid_phase(GridPhaseSpecies s0, GridPhaseSpecies s1, double *_
             s1.den[c00] = v; s1.den[c0M] = v; s1.den[cL0] = v; s1.den[cLM] = v;
             v = (rho[c00] + rho[cL0]) + (rho[c0M] + rho[cLM]);
             rho[c00] = v; rho[c0M] = v; rho[cL0] = v; rho[cLM] = v;
-        }
+        }                                                    // (L,j), (i,M) and the other corners are written by their owners
     }
 }
 
