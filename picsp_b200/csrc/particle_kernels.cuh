@@ -115,7 +115,10 @@ __device__ __forceinline__ void scatter_fixed(long long *__restrict__ acc, const
 // ---------------------------------------------------------------------------
 __global__ void k_tile_hist(const double *__restrict__ x, const double *__restrict__ y, long long n,
                             PushConst c, unsigned int *__restrict__ hist) {
-    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x)
+    // contiguous slice per CTA (see k_sort_scatter): keeps concurrent CTAs on different histogram bins
+    const long long per_cta = (n + gridDim.x - 1) / gridDim.x;
+    const long long lo = blockIdx.x * per_cta, hi = min(n, lo + per_cta);
+    for (long long p = lo + threadIdx.x; p < hi; p += blockDim.x)
         atomicAdd(&hist[tile_of(x[p], y[p], c)], 1u);
 }
 

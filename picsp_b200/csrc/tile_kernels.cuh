@@ -94,10 +94,14 @@ k_sort_scatter(const double *__restrict__ x, const double *__restrict__ y, const
                double *__restrict__ x2, double *__restrict__ y2, double *__restrict__ vx2, double *__restrict__ vy2,
                uint32_t *__restrict__ id2) {
     const int lane = threadIdx.x & 31;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long base = blockIdx.x * (long long)blockDim.x + threadIdx.x - lane; base < n; base += stride) {
+    // Each CTA takes one CONTIGUOUS slice of the array.  With a grid-stride loop all resident CTAs would
+    // work on neighbouring particles, i.e. on the same handful of bins, and their cursor atomics would
+    // serialise on a few L2 addresses; contiguous slices put every CTA in a different bin.
+    const long long per_cta = ((n + gridDim.x - 1) / gridDim.x + 31) & ~31ll;
+    const long long lo = blockIdx.x * per_cta, hi = min(n, lo + per_cta);
+    for (long long base = lo + (threadIdx.x - lane); base < hi; base += blockDim.x) {
         const long long p = base + lane;
-        const bool live = p < n;
+        const bool live = p < hi;
         double px = 0, py = 0;
         int t = -1;
         if (live) { px = x[p]; py = y[p]; t = tile_of(px, py, c); }
