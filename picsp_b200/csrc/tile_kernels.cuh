@@ -99,12 +99,22 @@ k_sort_scatter(const double *__restrict__ x, const double *__restrict__ y, const
     // serialise on a few L2 addresses; contiguous slices put every CTA in a different bin.
     const long long per_cta = ((n + gridDim.x - 1) / gridDim.x + 31) & ~31ll;
     const long long lo = blockIdx.x * per_cta, hi = min(n, lo + per_cta);
-    for (long long base = lo + (threadIdx.x - lane); base < hi; base += blockDim.x) {
+    // software pipeline: all five loads of the NEXT particle are in flight while the current one takes its slot
+    long long base = lo + (threadIdx.x - lane);
+    double px = 0, py = 0, pvx = 0, pvy = 0;
+    uint32_t pid = 0;
+    if (base + lane < hi) {
+        const long long p = base + lane;
+        px = x[p]; py = y[p]; pvx = vx[p]; pvy = vy[p]; pid = id ? id[p] : (uint32_t)p;
+    }
+    for (; base < hi; base += blockDim.x) {
         const long long p = base + lane;
         const bool live = p < hi;
-        double px = 0, py = 0;
-        int t = -1;
-        if (live) { px = x[p]; py = y[p]; t = tile_of(px, py, c); }
+        const long long pn = p + blockDim.x;
+        double nx = 0, ny = 0, nvx = 0, nvy = 0;
+        uint32_t nid = 0;
+        if (pn < hi) { nx = x[pn]; ny = y[pn]; nvx = vx[pn]; nvy = vy[pn]; nid = id ? id[pn] : (uint32_t)pn; }
+        const int t = live ? tile_of(px, py, c) : -1;
         const unsigned int peers = __match_any_sync(0xffffffffu, t);
         const int leader = __ffs(peers) - 1;
         const int rank = __popc(peers & ((1u << lane) - 1u));
@@ -113,9 +123,9 @@ k_sort_scatter(const double *__restrict__ x, const double *__restrict__ y, const
         first = __shfl_sync(0xffffffffu, first, leader);
         if (live) {
             const long long dst = tile_off[t] + first + rank;
-            x2[dst] = px; y2[dst] = py; vx2[dst] = vx[p]; vy2[dst] = vy[p];
-            id2[dst] = id ? id[p] : (uint32_t)p;
+            x2[dst] = px; y2[dst] = py; vx2[dst] = pvx; vy2[dst] = pvy; id2[dst] = pid;
         }
+        px = nx; py = ny; pvx = nvx; pvy = nvy; pid = nid;
     }
 }
 
