@@ -90,21 +90,32 @@ void compute_frac(picsp_ctx *c, int s) {
 }
 
 // -- tile binning -------------------------------------------------------------------------
+int mover_grid(const Species &sp);
+
 void op_sort(picsp_ctx *c, int s) {
     PhaseScope ph(c, PICSP_PHASE_SORT);
     Species &sp = c->sp[s];
     const Geom &g = c->g;
     const int nt = g.ntx * g.nty;
     ensure_hist(c, s);
-    PICSP_LAUNCH(c, k_scan_tiles, 1, 1024, 0, sp.hist, nt, sp.tile_off, (Chunk *)sp.chunks, sp.nchunks, sp.cursor);
     if (!sp.x2) {
         dalloc(&sp.x2, sp.cap); dalloc(&sp.y2, sp.cap); dalloc(&sp.vx2, sp.cap); dalloc(&sp.vy2, sp.cap);
         dalloc(&sp.id, sp.cap); dalloc(&sp.id2, sp.cap);
+        dalloc((Chunk **)&sp.chunks2, (size_t)sp.max_chunks); dalloc(&sp.nchunks2, 1);
     }
-    if (sp.n > 0)
-        PICSP_LAUNCH(c, k_sort_scatter, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy,
-                     sp.has_perm ? sp.id : (const uint32_t *)nullptr, (long long)sp.n, push_const(c, s), sp.tile_off,
-                     sp.cursor, sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2);
+    const uint32_t *ids = sp.has_perm ? sp.id : (const uint32_t *)nullptr;
+    // new bin offsets / chunk table go to the second table: the re-sort kernel still walks the current one
+    PICSP_LAUNCH(c, k_scan_tiles, 1, 1024, 0, sp.hist, nt, sp.tile_off, (Chunk *)sp.chunks2, sp.nchunks2, sp.cursor);
+    if (sp.n > 0) {
+        if (sp.sorted)
+            PICSP_LAUNCH(c, k_resort_chunks, mover_grid(sp), RESORT_THREADS, 0, sp.x, sp.y, sp.vx, sp.vy, ids,
+                         (const Chunk *)sp.chunks, sp.nchunks, push_const(c, s), sp.tile_off, sp.cursor,
+                         sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2);
+        else
+            PICSP_LAUNCH(c, k_sort_scatter, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy, ids,
+                         (long long)sp.n, push_const(c, s), sp.tile_off, sp.cursor, sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2);
+    }
+    std::swap(sp.chunks, sp.chunks2); std::swap(sp.nchunks, sp.nchunks2);
     std::swap(sp.x, sp.x2); std::swap(sp.y, sp.y2); std::swap(sp.vx, sp.vx2); std::swap(sp.vy, sp.vy2);
     std::swap(sp.id, sp.id2);
     sp.has_perm = true; sp.sorted = true; sp.steps_since_sort = 0;
@@ -463,6 +474,7 @@ void picsp_destroy(picsp_ctx *c) {
         cudaFree(sp.den); cudaFree(sp.acc); cudaFree(sp.frac); cudaFree(sp.frac_scratch); cudaFree(sp.hist); cudaFree(sp.hist_next); cudaFree(sp.counters);
         cudaFree(sp.x2); cudaFree(sp.y2); cudaFree(sp.vx2); cudaFree(sp.vy2); cudaFree(sp.id2);
         cudaFree(sp.tile_off); cudaFree(sp.chunks); cudaFree(sp.nchunks); cudaFree(sp.cursor);
+        cudaFree(sp.chunks2); cudaFree(sp.nchunks2);
     }
     cudaFree(c->rho); cudaFree(c->phi); cudaFree(c->E_alloc); cudaFree(c->rhok); cudaFree(c->phik);
     cudaFree(c->d_red); cudaFree(c->d_scalars); cudaFree(c->d_sor_status); cudaFree(c->d_sor_progress); cudaFree(c->d_error); cudaFree(c->stage);

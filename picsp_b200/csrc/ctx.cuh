@@ -87,6 +87,8 @@ struct Species {
     long long *tile_off = nullptr; // ntiles+1
     void *chunks = nullptr;        // picsp::Chunk[max_chunks]
     int *nchunks = nullptr;        // device scalar
+    void *chunks2 = nullptr;       // second chunk table (a re-sort reads the current one while the next is built)
+    int *nchunks2 = nullptr;
     unsigned int *cursor = nullptr;// ntiles
     long long max_chunks = 0;
 };

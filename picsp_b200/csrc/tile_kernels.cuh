@@ -129,6 +129,76 @@ k_sort_scatter(const double *__restrict__ x, const double *__restrict__ y, const
     }
 }
 
+// Re-sort of an already binned store: one CTA per source chunk.  Nearly every particle stays in its bin
+// or moves to one of the 8 neighbours, so the CTA first ranks its particles per destination class in shared
+// memory (warp-aggregated), reserves ONE contiguous range per destination bin with a single global atomic,
+// and then writes: every CTA emits a few long sequential runs instead of isolated 256-byte pieces, and the
+// global cursor sees ~10 atomics per 4096 particles.  Far movers (rare) take a cursor slot individually.
+constexpr int RESORT_THREADS = 256;
+constexpr int RESORT_ITERS = (CHUNK + RESORT_THREADS - 1) / RESORT_THREADS;
+
+__global__ void __launch_bounds__(RESORT_THREADS)
+k_resort_chunks(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ vx,
+                const double *__restrict__ vy, const uint32_t *__restrict__ id, const Chunk *__restrict__ chunks,
+                const int *__restrict__ nchunks, PushConst c, const long long *__restrict__ tile_off,
+                unsigned int *__restrict__ cursor, double *__restrict__ x2, double *__restrict__ y2,
+                double *__restrict__ vx2, double *__restrict__ vy2, uint32_t *__restrict__ id2) {
+    __shared__ unsigned s_cnt[9];
+    __shared__ unsigned s_base[9];
+    if ((int)blockIdx.x >= *nchunks) return;
+    const Chunk ck = chunks[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tx = ck.tile / c.nty, ty = ck.tile - tx * c.nty;
+    const bool nbr_ok = (c.ntx >= 3 && c.nty >= 3);
+    if (tid < 9) s_cnt[tid] = 0u;
+    __syncthreads();
+
+    unsigned code[RESORT_ITERS];        // class (4 bits) | rank inside the CTA and class (<= 4096)
+#pragma unroll
+    for (int it = 0; it < RESORT_ITERS; it++) {
+        const int k = tid + it * RESORT_THREADS;
+        const bool live = k < ck.count;
+        int cls = 15;                   // 15: nothing to do in pass B
+        if (live) {
+            const long long p = ck.start + k;
+            const int t = tile_of(x[p], y[p], c);
+            int ddx = t / c.nty - tx, ddy = t % c.nty - ty;
+            if (ddx > 1) ddx -= c.ntx; else if (ddx < -1) ddx += c.ntx;
+            if (ddy > 1) ddy -= c.nty; else if (ddy < -1) ddy += c.nty;
+            if (nbr_ok && ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1) {
+                cls = (ddx + 1) * 3 + (ddy + 1);
+            } else {                    // far mover (or a grid with fewer than 3 tiles per side): individual slot
+                const long long dst = tile_off[t] + atomicAdd(&cursor[t], 1u);
+                x2[dst] = x[p]; y2[dst] = y[p]; vx2[dst] = vx[p]; vy2[dst] = vy[p];
+                id2[dst] = id ? id[p] : (uint32_t)p;
+            }
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, cls);
+        unsigned first = 0;
+        const int leader = __ffs(peers) - 1;
+        if (cls < 9 && lane == leader) first = atomicAdd(&s_cnt[cls], (unsigned)__popc(peers));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        code[it] = (unsigned)cls | ((first + (unsigned)__popc(peers & ((1u << lane) - 1u))) << 4);
+    }
+    __syncthreads();
+    if (tid < 9 && s_cnt[tid]) {
+        const int ux = (tx + tid / 3 - 1 + c.ntx) % c.ntx, uy = (ty + tid % 3 - 1 + c.nty) % c.nty;
+        s_base[tid] = atomicAdd(&cursor[ux * c.nty + uy], s_cnt[tid]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < RESORT_ITERS; it++) {
+        const int cls = (int)(code[it] & 15u);
+        if (cls < 9) {
+            const long long p = ck.start + tid + it * RESORT_THREADS;
+            const int ux = (tx + cls / 3 - 1 + c.ntx) % c.ntx, uy = (ty + cls % 3 - 1 + c.nty) % c.nty;
+            const long long dst = tile_off[ux * c.nty + uy] + s_base[cls] + (code[it] >> 4);
+            x2[dst] = x[p]; y2[dst] = y[p]; vx2[dst] = vx[p]; vy2[dst] = vy[p];
+            id2[dst] = id ? id[p] : (uint32_t)p;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA tensor load
 // ---------------------------------------------------------------------------
