@@ -99,7 +99,7 @@ void op_sort(picsp_ctx *c, int s) {
     const int nt = g.ntx * g.nty;
     ensure_hist(c, s);
     if (!sp.x2) {
-        dalloc(&sp.x2, sp.cap); dalloc(&sp.y2, sp.cap); dalloc(&sp.vx2, sp.cap); dalloc(&sp.vy2, sp.cap);
+        dalloc(&sp.x2, sp.cap + 2); dalloc(&sp.y2, sp.cap + 2); dalloc(&sp.vx2, sp.cap + 2); dalloc(&sp.vy2, sp.cap + 2);
         dalloc(&sp.id, sp.cap); dalloc(&sp.id2, sp.cap);
         dalloc((Chunk **)&sp.chunks2, (size_t)sp.max_chunks); dalloc(&sp.nchunks2, 1);
     }
@@ -130,7 +130,14 @@ template <int MODE> void launch_tile_mover(picsp_ctx *c, int s) {
     Species &sp = c->sp[s];
     CUtensorMap tm;
     memcpy(&tm, c->tmapE, sizeof(tm));
-    PICSP_LAUNCH(c, (k_tile_mover<MODE>), mover_grid(sp), MOVER_THREADS, 0, tm, sp.x, sp.y, sp.vx, sp.vy,
+    static bool smem_opted_in = false;     // dynamic shared memory above 48 KB needs a per-function opt-in
+    if (!smem_opted_in) {
+        PICSP_CUDA(cudaFuncSetAttribute(k_tile_mover<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVER_SMEM_BYTES));
+        PICSP_CUDA(cudaFuncSetAttribute(k_tile_mover<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVER_SMEM_BYTES));
+        PICSP_CUDA(cudaFuncSetAttribute(k_tile_mover<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVER_SMEM_BYTES));
+        smem_opted_in = true;
+    }
+    PICSP_LAUNCH(c, (k_tile_mover<MODE>), mover_grid(sp), MOVER_THREADS, MOVER_SMEM_BYTES, tm, sp.x, sp.y, sp.vx, sp.vy,
                  (const Chunk *)sp.chunks, sp.nchunks, push_const(c, s), c->E, sp.acc, sp.frac, sp.hist_next,
                  sp.counters, c->d_error);
 }
@@ -150,7 +157,7 @@ void make_tensor_map(picsp_ctx *c) {
     const Geom &g = c->g;
     cuuint64_t dims[2] = {(cuuint64_t)(2 * g.niy), (cuuint64_t)g.nix};
     cuuint64_t strides[1] = {(cuuint64_t)(2 * g.niy) * sizeof(double)};
-    cuuint32_t box[2] = {(cuuint32_t)(2 * WIN), (cuuint32_t)WIN};
+    cuuint32_t box[2] = {(cuuint32_t)(2 * WPITCH), (cuuint32_t)WIN};
     cuuint32_t estr[2] = {1, 1};
     CUtensorMap tm;
     CUresult r = ((EncodeTiledFn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)c->E, dims, strides, box, estr,
@@ -411,7 +418,7 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
         for (int s = 0; s < 2; s++) {
             Species &sp = c->sp[s];
             sp.cap = p->capacity[s]; sp.q = p->charge[s]; sp.m = p->mass[s]; sp.spwt = p->spwt[s];
-            dalloc(&sp.x, sp.cap); dalloc(&sp.y, sp.cap); dalloc(&sp.vx, sp.cap); dalloc(&sp.vy, sp.cap);
+            dalloc(&sp.x, sp.cap + 2); dalloc(&sp.y, sp.cap + 2); dalloc(&sp.vx, sp.cap + 2); dalloc(&sp.vy, sp.cap + 2);   // +2: bulk slices are widened to even indices
             dalloc(&sp.den, g.nn); dalloc(&sp.acc, g.nn); dalloc(&sp.frac, 1); dalloc(&sp.frac_scratch, 2);
             dalloc(&sp.hist, (size_t)g.ntx * g.nty); dalloc(&sp.hist_next, (size_t)g.ntx * g.nty);
             dalloc(&sp.counters, 2);

@@ -23,24 +23,55 @@
 
 namespace picsp {
 
+#ifndef PICSP_REPL
+#define PICSP_REPL 1          // bank-staggered copies of the shared-memory window (1 = plain window, 4 = experiment)
+#endif
+#ifndef PICSP_BULK_PIPE
+#define PICSP_BULK_PIPE 1     // particle data streamed through shared memory by TMA bulk copies (0: per-thread register prefetch)
+#endif
+#ifndef PICSP_STAGES
+#define PICSP_STAGES 2
+#endif
 #ifndef PICSP_HALO
-#define PICSP_HALO 6
+#define PICSP_HALO 4
 #endif
 #ifndef PICSP_CHUNK
 #define PICSP_CHUNK 4096
 #endif
 constexpr int HALO = PICSP_HALO;              // cells of drift a window tolerates on each side
-constexpr int WIN = TILE + 1 + 2 * HALO;      // window edge in nodes (29)
+constexpr int WIN = TILE + 1 + 2 * HALO;      // window edge in nodes (25)
+// Bank-conflict avoidance by replication.  Particle positions inside a tile are random, so the 16-byte E
+// loads of a quarter-warp (8 lanes over 8 bank groups) and the 4-byte accumulator atomics of a warp
+// (32 lanes over 32 banks) collide like birthdays: 2.7 and 3.7 wavefronts per access measured.  The window
+// is therefore kept REPL times, copy r shifted by 2r bank groups (E) / 8r banks (accumulators); every lane
+// computes its rank among the lanes that would collide with it (one VOTE / one MATCH) and takes the copy
+// that lands it on a bank of its own.  All copies hold the same E and the accumulator copies are summed at
+// the flush, so ANY choice is correct: the choice only decides speed.
+constexpr int REPL = PICSP_REPL;
+constexpr int WPITCH = (REPL > 1) ? WIN + 2 * (REPL - 1) : WIN;        // E row pitch in nodes (copy r starts 2r nodes in)
+constexpr int E_COPY = ((WIN * WPITCH + 7) / 8) * 8;                   // nodes per E copy: multiple of 8 bank groups
+constexpr int ACC_COPY = (REPL > 1) ? (((WIN * WIN + 23) / 32) * 32 + 8) : WIN * WIN;   // words per accumulator copy: == 8 (mod 32)
+static_assert(REPL == 1 || REPL == 4, "REPL must be 1 or 4");
+static_assert(REPL == 1 || (ACC_COPY % 32 == 8 && ACC_COPY >= WIN * WIN), "accumulator copy stride must be 8 mod 32");
+constexpr size_t MOVER_WINDOW_BYTES = ((sizeof(double2) * (size_t)REPL * E_COPY + 2 * sizeof(unsigned) * (size_t)REPL * ACC_COPY + 127) / 128) * 128;
 constexpr int CHUNK = PICSP_CHUNK;            // particles per CTA work item
 constexpr int MAX_FRAC_TILED = 51;            // w*2^frac <= 2^51 keeps (w*2^frac + 2^52) below 2^53: the magic-number conversion is exact
 #ifndef PICSP_MOVER_THREADS
-#define PICSP_MOVER_THREADS 256
+#define PICSP_MOVER_THREADS (PICSP_REPL > 1 ? 512 : 128)
 #endif
 constexpr int MOVER_THREADS = PICSP_MOVER_THREADS;
 #ifndef PICSP_MOVER_MIN_CTAS
-#define PICSP_MOVER_MIN_CTAS 4
+#define PICSP_MOVER_MIN_CTAS (PICSP_REPL > 1 ? 2 : 8)     // 8 x 128 threads: small CTAs interleave their load / compute / flush phases best (profiles/r01_sweeps.md)
 #endif
 constexpr int MOVER_MIN_CTAS = PICSP_MOVER_MIN_CTAS;
+// Particle pipeline: the chunk is consumed in slices of MOVER_THREADS particles.  One elected thread keeps
+// STAGES-1 slices in flight with TMA bulk copies (cp.async.bulk, completion on an mbarrier per stage); the
+// threads read their particle from shared memory.  Global-load latency is then covered by the copy engine,
+// not by registers or occupancy (the register-prefetch version spent 38 % of its stall samples on it).
+constexpr bool BULK_PIPE = PICSP_BULK_PIPE != 0;
+constexpr int STAGES = PICSP_STAGES;
+constexpr int STAGE_W = MOVER_THREADS + 2;          // doubles per array per stage (+2: a slice may start at an odd index)
+constexpr size_t MOVER_SMEM_BYTES = MOVER_WINDOW_BYTES + (BULK_PIPE ? sizeof(double) * (size_t)STAGES * 4 * STAGE_W : 0) + 64;
 
 struct __align__(16) Chunk {
     long long start;   // first particle (index into the species arrays)
@@ -229,6 +260,12 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, 
         ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
+// 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completes on bar
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 struct TileCtx {
     int wx0, wy0;        // window origin (node indices, may be negative)
     int ilo, jlo;        // cells whose four nodes lie inside window AND grid: [ilo, ilo+ispan] x [jlo, jlo+jspan]
@@ -262,8 +299,20 @@ __device__ __forceinline__ int push_one(double &px, double &py, double &pvx, dou
             if (iter == 0) { oi = i; oj = j; }
             if ((unsigned)(i - tc.ilo) <= tc.ispan && (unsigned)(j - tc.jlo) <= tc.jspan) {
                 double di = lx - fi, dj = ly - fj;
-                const double2 *w = sE + ((i - tc.wx0) * WIN + (j - tc.wy0));
-                double2 f00 = w[0], f01 = w[1], f10 = w[WIN], f11 = w[WIN + 1];
+                const int li = i - tc.wx0, lj = j - tc.wy0;
+                int e0 = li * WPITCH + lj;                       // node offset inside copy 0
+                if (REPL > 1) {
+                    // lanes of my quarter-warp with my bank-group parity; the r-th of them takes copy r
+                    const unsigned act = __activemask();
+                    const unsigned lane = threadIdx.x & 31u;
+                    const unsigned odd = __ballot_sync(act, e0 & 1);
+                    const unsigned mine = ((e0 & 1) ? odd : ~odd) & act & (0xFFu << (lane & 24u));
+                    const int rank = __popc(mine & ((1u << lane) - 1u));
+                    const int r = (((e0 & 1) + 2 * (rank & 3) - e0) >> 1) & 3;   // bank group (e0 + 2r) mod 8 == parity + 2*rank
+                    e0 += r * (E_COPY + 2);
+                }
+                const double2 *w = sE + e0;
+                double2 f00 = w[0], f01 = w[1], f10 = w[WPITCH], f11 = w[WPITCH + 1];
                 double a = 1 - di, b = 1 - dj;
                 double w00 = a * b, w10 = di * b, w01 = a * dj, w11 = di * dj;
                 e.x = f00.x * w00 + f10.x * w10 + f01.x * w01 + f11.x * w11;
@@ -326,7 +375,15 @@ __device__ __forceinline__ bool deposit_one(double px, double py, const PushCons
     unsigned long long w01 = (unsigned long long)__double_as_longlong(fma(a, dj, magic)) & mm;
     unsigned long long w11 = (unsigned long long)__double_as_longlong(fma(d, dj, magic)) & mm;
     if ((unsigned)(i - tc.ilo) <= tc.ispan && (unsigned)(j - tc.jlo) <= tc.jspan) {
-        const int k = (i - tc.wx0) * WIN + (j - tc.wy0);
+        int k = (i - tc.wx0) * WIN + (j - tc.wy0);
+        if (REPL > 1) {
+            // lanes whose node index is congruent to mine mod 8 share my banks; the r-th of them takes copy r
+            const unsigned act = __activemask();
+            const unsigned peers = __match_any_sync(act, k & 7);
+            const int rank = __popc(peers & ((1u << (threadIdx.x & 31u)) - 1u));
+            const int r = (((k & 7) + 8 * (rank & 3) - k) >> 3) & 3;            // bank (k + 8r) mod 32 == class + 8*rank
+            k += r * ACC_COPY;
+        }
         add64_limbs(sLo, sHi, k, w00);
         add64_limbs(sLo, sHi, k + WIN, w10);
         add64_limbs(sLo, sHi, k + 1, w01);
@@ -352,11 +409,13 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
              const int *__restrict__ nchunks, PushConst c, const double2 *__restrict__ E,
              long long *__restrict__ acc, const int *__restrict__ frac, unsigned int *__restrict__ hist_next,
              unsigned long long *__restrict__ counters, int *__restrict__ err) {
-    __shared__ __align__(128) double2 sE[WIN * WIN];
-    __shared__ unsigned sLo[WIN * WIN];
-    __shared__ unsigned sHi[WIN * WIN];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *sE = reinterpret_cast<double2 *>(smem_raw);                               // REPL copies of E_COPY nodes
+    unsigned *sLo = reinterpret_cast<unsigned *>(smem_raw + sizeof(double2) * (size_t)REPL * E_COPY);
+    unsigned *sHi = sLo + (size_t)REPL * ACC_COPY;
     __shared__ unsigned sCnt[9];
     __shared__ __align__(8) unsigned long long sBar;
+    __shared__ __align__(8) unsigned long long sFull[STAGES];
 
     if ((int)blockIdx.x >= *nchunks) return;
     const Chunk ck = chunks[blockIdx.x];
@@ -371,15 +430,20 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
     tc.xl_bits = (unsigned long long)__double_as_longlong(c.xl);
     tc.yl_bits = (unsigned long long)__double_as_longlong(c.yl);
 
-    if (MODE != 1 && tid == 0) {
+    if (tid == 0) {
         mbar_init(&sBar, 1);
+        for (int st = 0; st < STAGES; st++) mbar_init(&sFull[st], 1);
         fence_barrier_init();
-        mbar_expect_tx(&sBar, (uint32_t)(WIN * WIN * sizeof(double2)));
-        // tensor = E viewed as [nix][2*niy] doubles; box = [WIN][2*WIN]; out-of-grid elements arrive as 0
-        tma_load_2d(sE, &tmapE, 2 * tc.wy0, tc.wx0, &sBar);
+    }
+    if (MODE != 1 && tid == 0) {
+        mbar_expect_tx(&sBar, (uint32_t)(REPL * WIN * WPITCH * sizeof(double2)));
+        // tensor = E viewed as [nix][2*niy] doubles; box = [WIN][2*WPITCH]; out-of-grid elements arrive as 0.
+        // copy r is loaded 2r nodes to the left, so node (li, lj) sits at column lj + 2r: two bank groups further
+#pragma unroll
+        for (int r = 0; r < REPL; r++) tma_load_2d(sE + (size_t)r * E_COPY, &tmapE, 2 * (tc.wy0 - 2 * r), tc.wx0, &sBar);
     }
     if (MODE != 2)
-        for (int k = tid; k < WIN * WIN; k += MOVER_THREADS) { sLo[k] = 0u; sHi[k] = 0u; }
+        for (int k = tid; k < REPL * ACC_COPY; k += MOVER_THREADS) { sLo[k] = 0u; sHi[k] = 0u; }
     if (tid < 9) sCnt[tid] = 0u;
 
     // chunk-local pointers: 32-bit indexing inside the loop
@@ -388,33 +452,13 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
     double *__restrict__ cvx = vx + ck.start;
     double *__restrict__ cvy = vy + ck.start;
     const int count = ck.count;
-    const int last = count - 1;
     const bool nbr_ok = (c.ntx >= 3 && c.nty >= 3);
-
-    // first particle of this thread in flight while the window lands
-    int k = tid;
-    double px, py, pvx = 0, pvy = 0;
-    {
-        const int k0 = min(k, last);
-        px = cx[k0]; py = cy[k0];
-        if (MODE != 1) { pvx = cvx[k0]; pvy = cvy[k0]; }
-    }
-    __syncthreads();
-    if (MODE != 1) mbar_wait(&sBar, 0);
-
     const double inv_dx = 1.0 / c.dx;
     const double scale = (MODE != 2) ? exp2((double)*frac) : 0.0;
     unsigned extra = 0, outside = 0, same = 0;
 
-    while (k < count) {
-        // software prefetch of this thread's next particle (predicated: no redundant traffic)
-        const int kn = k + MOVER_THREADS;
-        double nx = px, ny = py, nvx = pvx, nvy = pvy;
-        if (kn < count) {
-            nx = cx[kn]; ny = cy[kn];
-            if (MODE != 1) { nvx = cvx[kn]; nvy = cvy[kn]; }
-        }
-
+    // everything that happens to particle k of the chunk
+    auto process = [&](int k, double px, double py, double pvx, double pvy) {
         int oi = -1, oj = -1;
         if (MODE != 1) {
             extra += push_one(px, py, pvx, pvy, c, inv_dx, tc, sE, E, err, oi, oj);
@@ -453,7 +497,70 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
                 if (ax > 1 || ay > 1) atomicOr(err, ERR_BIT_DISPLACEMENT);
             }
         }
-        k = kn; px = nx; py = ny; pvx = nvx; pvy = nvy;
+    };
+
+    if (BULK_PIPE) {
+        double *sP = reinterpret_cast<double *>(smem_raw + MOVER_WINDOW_BYTES);      // [STAGES][4][STAGE_W]
+        constexpr int NARR = (MODE == 1) ? 2 : 4;
+        const int niter = (count + MOVER_THREADS - 1) / MOVER_THREADS;
+        // slice `it` -> stage it % STAGES.  Bulk copies need 16-byte alignment: the slice is widened to even
+        // particle indices (the extra neighbours are never read).
+        auto issue = [&](int it) {
+            const int st = it % STAGES;
+            const long long first = ck.start + (long long)it * MOVER_THREADS;
+            const int cnt = min(MOVER_THREADS, count - it * MOVER_THREADS);
+            const long long a0 = first & ~1ll, a1 = (first + cnt + 1) & ~1ll;
+            const uint32_t bytes = (uint32_t)((a1 - a0) * sizeof(double));
+            double *dst = sP + (size_t)st * 4 * STAGE_W;
+            mbar_expect_tx(&sFull[st], NARR * bytes);
+            bulk_load(dst, x + a0, bytes, &sFull[st]);
+            bulk_load(dst + STAGE_W, y + a0, bytes, &sFull[st]);
+            if (MODE != 1) {
+                bulk_load(dst + 2 * STAGE_W, vx + a0, bytes, &sFull[st]);
+                bulk_load(dst + 3 * STAGE_W, vy + a0, bytes, &sFull[st]);
+            }
+        };
+        if (tid == 0)
+            for (int it = 0; it < STAGES - 1 && it < niter; it++) issue(it);
+        __syncthreads();                       // accumulators zeroed, barriers initialised
+        if (MODE != 1) mbar_wait(&sBar, 0);    // E window landed
+        for (int it = 0; it < niter; it++) {
+            const int st = it % STAGES;
+            // the stage refilled here was drained in iteration it-1 (barrier at the end of that iteration)
+            if (tid == 0 && it + STAGES - 1 < niter) issue(it + STAGES - 1);
+            mbar_wait(&sFull[st], (uint32_t)((it / STAGES) & 1));
+            const int k = it * MOVER_THREADS + tid;
+            if (k < count) {
+                const double *src = sP + (size_t)st * 4 * STAGE_W + (int)((ck.start + (long long)it * MOVER_THREADS) & 1ll) + tid;
+                const double px = src[0], py = src[STAGE_W];
+                double pvx = 0, pvy = 0;
+                if (MODE != 1) { pvx = src[2 * STAGE_W]; pvy = src[3 * STAGE_W]; }
+                process(k, px, py, pvx, pvy);
+            }
+            __syncthreads();
+        }
+    } else {
+        // per-thread register prefetch: the next particle's loads are in flight while the current one is processed
+        const int last = count - 1;
+        int k = tid;
+        double px, py, pvx = 0, pvy = 0;
+        {
+            const int k0 = min(k, last);
+            px = cx[k0]; py = cy[k0];
+            if (MODE != 1) { pvx = cvx[k0]; pvy = cvy[k0]; }
+        }
+        __syncthreads();
+        if (MODE != 1) mbar_wait(&sBar, 0);
+        while (k < count) {
+            const int kn = k + MOVER_THREADS;
+            double nx = px, ny = py, nvx = pvx, nvy = pvy;
+            if (kn < count) {
+                nx = cx[kn]; ny = cy[kn];
+                if (MODE != 1) { nvx = cvx[kn]; nvy = cvy[kn]; }
+            }
+            process(k, px, py, pvx, pvy);
+            k = kn; px = nx; py = ny; pvx = nvx; pvy = nvy;
+        }
     }
     for (int o = 16; o > 0; o >>= 1) {
         extra += __shfl_xor_sync(0xffffffffu, extra, o);
@@ -470,7 +577,10 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
     // flush the window: limbs -> one native 64-bit integer RED per touched node
     if (MODE != 2) {
         for (int q = tid; q < WIN * WIN; q += MOVER_THREADS) {
-            unsigned long long v = ((unsigned long long)sHi[q] << 32) | (unsigned long long)sLo[q];
+            unsigned long long v = 0;
+#pragma unroll
+            for (int r = 0; r < REPL; r++)
+                v += ((unsigned long long)sHi[q + r * ACC_COPY] << 32) | (unsigned long long)sLo[q + r * ACC_COPY];
             if (v) {
                 int li = q / WIN, lj = q - li * WIN;
                 long long gi = tc.wx0 + li, gj = tc.wy0 + lj;
