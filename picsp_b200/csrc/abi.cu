@@ -130,12 +130,11 @@ template <int MODE> void launch_tile_mover(picsp_ctx *c, int s) {
     Species &sp = c->sp[s];
     CUtensorMap tm;
     memcpy(&tm, c->tmapE, sizeof(tm));
-    static bool smem_opted_in = false;     // dynamic shared memory above 48 KB needs a per-function opt-in
-    if (!smem_opted_in) {
+    if (!c->smem_opted_in) {               // dynamic shared memory above 48 KB needs a per-function opt-in (per device)
         PICSP_CUDA(cudaFuncSetAttribute(k_tile_mover<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVER_SMEM_BYTES));
         PICSP_CUDA(cudaFuncSetAttribute(k_tile_mover<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVER_SMEM_BYTES));
         PICSP_CUDA(cudaFuncSetAttribute(k_tile_mover<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVER_SMEM_BYTES));
-        smem_opted_in = true;
+        c->smem_opted_in = true;
     }
     PICSP_LAUNCH(c, (k_tile_mover<MODE>), mover_grid(sp), MOVER_THREADS, MOVER_SMEM_BYTES, tm, sp.x, sp.y, sp.vx, sp.vy,
                  (const Chunk *)sp.chunks, sp.nchunks, push_const(c, s), c->E, sp.acc, sp.frac, sp.hist_next,

@@ -125,6 +125,7 @@ struct picsp_ctx {
     // TMA descriptor of E viewed as [nix][2*niy] doubles (128 bytes, CUtensorMap)
     alignas(64) unsigned char tmapE[128];
     bool have_tmap = false;
+    bool smem_opted_in = false;
 
     // staging for un-permuted downloads
     double *stage = nullptr; int64_t stage_cap = 0;
