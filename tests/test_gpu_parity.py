@@ -279,6 +279,32 @@ def test_charge_conservation_large():
         assert x.min() >= 0 and x.max() < xl and y.min() >= 0 and y.max() < xl
 
 
+@pytest.mark.parametrize("numx", [256, 1024, 2048])
+def test_spectral_solve_at_baseline_grid_sizes(numx):
+    """spectralPotentialSolver (main.cpp:960-1058) on the node counts of BASELINE configs 2, 4 and 5
+    (257 is prime, 1025 = 5^2*41, 2049 = 3*683: cuFFT takes its mixed-radix / Bluestein paths) against the
+    oracle's DFT (cached double-precision Bluestein, itself checked against the long-double engine)."""
+    nm = normalise()
+    rng = np.random.default_rng(numx)
+    nix = numx + 1
+    rho = np.zeros((nix, nix)); rho[1:-1, 1:-1] = rng.standard_normal((nix - 2, nix - 2))
+    Oracle.lib().oracle_set_fft_mode(3)
+    try:
+        o = Oracle(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], 8, 8, solver=1)
+        o.set_grid("rho", rho)
+        o.spectralPotentialSolver()
+    finally:
+        Oracle.lib().oracle_set_fft_mode(0)
+    with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], 8, 8, solverType=1)) as sim:
+        sim.set_grid("rho", rho)
+        sim.spectralPotentialSolver()
+        err = relerr(sim.grid("phi"), o.phi)
+        assert err <= RTOL, f"phi rel err {err:.3e} at {nix}^2 nodes"
+        sim.computeEF()
+        o.computeEF()
+        assert relerr(sim.grid("efx"), o.efx) <= RTOL and relerr(sim.grid("efy"), o.efy) <= RTOL
+
+
 def test_full_size_cross_implementation_and_determinism():
     """BASELINE-scale grid (1024^2 cells, spectral), 4e7 particles: the tiled/fused path (TMA windows, shared-memory
     fixed point, periodic sort) and the unsorted path (global gathers, global 64-bit REDs) are two independent
