@@ -218,7 +218,7 @@ void op_grid_phase(picsp_ctx *c) {
             sp.acc_valid = false;
         }
         const int clear = (c->prm.flags & PICSP_FLAG_CLEAR_DENSITY) ? 1 : 0;
-        PICSP_LAUNCH(c, k_grid_phase, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, gs[0], gs[1], c->rho, g.nix, g.niy, clear);
+        PICSP_LAUNCH(c, k_grid_phase, dim3((g.niy + 255) / 256, g.nix), 256, 0, gs[0], gs[1], c->rho, g.nix, g.niy, clear);
     }
     if (c->comm) op_allreduce_rho(c);    // the folds are linear: folding the partial rho first commutes with the sum
 }
