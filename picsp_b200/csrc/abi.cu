@@ -92,6 +92,15 @@ void compute_frac(picsp_ctx *c, int s) {
 // -- tile binning -------------------------------------------------------------------------
 int mover_grid(const Species &sp);
 
+// Particles per CTA work item: CHUNK (4096) for big populations; smaller when there are too few particles to give
+// every SM several waves of CTAs (tail effect), never below 512, always a multiple of the slice size.
+int pick_chunk(const picsp_ctx *c, int64_t n) {
+    const int64_t want_ctas = (int64_t)c->num_sms * MOVER_MIN_CTAS * 6;
+    int64_t ch = (n + want_ctas - 1) / want_ctas;
+    ch = ((ch + MOVER_THREADS - 1) / MOVER_THREADS) * MOVER_THREADS;
+    return (int)std::min<int64_t>(CHUNK, std::max<int64_t>(512, ch));
+}
+
 void op_sort(picsp_ctx *c, int s) {
     PhaseScope ph(c, PICSP_PHASE_SORT);
     Species &sp = c->sp[s];
@@ -105,7 +114,8 @@ void op_sort(picsp_ctx *c, int s) {
     }
     const uint32_t *ids = sp.has_perm ? sp.id : (const uint32_t *)nullptr;
     // new bin offsets / chunk table go to the second table: the re-sort kernel still walks the current one
-    PICSP_LAUNCH(c, k_scan_tiles, 1, 1024, 0, sp.hist, nt, sp.tile_off, (Chunk *)sp.chunks2, sp.nchunks2, sp.cursor);
+    sp.chunk = pick_chunk(c, sp.n);
+    PICSP_LAUNCH(c, k_scan_tiles, 1, 1024, 0, sp.hist, nt, sp.tile_off, (Chunk *)sp.chunks2, sp.nchunks2, sp.cursor, sp.chunk);
     if (sp.n > 0) {
         if (sp.sorted)
             PICSP_LAUNCH(c, k_resort_chunks, mover_grid(sp), RESORT_THREADS, 0, sp.x, sp.y, sp.vx, sp.vy, ids,
@@ -122,8 +132,8 @@ void op_sort(picsp_ctx *c, int s) {
 }
 
 int mover_grid(const Species &sp) {
-    long long b = sp.n / CHUNK + sp.max_chunks - sp.cap / CHUNK;   // n/CHUNK + ntiles + 1 (upper bound on chunks)
-    return (int)std::max<long long>(1, b);
+    long long b = sp.n / sp.chunk + sp.ntiles + 1;   // upper bound on the number of chunks
+    return (int)std::max<long long>(1, std::min<long long>(b, sp.max_chunks));
 }
 
 template <int MODE> void launch_tile_mover(picsp_ctx *c, int s) {
@@ -218,7 +228,7 @@ void op_grid_phase(picsp_ctx *c) {
             sp.acc_valid = false;
         }
         const int clear = (c->prm.flags & PICSP_FLAG_CLEAR_DENSITY) ? 1 : 0;
-        PICSP_LAUNCH(c, k_grid_phase, dim3((g.niy + 255) / 256, g.nix), 256, 0, gs[0], gs[1], c->rho, g.nix, g.niy, clear);
+        PICSP_LAUNCH(c, k_grid_phase, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, gs[0], gs[1], c->rho, g.nix, g.niy, clear);
     }
     if (c->comm) op_allreduce_rho(c);    // the folds are linear: folding the partial rho first commutes with the sum
 }
@@ -422,7 +432,8 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
             dalloc(&sp.hist, (size_t)g.ntx * g.nty); dalloc(&sp.hist_next, (size_t)g.ntx * g.nty);
             dalloc(&sp.counters, 2);
             sp.sort_period = (s == 0) ? 96 : 12;
-            sp.max_chunks = sp.cap / CHUNK + (long long)g.ntx * g.nty + 1;
+            sp.ntiles = g.ntx * g.nty;
+            sp.max_chunks = sp.cap / 512 + (long long)g.ntx * g.nty + 1;   // 512 = smallest chunk pick_chunk() returns
             dalloc(&sp.tile_off, (size_t)g.ntx * g.nty + 1);
             dalloc((Chunk **)&sp.chunks, (size_t)sp.max_chunks);
             dalloc(&sp.nchunks, 1);

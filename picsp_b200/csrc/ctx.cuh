@@ -91,6 +91,8 @@ struct Species {
     int *nchunks2 = nullptr;
     unsigned int *cursor = nullptr;// ntiles
     long long max_chunks = 0;
+    int chunk = 4096;              // particles per CTA work item of the current binning (pick_chunk)
+    int ntiles = 0;
 };
 
 struct PhaseTimer {

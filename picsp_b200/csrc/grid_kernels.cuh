@@ -79,11 +79,9 @@ __device__ __forceinline__ double finalize_node(const GridPhaseSpecies &sp, long
 __global__ void k_grid_phase(GridPhaseSpecies s0, GridPhaseSpecies s1, double *__restrict__ rho, int nix, int niy, int clear) {
     const int L = nix - 1, M = niy - 1;
     const double sc0 = s0.weight * exp2((double)(-*s0.frac)), sc1 = s1.weight * exp2((double)(-*s1.frac));
-    // 2-D launch: blockIdx.y = row i, threads along j (coalesced, no index division, one node per thread)
-    const int i = blockIdx.y;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < niy) {
-        const long long k = (long long)i * niy + j;
+    const unsigned nn = (unsigned)nix * (unsigned)niy;      // <= 2^31 by the capacity of int node counts
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < nn; k += gridDim.x * blockDim.x) {
+        const int i = (int)(k / (unsigned)niy), j = (int)(k - (unsigned)i * (unsigned)niy);
         if (i > 0 && i < L && j > 0 && j < M) {              // interior node
             const double di = finalize_node(s0, k, sc0, clear), de = finalize_node(s1, k, sc1, clear);
             s0.den[k] = di; s1.den[k] = de;

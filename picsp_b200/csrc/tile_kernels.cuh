@@ -85,14 +85,14 @@ struct __align__(16) Chunk {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
 k_scan_tiles(const unsigned int *__restrict__ hist, int ntiles, long long *__restrict__ tile_off,
-             Chunk *__restrict__ chunks, int *__restrict__ nchunks, unsigned int *__restrict__ cursor) {
+             Chunk *__restrict__ chunks, int *__restrict__ nchunks, unsigned int *__restrict__ cursor, int chunk) {
     __shared__ long long s_part[1024];
     __shared__ int s_chunk[1024];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int per = (ntiles + nt - 1) / nt;
     const int lo = tid * per, hi = min(lo + per, ntiles);
     long long sum = 0; int csum = 0;
-    for (int t = lo; t < hi; t++) { unsigned int h = hist[t]; sum += h; csum += (int)((h + CHUNK - 1) / CHUNK); }
+    for (int t = lo; t < hi; t++) { unsigned int h = hist[t]; sum += h; csum += (int)((h + chunk - 1) / chunk); }
     s_part[tid] = sum; s_chunk[tid] = csum;
     __syncthreads();
     if (tid == 0) {
@@ -107,8 +107,8 @@ k_scan_tiles(const unsigned int *__restrict__ hist, int ntiles, long long *__res
         unsigned int h = hist[t];
         tile_off[t] = off;
         cursor[t] = 0u;
-        for (unsigned int done = 0; done < h; done += CHUNK) {
-            Chunk ck; ck.start = off + done; ck.count = (int)min((unsigned int)CHUNK, h - done); ck.tile = t;
+        for (unsigned int done = 0; done < h; done += chunk) {
+            Chunk ck; ck.start = off + done; ck.count = (int)min((unsigned int)chunk, h - done); ck.tile = t;
             chunks[coff++] = ck;
         }
         off += h;
