@@ -3,6 +3,7 @@
 summaries committed under profiles/.
 
   python profiles/summarize.py launches gpurun_out/launches_X.csv          # per-kernel launch table
+  python profiles/summarize.py launches gpurun_out/launches_X.csv 'k_tile_mover<0>' 2   # only after the 2nd mover launch
   python profiles/summarize.py full gpurun_out/prof_X.ncu-rep [regex]      # key counters of an ncu --set full capture
 """
 import collections
@@ -31,15 +32,22 @@ KEYS = [
 ]
 
 
-def launches(path):
+def launches(path, after_kernel=None, after_count=0):
+    """Per-kernel totals; with after_kernel/after_count only the launches AFTER the after_count-th launch of
+    that kernel are counted (used to cut the list down to bench.py's timed region)."""
     rows = list(csv.reader(l for l in open(path) if l.startswith('"')))
     hdr = rows[0]
     ki, vi, mi, ui = (hdr.index(k) for k in ("Kernel Name", "Metric Value", "Metric Name", "Metric Unit"))
     agg = collections.OrderedDict()
+    seen = 0
     for r in rows[1:]:
         if r[mi] != "gpu__time_duration.sum":
             continue
         name = re.sub(r"\(.*", "", r[ki]).strip()
+        if after_kernel is not None and seen < after_count:
+            if after_kernel in name:
+                seen += 1
+            continue
         v = float(r[vi].replace(",", ""))
         scale = {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3}[r[ui]]
         a = agg.setdefault(name, [0, 0.0])
@@ -67,6 +75,9 @@ def full(path, regex=None):
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
-        launches(sys.argv[2])
+        if len(sys.argv) > 4:
+            launches(sys.argv[2], sys.argv[3], int(sys.argv[4]))
+        else:
+            launches(sys.argv[2])
     else:
         full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
