@@ -123,6 +123,12 @@ def whole_run():
         keep[f"phi_{ts}"] = res[f"/phi/{ts}"]
     keep["den_e_0"] = res["/den.e/0"]; keep["den_i_50"] = res["/den.i/50"]
     keep["particle_e_0"] = res["/particle.e/0"]; keep["particle_i_0"] = res["/particle.i/0"]
+    # momentum trace: sum of velocities of each species at every dump (201 dumps), from the reference's own
+    # /particle.{i,e}/<ts> datasets — the north_star asks for energy AND momentum traces
+    ts_list = sorted(int(k.split("/")[-1]) for k in res if k.startswith("/particle.e/"))
+    keep["momentum_ts"] = np.array(ts_list)
+    keep["momentum"] = np.array([[res[f"/particle.i/{ts}"][:, 2].sum(), res[f"/particle.i/{ts}"][:, 3].sum(),
+                                  res[f"/particle.e/{ts}"][:, 2].sum(), res[f"/particle.e/{ts}"][:, 3].sum()] for ts in ts_list])
     names = sorted(k for k in res if not k.startswith("#"))
     keep["dataset_names"] = np.array(names)
     keep["groups"] = np.array(res["#groups"])
