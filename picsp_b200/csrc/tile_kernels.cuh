@@ -166,9 +166,9 @@ k_sort_scatter(const double *__restrict__ x, const double *__restrict__ y, const
 // and then writes: every CTA emits a few long sequential runs instead of isolated 256-byte pieces, and the
 // global cursor sees ~10 atomics per 4096 particles.  Far movers (rare) take a cursor slot individually.
 constexpr int RESORT_THREADS = 256;
-constexpr int RESORT_ITERS = (CHUNK + RESORT_THREADS - 1) / RESORT_THREADS;
+static_assert(CHUNK <= 4096, "k_resort_chunks packs a rank < 4096 into 12 bits");
 
-__global__ void __launch_bounds__(RESORT_THREADS)
+__global__ void __launch_bounds__(RESORT_THREADS, 6)
 k_resort_chunks(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ vx,
                 const double *__restrict__ vy, const uint32_t *__restrict__ id, const Chunk *__restrict__ chunks,
                 const int *__restrict__ nchunks, PushConst c, const long long *__restrict__ tile_off,
@@ -176,6 +176,7 @@ k_resort_chunks(const double *__restrict__ x, const double *__restrict__ y, cons
                 double *__restrict__ vx2, double *__restrict__ vy2, uint32_t *__restrict__ id2) {
     __shared__ unsigned s_cnt[9];
     __shared__ unsigned s_base[9];
+    __shared__ unsigned short s_code[CHUNK];     // class (4 bits) | rank inside the CTA and class (12 bits); kept out of registers
     if ((int)blockIdx.x >= *nchunks) return;
     const Chunk ck = chunks[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -184,10 +185,8 @@ k_resort_chunks(const double *__restrict__ x, const double *__restrict__ y, cons
     if (tid < 9) s_cnt[tid] = 0u;
     __syncthreads();
 
-    unsigned code[RESORT_ITERS];        // class (4 bits) | rank inside the CTA and class (<= 4096)
-#pragma unroll
-    for (int it = 0; it < RESORT_ITERS; it++) {
-        const int k = tid + it * RESORT_THREADS;
+    for (int k0 = 0; k0 < ck.count; k0 += RESORT_THREADS) {       // warp-uniform trip count
+        const int k = k0 + tid;
         const bool live = k < ck.count;
         int cls = 15;                   // 15: nothing to do in pass B
         if (live) {
@@ -209,7 +208,7 @@ k_resort_chunks(const double *__restrict__ x, const double *__restrict__ y, cons
         const int leader = __ffs(peers) - 1;
         if (cls < 9 && lane == leader) first = atomicAdd(&s_cnt[cls], (unsigned)__popc(peers));
         first = __shfl_sync(0xffffffffu, first, leader);
-        code[it] = (unsigned)cls | ((first + (unsigned)__popc(peers & ((1u << lane) - 1u))) << 4);
+        if (live) s_code[k] = (unsigned short)((unsigned)cls | ((first + (unsigned)__popc(peers & ((1u << lane) - 1u))) << 4));
     }
     __syncthreads();
     if (tid < 9 && s_cnt[tid]) {
@@ -217,13 +216,13 @@ k_resort_chunks(const double *__restrict__ x, const double *__restrict__ y, cons
         s_base[tid] = atomicAdd(&cursor[ux * c.nty + uy], s_cnt[tid]);
     }
     __syncthreads();
-#pragma unroll
-    for (int it = 0; it < RESORT_ITERS; it++) {
-        const int cls = (int)(code[it] & 15u);
+    for (int k = tid; k < ck.count; k += RESORT_THREADS) {
+        const unsigned code = s_code[k];
+        const int cls = (int)(code & 15u);
         if (cls < 9) {
-            const long long p = ck.start + tid + it * RESORT_THREADS;
+            const long long p = ck.start + k;
             const int ux = (tx + cls / 3 - 1 + c.ntx) % c.ntx, uy = (ty + cls % 3 - 1 + c.nty) % c.nty;
-            const long long dst = tile_off[ux * c.nty + uy] + s_base[cls] + (code[it] >> 4);
+            const long long dst = tile_off[ux * c.nty + uy] + s_base[cls] + (code >> 4);
             x2[dst] = x[p]; y2[dst] = y[p]; vx2[dst] = vx[p]; vy2[dst] = vy[p];
             id2[dst] = id ? id[p] : (uint32_t)p;
         }
