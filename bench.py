@@ -230,7 +230,7 @@ def main_ours(args, rank, world, local_rank):
     lo, hi = shard_range(n_species, rank, world)
     n_local = hi - lo
     sim = Simulation(Params(args.cells, args.cells, nm["dx"], nm["dt"], nm["mass_i"], n_species, n_species,
-                            solverType=1, device=local_rank, capacity=(n_local, n_local)))
+                            solverType=1, device=local_rank, capacity=(n_local, n_local), flags=args.flags))
     sim.fill_synthetic(ION, n_local, first_index=lo, seed=1, vth=nm["vth_i"], xdrift=0.0)
     sim.fill_synthetic(ELECTRON, n_local, first_index=lo, seed=2, vth=nm["vth_e"], xdrift=nm["drift_e"])
     if world > 1:
@@ -376,6 +376,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--sort-period-e", type=int, default=0, help="steps between electron tile sorts (0: library default)")
     ap.add_argument("--sort-period-i", type=int, default=0, help="steps between ion tile sorts (0: library default)")
+    ap.add_argument("--flags", type=int, default=0, help="PICSP_FLAG_* bits for A/B runs (16: stand-alone re-sort instead of the re-binning mover)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-particles", type=int, default=4_000_000, help="particles/species of the CPU sample")

@@ -63,6 +63,8 @@ void check_device_error(picsp_ctx *c) {
     if (*h) {
         int v = *h;
         PICSP_CUDA(cudaMemsetAsync(c->d_error, 0, sizeof(int), c->stream));
+        if (v & ERR_BIT_REBIN)
+            throw Error(PICSP_ERR_STATE, "internal: a re-binning mover overflowed a bin (histogram and bin function disagree)");
         if (v & ERR_BIT_RUNAWAY)
             throw Error(PICSP_ERR_DISPLACEMENT, "a particle needed more than 64 consecutive re-pushes (non-finite or absurd velocity)");
         throw Error(PICSP_ERR_DISPLACEMENT, "a particle moved by more than one particle tile (16 cells) in a single step");
@@ -101,8 +103,9 @@ int pick_chunk(const picsp_ctx *c, int64_t n) {
     return (int)std::min<int64_t>(CHUNK, std::max<int64_t>(512, ch));
 }
 
-void op_sort(picsp_ctx *c, int s) {
-    PhaseScope ph(c, PICSP_PHASE_SORT);
+// allocates the second buffer set, scans the histogram of the stored positions into the NEW bin offsets and
+// chunk table (second table: the kernels that move the particles still walk the current one), zeroes the cursors
+void sort_prepare(picsp_ctx *c, int s) {
     Species &sp = c->sp[s];
     const Geom &g = c->g;
     const int nt = g.ntx * g.nty;
@@ -112,10 +115,22 @@ void op_sort(picsp_ctx *c, int s) {
         dalloc(&sp.id, sp.cap); dalloc(&sp.id2, sp.cap);
         dalloc((Chunk **)&sp.chunks2, (size_t)sp.max_chunks); dalloc(&sp.nchunks2, 1);
     }
+    sp.chunk2 = pick_chunk(c, sp.n);
+    PICSP_LAUNCH(c, k_scan_tiles, 1, 1024, 0, sp.hist, nt, sp.tile_off, (Chunk *)sp.chunks2, sp.nchunks2, sp.cursor, sp.chunk2);
+}
+void sort_finish(picsp_ctx *c, int s) {
+    Species &sp = c->sp[s];
+    std::swap(sp.chunks, sp.chunks2); std::swap(sp.nchunks, sp.nchunks2); sp.chunk = sp.chunk2;
+    std::swap(sp.x, sp.x2); std::swap(sp.y, sp.y2); std::swap(sp.vx, sp.vx2); std::swap(sp.vy, sp.vy2);
+    std::swap(sp.id, sp.id2);
+    sp.has_perm = true; sp.sorted = true; sp.steps_since_sort = 0;
+}
+
+void op_sort(picsp_ctx *c, int s) {
+    PhaseScope ph(c, PICSP_PHASE_SORT);
+    Species &sp = c->sp[s];
+    sort_prepare(c, s);
     const uint32_t *ids = sp.has_perm ? sp.id : (const uint32_t *)nullptr;
-    // new bin offsets / chunk table go to the second table: the re-sort kernel still walks the current one
-    sp.chunk = pick_chunk(c, sp.n);
-    PICSP_LAUNCH(c, k_scan_tiles, 1, 1024, 0, sp.hist, nt, sp.tile_off, (Chunk *)sp.chunks2, sp.nchunks2, sp.cursor, sp.chunk);
     if (sp.n > 0) {
         if (sp.sorted)
             PICSP_LAUNCH(c, k_resort_chunks, mover_grid(sp), RESORT_THREADS, 0, sp.x, sp.y, sp.vx, sp.vy, ids,
@@ -125,10 +140,7 @@ void op_sort(picsp_ctx *c, int s) {
             PICSP_LAUNCH(c, k_sort_scatter, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy, ids,
                          (long long)sp.n, push_const(c, s), sp.tile_off, sp.cursor, sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2);
     }
-    std::swap(sp.chunks, sp.chunks2); std::swap(sp.nchunks, sp.nchunks2);
-    std::swap(sp.x, sp.x2); std::swap(sp.y, sp.y2); std::swap(sp.vx, sp.vx2); std::swap(sp.vy, sp.vy2);
-    std::swap(sp.id, sp.id2);
-    sp.has_perm = true; sp.sorted = true; sp.steps_since_sort = 0;
+    sort_finish(c, s);
 }
 
 int mover_grid(const Species &sp) {
@@ -138,17 +150,24 @@ int mover_grid(const Species &sp) {
 
 template <int MODE> void launch_tile_mover(picsp_ctx *c, int s) {
     Species &sp = c->sp[s];
+    RebinArgs rb = {};
+    if (MODE == 3) {
+        rb.id = sp.has_perm ? sp.id : (const uint32_t *)nullptr;
+        rb.tile_off = sp.tile_off; rb.cursor = sp.cursor;
+        rb.x2 = sp.x2; rb.y2 = sp.y2; rb.vx2 = sp.vx2; rb.vy2 = sp.vy2; rb.id2 = sp.id2;
+    }
     CUtensorMap tm;
     memcpy(&tm, c->tmapE, sizeof(tm));
     if (!c->smem_opted_in) {               // dynamic shared memory above 48 KB needs a per-function opt-in (per device)
         PICSP_CUDA(cudaFuncSetAttribute(k_tile_mover<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVER_SMEM_BYTES));
         PICSP_CUDA(cudaFuncSetAttribute(k_tile_mover<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVER_SMEM_BYTES));
         PICSP_CUDA(cudaFuncSetAttribute(k_tile_mover<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVER_SMEM_BYTES));
+        PICSP_CUDA(cudaFuncSetAttribute(k_tile_mover<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVER_SMEM_BYTES));
         c->smem_opted_in = true;
     }
     PICSP_LAUNCH(c, (k_tile_mover<MODE>), mover_grid(sp), MOVER_THREADS, MOVER_SMEM_BYTES, tm, sp.x, sp.y, sp.vx, sp.vy,
                  (const Chunk *)sp.chunks, sp.nchunks, push_const(c, s), c->E, sp.acc, sp.frac, sp.hist_next,
-                 sp.counters, c->d_error);
+                 sp.counters, c->d_error, rb);
 }
 
 // -- TMA descriptor of the E field -------------------------------------------------------
@@ -291,7 +310,12 @@ void op_push(picsp_ctx *c, int s) {
     Species &sp = c->sp[s];
     const bool fuse = !(c->prm.flags & PICSP_FLAG_NO_FUSE);
     const bool tile = tiled(c);
-    if (tile && (!sp.sorted || sp.steps_since_sort >= sp.sort_period)) op_sort(c, s);
+    const bool due = tile && sp.sorted && sp.steps_since_sort >= sp.sort_period;
+    // a periodic re-bin rides on the mover itself (MODE 3) when the fused bulk-pipeline mover is in use;
+    // the first binning of an arbitrary load, and the unfused mover, use the stand-alone sort
+    const bool rebin_in_mover = due && fuse && BULK_PIPE && sp.n > 0 && !(c->prm.flags & PICSP_FLAG_SEPARATE_SORT);
+    if (tile && (!sp.sorted || (due && !rebin_in_mover))) op_sort(c, s);
+    if (rebin_in_mover) { PhaseScope phs(c, PICSP_PHASE_SORT); sort_prepare(c, s); }
     if (fuse || tile) ensure_hist(c, s);   // histogram of the positions about to be pushed -> bound for acc
     if (fuse) compute_frac(c, s);
     PhaseScope ph(c, PICSP_PHASE_PUSH);
@@ -302,7 +326,9 @@ void op_push(picsp_ctx *c, int s) {
         PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
     if (sp.n > 0) {
         if (tile) {
-            if (fuse) launch_tile_mover<0>(c, s); else launch_tile_mover<2>(c, s);
+            if (rebin_in_mover) { launch_tile_mover<3>(c, s); sort_finish(c, s); }
+            else if (fuse) launch_tile_mover<0>(c, s);
+            else launch_tile_mover<2>(c, s);
         } else {
             const int blocks = particle_blocks(c, sp.n, 256);
             if (fuse)

@@ -92,6 +92,7 @@ struct Species {
     unsigned int *cursor = nullptr;// ntiles
     long long max_chunks = 0;
     int chunk = 4096;              // particles per CTA work item of the current binning (pick_chunk)
+    int chunk2 = 4096;             // ... of the binning under construction
     int ntiles = 0;
 };
 

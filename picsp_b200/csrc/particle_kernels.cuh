@@ -185,6 +185,7 @@ __global__ void k_deposit(const double *__restrict__ x, const double *__restrict
 // ---------------------------------------------------------------------------
 constexpr int ERR_BIT_DISPLACEMENT = 1;
 constexpr int ERR_BIT_RUNAWAY = 2;
+constexpr int ERR_BIT_REBIN = 4;
 
 template <bool FUSE_DEPOSIT>
 __global__ void __launch_bounds__(256)

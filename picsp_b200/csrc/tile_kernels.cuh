@@ -281,6 +281,43 @@ __device__ __forceinline__ bool in_range_bits(double v, unsigned long long limit
     return (unsigned long long)__double_as_longlong(v) < limit_bits;
 }
 
+// bilinear interpolation of E from the four corners of a cell (gather, src/main.cpp:671-681).  Written with
+// explicit roundings so that the window path and the straggler path are the same arithmetic bit for bit whatever the
+// compiler would contract: a particle's result must not depend on which bin it happens to be stored in.
+__device__ __forceinline__ double2 interp_E(double2 f00, double2 f01, double2 f10, double2 f11, double di, double dj) {
+    const double a = 1 - di, b = 1 - dj;
+    const double w00 = __dmul_rn(a, b), w10 = __dmul_rn(di, b), w01 = __dmul_rn(a, dj), w11 = __dmul_rn(di, dj);
+    double2 e;
+    e.x = __fma_rn(f11.x, w11, __fma_rn(f01.x, w01, __fma_rn(f10.x, w10, __dmul_rn(f00.x, w00))));
+    e.y = __fma_rn(f11.y, w11, __fma_rn(f01.y, w01, __fma_rn(f10.y, w10, __dmul_rn(f00.y, w00))));
+    return e;
+}
+
+// E at the position of a particle whose cell is outside its bin's window (it drifted since the last sort, or it
+// wrapped through the periodic boundary and is pushed again): same nodes from global memory, same arithmetic as the
+// window path.  i/j: the particle's cell, or -1 for a position outside the box (caller-supplied garbage; the mover
+// keeps particles inside), which takes the reference's flat-index gather with the zero guard band.  Rare: not inlined.
+struct Straggler { double ex, ey; int i, j; };     // returned by value: reference outputs would cost a stack frame
+__device__ __noinline__ Straggler gather_straggler(const double2 *__restrict__ E, double px, double py, double dx, double inv_dx,
+                                                   double xl, double yl, int nix, int niy, long long nn, long long guard) {
+    // scalars, not the PushConst: taking the address of the kernel parameter would give every thread a stack copy
+    PushConst c;
+    c.dx = dx; c.xl = xl; c.yl = yl; c.nix = nix; c.niy = niy; c.nn = nn; c.guard = guard;
+    Straggler r;
+    if (!in_box(px, py, c)) {
+        const double2 e = gather_E(E, c, to_logical(px, dx), to_logical(py, dx));
+        r.ex = e.x; r.ey = e.y; r.i = r.j = -1;
+        return r;
+    }
+    const double lx = to_logical_fast(px, dx, inv_dx), ly = to_logical_fast(py, dx, inv_dx);
+    double fi, fj;
+    r.i = floor_nonneg(lx, fi); r.j = floor_nonneg(ly, fj);    // -0.0 -> cell 0, as in tile_of()
+    const double2 *w = E + ((long long)r.i * niy + r.j);       // 0 <= pos < xl: all four corners are real nodes
+    const double2 e = interp_E(w[0], w[1], w[niy], w[niy + 1], lx - fi, ly - fj);
+    r.ex = e.x; r.ey = e.y;
+    return r;
+}
+
 // mover body for one particle (pushSpecies, src/main.cpp:779-846); returns the number of extra pushes.
 // oi/oj: cell the push starts from (-1 if outside the box).
 __device__ __forceinline__ int push_one(double &px, double &py, double &pvx, double &pvy, const PushConst &c,
@@ -311,16 +348,15 @@ __device__ __forceinline__ int push_one(double &px, double &py, double &pvx, dou
                     e0 += r * (E_COPY + 2);
                 }
                 const double2 *w = sE + e0;
-                double2 f00 = w[0], f01 = w[1], f10 = w[WPITCH], f11 = w[WPITCH + 1];
-                double a = 1 - di, b = 1 - dj;
-                double w00 = a * b, w10 = di * b, w01 = a * dj, w11 = di * dj;
-                e.x = f00.x * w00 + f10.x * w10 + f01.x * w01 + f11.x * w11;
-                e.y = f00.y * w00 + f10.y * w10 + f01.y * w01 + f11.y * w11;
+                e = interp_E(w[0], w[1], w[WPITCH], w[WPITCH + 1], di, dj);
                 done_fast = true;
             }
         }
-        if (!done_fast)   // straggler, wrapped or out-of-box position: the reference's flat-index gather
-            e = gather_E(E, c, to_logical(px, c.dx), to_logical(py, c.dx));
+        if (!done_fast) { // straggler, wrapped or out-of-box position
+            const Straggler r = gather_straggler(E, px, py, c.dx, inv_dx, c.xl, c.yl, c.nix, c.niy, c.nn, c.guard);
+            e.x = r.ex; e.y = r.ey;
+            if (iter == 0) { oi = r.i; oj = r.j; }
+        }
         pvx += c.dtqm * e.x;
         pvy += c.dtqm * e.y;
         px += c.dt * pvx;
@@ -398,21 +434,35 @@ __device__ __forceinline__ bool deposit_one(double px, double py, const PushCons
 
 // ---------------------------------------------------------------------------
 // the fused chunk kernel.  MODE 0: push + deposit(next step); 1: deposit only
-// (standalone scatterSpecies); 2: push only (PICSP_FLAG_NO_FUSE)
+// (standalone scatterSpecies); 2: push only (PICSP_FLAG_NO_FUSE);
+// MODE 3: MODE 0 that also RE-BINS: instead of writing the pushed particle back in place it writes it into
+// the new binned layout (destination = bin of the position the push STARTED from, whose histogram is known
+// before the launch), so a periodic re-sort costs no extra pass over the particles.  The store is then
+// "binned as of one step ago", which the window halo absorbs like any other drift.
 // counters[0] = extra pushes, counters[1] = particles that deposited outside their window
 // ---------------------------------------------------------------------------
+struct RebinArgs {
+    const uint32_t *id;            // current slot -> upload index (nullptr: identity)
+    const long long *tile_off;     // offsets of the NEW layout
+    unsigned int *cursor;          // per-bin fill cursors of the NEW layout (zeroed)
+    double *x2, *y2, *vx2, *vy2;   // destination arrays
+    uint32_t *id2;
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(MOVER_THREADS, MOVER_MIN_CTAS)
 k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, double *__restrict__ y,
              double *__restrict__ vx, double *__restrict__ vy, const Chunk *__restrict__ chunks,
              const int *__restrict__ nchunks, PushConst c, const double2 *__restrict__ E,
              long long *__restrict__ acc, const int *__restrict__ frac, unsigned int *__restrict__ hist_next,
-             unsigned long long *__restrict__ counters, int *__restrict__ err) {
+             unsigned long long *__restrict__ counters, int *__restrict__ err, RebinArgs rb) {
+    static_assert(MODE != 3 || BULK_PIPE, "the re-binning mover is built on the bulk-copy pipeline");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *sE = reinterpret_cast<double2 *>(smem_raw);                               // REPL copies of E_COPY nodes
     unsigned *sLo = reinterpret_cast<unsigned *>(smem_raw + sizeof(double2) * (size_t)REPL * E_COPY);
     unsigned *sHi = sLo + (size_t)REPL * ACC_COPY;
     __shared__ unsigned sCnt[9];
+    __shared__ unsigned sRbCnt[9], sRbBase[9];     // MODE 3: per-slice population / reserved base of each neighbour bin
     __shared__ __align__(8) unsigned long long sBar;
     __shared__ __align__(8) unsigned long long sFull[STAGES];
 
@@ -443,7 +493,7 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
     }
     if (MODE != 2)
         for (int k = tid; k < REPL * ACC_COPY; k += MOVER_THREADS) { sLo[k] = 0u; sHi[k] = 0u; }
-    if (tid < 9) sCnt[tid] = 0u;
+    if (tid < 9) { sCnt[tid] = 0u; sRbCnt[tid] = 0u; }
 
     // chunk-local pointers: 32-bit indexing inside the loop
     double *__restrict__ cx = x + ck.start;
@@ -457,11 +507,11 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
     unsigned extra = 0, outside = 0, same = 0;
 
     // everything that happens to particle k of the chunk
-    auto process = [&](int k, double px, double py, double pvx, double pvy) {
-        int oi = -1, oj = -1;
+    auto process = [&](int k, double &px, double &py, double &pvx, double &pvy, int &oi, int &oj) {
+        oi = oj = -1;
         if (MODE != 1) {
             extra += push_one(px, py, pvx, pvy, c, inv_dx, tc, sE, E, err, oi, oj);
-            cx[k] = px; cy[k] = py; cvx[k] = pvx; cvy[k] = pvy;
+            if (MODE != 3) { cx[k] = px; cy[k] = py; cvx[k] = pvx; cvy[k] = pvy; }
         }
         int ci = -1, cj = -1;
         if (MODE != 2) {
@@ -529,12 +579,56 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
             if (tid == 0 && it + STAGES - 1 < niter) issue(it + STAGES - 1);
             mbar_wait(&sFull[st], (uint32_t)((it / STAGES) & 1));
             const int k = it * MOVER_THREADS + tid;
-            if (k < count) {
+            const bool live = k < count;
+            double px = 0, py = 0, pvx = 0, pvy = 0;
+            int oi = -1, oj = -1;
+            if (live) {
                 const double *src = sP + (size_t)st * 4 * STAGE_W + (int)((ck.start + (long long)it * MOVER_THREADS) & 1ll) + tid;
-                const double px = src[0], py = src[STAGE_W];
-                double pvx = 0, pvy = 0;
+                px = src[0]; py = src[STAGE_W];
                 if (MODE != 1) { pvx = src[2 * STAGE_W]; pvy = src[3 * STAGE_W]; }
-                process(k, px, py, pvx, pvy);
+                process(k, px, py, pvx, pvy, oi, oj);
+            }
+            if (MODE == 3) {
+                // destination bin = bin of the position the push started from (same bin function as the histogram)
+                int cls = 15, tpre = 0;
+                if (live) {
+                    tpre = oi >= 0 ? tile_of_cell(oi, oj, c) : 0;
+                    int ddx = tpre / c.nty - tc.tx, ddy = tpre % c.nty - tc.ty;
+                    if (ddx > 1) ddx -= c.ntx; else if (ddx < -1) ddx += c.ntx;
+                    if (ddy > 1) ddy -= c.nty; else if (ddy < -1) ddy += c.nty;
+                    cls = (nbr_ok && ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1) ? (ddx + 1) * 3 + (ddy + 1) : 9;
+                }
+                // rank inside (slice, destination bin): warp-aggregated shared-memory counter
+                const unsigned lane = tid & 31u;
+                const unsigned peers = __match_any_sync(0xffffffffu, cls);
+                const int leader = __ffs(peers) - 1;
+                unsigned first = 0;
+                if (cls < 9 && (int)lane == leader) first = atomicAdd(&sRbCnt[cls], (unsigned)__popc(peers));
+                first = __shfl_sync(0xffffffffu, first, leader);
+                const unsigned rank = first + (unsigned)__popc(peers & ((1u << lane) - 1u));
+                __syncthreads();
+                if (tid < 9 && sRbCnt[tid]) {          // one contiguous reservation per destination bin and slice
+                    const int ux = (tc.tx + tid / 3 - 1 + c.ntx) % c.ntx, uy = (tc.ty + tid % 3 - 1 + c.nty) % c.nty;
+                    const int ut = ux * c.nty + uy;
+                    const unsigned base = atomicAdd(&rb.cursor[ut], sRbCnt[tid]);
+                    // the bin sizes come from the histogram taken by the previous launch: same bin function, so this never fires
+                    if ((long long)base + sRbCnt[tid] > rb.tile_off[ut + 1] - rb.tile_off[ut]) atomicOr(err, ERR_BIT_REBIN);
+                    sRbBase[tid] = base;
+                    sRbCnt[tid] = 0u;
+                }
+                __syncthreads();
+                if (live) {
+                    long long dst;
+                    if (cls < 9) {
+                        const int ux = (tc.tx + cls / 3 - 1 + c.ntx) % c.ntx, uy = (tc.ty + cls % 3 - 1 + c.nty) % c.nty;
+                        dst = rb.tile_off[ux * c.nty + uy] + sRbBase[cls] + rank;
+                    } else {                           // far bin (straggler of stragglers): individual slot
+                        dst = rb.tile_off[tpre] + atomicAdd(&rb.cursor[tpre], 1u);
+                    }
+                    const long long p = ck.start + k;
+                    rb.x2[dst] = px; rb.y2[dst] = py; rb.vx2[dst] = pvx; rb.vy2[dst] = pvy;
+                    rb.id2[dst] = rb.id ? rb.id[p] : (uint32_t)p;
+                }
             }
             __syncthreads();
         }
@@ -557,7 +651,8 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
                 nx = cx[kn]; ny = cy[kn];
                 if (MODE != 1) { nvx = cvx[kn]; nvy = cvy[kn]; }
             }
-            process(k, px, py, pvx, pvy);
+            int oi, oj;
+            process(k, px, py, pvx, pvy, oi, oj);
             k = kn; px = nx; py = ny; pvx = nvx; pvy = nvy;
         }
     }

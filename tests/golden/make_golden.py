@@ -136,8 +136,47 @@ def whole_run():
     print("wrote whole_run; energy[0], energy[-1] =", keep["energy"][0], keep["energy"][-1])
 
 
+def _envelope_member(perturb):
+    """One whole run of the shipped input.ini through the unmodified reference TU (-O0, like whole_run), with the x
+    coordinate of electron `perturb` moved by ONE ulp after loading (perturb < 0: untouched).  Same loop and dump
+    cadence as the reference's main() (main.cpp:453-531): traces sampled after the push of every 50th step."""
+    nm = normalise()
+    r = Reference(64, 64, nm["dx"], nm["dt"], nm["mass_i"], 10000, 10000, vth_i=nm["vth_i"], vth_e=nm["vth_e"],
+                  solver=2, lib_path=REF_O0_SO)
+    r.seed(0); r.init_both(2, 0.0, nm["drift_e"])
+    if perturb >= 0:
+        x, y, vx, vy = [a.copy() for a in r.get_species(ELECTRON)]
+        x[perturb] = np.nextafter(x[perturb], np.inf)
+        r.set_species(ELECTRON, x, y, vx, vy)
+    r.bootstrap()
+    mom, ke = [], []
+    for ts in range(10001):
+        r.step(1)
+        if ts % 50 == 0:
+            pi, pe = r.get_species(ION), r.get_species(ELECTRON)
+            mom.append([pi[2].sum(), pi[3].sum(), pe[2].sum(), pe[3].sum()])
+            ke.append([r.computeKE(ION), r.computeKE(ELECTRON)])
+    r.close()
+    return np.array(mom), np.array(ke)
+
+
+def chaos_envelope(members=(-1, 2500, 5001, 7777, 9998, 1234, 42, 6100)):
+    """How far the REFERENCE'S OWN long-run traces move under a one-ulp change of one particle coordinate: the
+    two-stream run of input.ini is chaotic, so this ensemble is the yardstick for 'agrees within a statistical
+    tolerance' (tests/test_gpu_host_run.py).  Member -1 is the unperturbed run and must reproduce whole_run()."""
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(min(len(members), os.cpu_count() or 1)) as pool:
+        res = pool.map(_envelope_member, members)
+    whole = np.load(os.path.join(OUT, "whole_run_input_ini.npz"))
+    assert np.array_equal(res[0][0], whole["momentum"]) and np.array_equal(res[0][1], whole["energy"]), \
+        "the unperturbed member must equal the reference's main()"
+    np.savez_compressed(os.path.join(OUT, "chaos_envelope_input_ini.npz"), members=np.array(members),
+                        momentum=np.array([m for m, _ in res]), energy=np.array([k for _, k in res]))
+    print("wrote chaos_envelope", len(members), "members")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["loops", "edge", "rng", "whole"]
+    which = sys.argv[1:] or ["loops", "edge", "rng", "whole", "envelope"]
     if "loops" in which:
         loop_case("loop_sor_65_load2_O0", 64, 1500, 2, 2, 4, lib=REF_O0_SO, drift_e=normalise()["drift_e"])
         loop_case("loop_sor_33_load1", 32, 1500, 2, 1, 4)
@@ -149,3 +188,5 @@ if __name__ == "__main__":
         rng_and_ini()
     if "whole" in which:
         whole_run()
+    if "envelope" in which:
+        chaos_envelope()

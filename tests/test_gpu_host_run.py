@@ -48,48 +48,69 @@ def test_whole_program_first_100_steps(tmp_path):
     assert np.allclose(e[:3], g["energy"][:3], rtol=1e-8, atol=0)
 
 
+def trace_stats(e, m, g, gm):
+    """Distances between two whole runs (KE traces e/g: 201 x 2, momentum traces m/gm: 201 x 4)."""
+    rel = np.abs(e - g) / np.abs(g)
+    pk_a, pk_b = int(np.argmax(e[:30, 1])), int(np.argmax(g[:30, 1]))
+    tr_a, tr_b = pk_a + int(np.argmin(e[pk_a:60, 1])), pk_b + int(np.argmin(g[pk_b:60, 1]))
+    return {
+        "ke_early": rel[:6].max(), "ke_all": rel.max(), "ke_final": rel[-1].max(),
+        "ke_logcorr": min(np.corrcoef(np.log(e[:, k]), np.log(g[:, k]))[0, 1] for k in (0, 1)),
+        "peak_shift": abs(pk_a - pk_b), "peak_value": abs(e[pk_a, 1] - g[pk_b, 1]) / g[pk_b, 1],
+        "trough_shift": abs(tr_a - tr_b), "trough_value": abs(e[tr_a, 1] - g[tr_b, 1]) / g[tr_b, 1],
+        "mom_early": (np.abs(m[:6] - gm[:6]).max(axis=1) / np.abs(gm[:6]).max(axis=1)).max(),
+        "mom_corr": np.array([np.corrcoef(m[:, k], gm[:, k])[0, 1] for k in range(4)]),
+        "mom_dev": np.array([np.abs(m[:, k] - gm[:, k]).max() / np.abs(gm[:, k]).max() for k in range(4)]),
+    }
+
+
 def test_long_run_energy_trace_statistics(tmp_path):
-    """north_star: 'energy ... traces over long runs must agree within a stated statistical tolerance, since
-    chaotic trajectories diverge'.  The full 10001-step run of the shipped input.ini (BASELINE config 1) against the
-    reference's own main().  Stated tolerances (measured in round 1 in brackets):
-      * dumps up to ts = 250, before the instability amplifies round-off: 1e-9 relative        [2.6e-13]
-      * position of the first KE_e maximum (ts ~ 650): +-1 dump; its value: 2 %               [same dump, 0.06 %]
-      * position of the following minimum (ts ~ 1200): +-2 dumps; its value: 5 %              [+1 dump, 1.0 %]
-      * every dump of the run: 10 % (electrons and ions)                                      [2.5 %, 1.0 %]
-      * final values: 5 %                                                                      [0.4 %, 0.9 %]
-      * correlation of the log-traces: >= 0.999                                               [0.99986, 0.999998]
-    Momentum (sum of velocities per species and component, from the 201 phase-space dumps) is a sum of signed
-    terms and diverges faster:
-      * dumps up to ts = 250: 1e-7 relative to the largest component                          [2e-9]
-      * correlation of each of the four traces with the reference's: >= 0.9                   [0.934 .. 0.997]
-      * largest deviation of a trace: <= 0.5 x the trace's own maximum                        [0.12 .. 0.42]"""
+    """north_star: 'energy and momentum traces over long runs must agree within a stated statistical tolerance,
+    since chaotic trajectories diverge'.  The full 10001-step run of the shipped input.ini (BASELINE config 1)
+    against the reference's own main().
+
+    The yardstick is the reference itself: tests/golden/chaos_envelope_input_ini.npz holds the traces of the
+    unmodified reference TU re-run with ONE particle coordinate moved by ONE ulp (8 members, member 0 = main()).
+    Round-off grows to O(1) differences after ts ~ 450; the spread between members is what 'the same run' means
+    from then on.  Stated tolerances (envelope = worst value over all pairs of distinct members):
+      * dumps up to ts = 250, before the instability amplifies round-off: KE 1e-9 relative, momentum 1e-7 of the
+        largest component                                       [envelope 9e-13; measured here 2.6e-13 and 2e-9]
+      * first KE_e maximum (ts ~ 650): position +-1 dump, value 2 %;  following minimum: +-2 dumps, 5 %
+      * KE at every dump: 2 x envelope (envelope 1.3 % ions, 5.7 % electrons);  final KE: 2 x envelope
+      * correlation of the log KE traces: 1 - corr <= 3 x envelope (envelope 1 - 0.99959)
+      * momentum (sum of velocities per species and component; signed sums, diverge fastest): correlation of each
+        trace with the reference's >= envelope minimum - 0.15 (envelope 0.99, 0.95, 0.82, 0.72); largest deviation
+        <= 2 x envelope (envelope 0.17, 1.29, 0.50, 0.39 of the trace's own maximum)."""
     gold = load_golden("whole_run_input_ini")
-    g = gold["energy"]
+    env = load_golden("chaos_envelope_input_ini")
+    g, gm = gold["energy"], gold["momentum"]
+    EK, EM = env["energy"], env["momentum"]
+    assert np.array_equal(EK[0], g) and np.array_equal(EM[0], gm), "member 0 of the envelope is the reference's main()"
+    pairs = [trace_stats(EK[a], EM[a], EK[b], EM[b]) for a in range(len(EK)) for b in range(len(EK))
+             if a != b and not np.array_equal(EM[a], EM[b])]
+    assert len(pairs) >= 20
+    worst = {k: (np.min([p[k] for p in pairs], axis=0) if k in ("ke_logcorr", "mom_corr") else np.max([p[k] for p in pairs], axis=0))
+             for k in pairs[0]}
+    assert worst["ke_early"] < 1e-9 and worst["peak_shift"] <= 1 and worst["trough_shift"] <= 2   # the fixed bounds hold for the reference itself
+
     out = str(tmp_path / "full.h5")
     host.run(INI, out, max_steps=-1, quiet=True)
-    e = h5mini.File(out).read("/timedata/energy")
-    assert e.shape == g.shape == (201, 2)
-    rel = np.abs(e - g) / np.abs(g)
-    assert rel[:6].max() < 1e-9
-    for a, b, in ((e, g),):
-        pk_a, pk_b = int(np.argmax(a[:30, 1])), int(np.argmax(b[:30, 1]))
-        assert abs(pk_a - pk_b) <= 1 and abs(a[pk_a, 1] - b[pk_b, 1]) <= 0.02 * b[pk_b, 1]
-        tr_a, tr_b = pk_a + int(np.argmin(a[pk_a:60, 1])), pk_b + int(np.argmin(b[pk_b:60, 1]))
-        assert abs(tr_a - tr_b) <= 2 and abs(a[tr_a, 1] - b[tr_b, 1]) <= 0.05 * b[tr_b, 1]
-    assert rel.max() < 0.10
-    assert (rel[-1] < 0.05).all()
-    for k in (0, 1):
-        assert np.corrcoef(np.log(e[:, k]), np.log(g[:, k]))[0, 1] >= 0.999
     f = h5mini.File(out)
-    gm = gold["momentum"]
+    e = f.read("/timedata/energy")
     m = np.array([[f.read(f"/particle.i/{ts}")[:, 2].sum(), f.read(f"/particle.i/{ts}")[:, 3].sum(),
                    f.read(f"/particle.e/{ts}")[:, 2].sum(), f.read(f"/particle.e/{ts}")[:, 3].sum()]
                   for ts in gold["momentum_ts"]])
-    assert m.shape == gm.shape == (201, 4)
-    assert (np.abs(m[:6] - gm[:6]).max(axis=1) <= 1e-7 * np.abs(gm[:6]).max(axis=1)).all()
-    for k in range(4):
-        assert np.corrcoef(m[:, k], gm[:, k])[0, 1] >= 0.9
-        assert np.abs(m[:, k] - gm[:, k]).max() <= 0.5 * np.abs(gm[:, k]).max()
+    assert e.shape == g.shape == (201, 2) and m.shape == gm.shape == (201, 4)
+    s = trace_stats(e, m, g, gm)
+    report = {k: (s[k], worst[k]) for k in s}
+    assert s["ke_early"] < 1e-9 and s["mom_early"] <= 1e-7, report
+    assert s["peak_shift"] <= 1 and s["peak_value"] <= 0.02, report
+    assert s["trough_shift"] <= 2 and s["trough_value"] <= 0.05, report
+    assert s["ke_all"] <= 2 * worst["ke_all"] and s["ke_final"] <= 2 * worst["ke_final"], report
+    assert 1 - s["ke_logcorr"] <= 3 * (1 - worst["ke_logcorr"]), report
+    assert (s["mom_corr"] >= worst["mom_corr"] - 0.15).all(), report
+    assert (s["mom_dev"] <= 2 * worst["mom_dev"]).all(), report
+    print("long-run statistics (ours vs reference, envelope):", report)
 
 
 def test_cli_executable_prints_the_reference_banner(tmp_path):

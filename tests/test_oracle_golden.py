@@ -135,3 +135,20 @@ def test_ini_golden_matches_shipped_values():
         cfg = json.load(f)
     assert cfg["numxCells"] == 64 and cfg["nParticlesI"] == 10000 and cfg["solverType"] == 2 and cfg["loadType"] == 2
     assert abs(cfg["timeStep"] - 0.005640957083153478) < 1e-18
+
+
+def test_chaos_envelope_is_anchored_on_the_reference_main():
+    """tests/golden/chaos_envelope_input_ini.npz (the reference re-run with one-ulp perturbations, the yardstick of
+    the long-run statistical test): member 0 is the unperturbed run and equals the reference's own main() trace."""
+    env, whole = load_golden("chaos_envelope_input_ini"), load_golden("whole_run_input_ini")
+    assert int(env["members"][0]) == -1
+    assert np.array_equal(env["energy"][0], whole["energy"]) and np.array_equal(env["momentum"][0], whole["momentum"])
+    assert env["energy"].shape[1:] == (201, 2) and env["momentum"].shape[1:] == (201, 4)
+    distinct = sum(not np.array_equal(env["momentum"][k], env["momentum"][0]) for k in range(1, len(env["members"])))
+    assert distinct >= 5
+    # before the instability has amplified the perturbation the members agree to round-off ...
+    early = np.abs(env["energy"][:, :6] - env["energy"][0, :6]) / env["energy"][0, :6]
+    assert early.max() < 1e-11
+    # ... afterwards they do not: this is why the long-run comparison is statistical
+    late = np.abs(env["energy"][:, -1] - env["energy"][0, -1]) / env["energy"][0, -1]
+    assert late.max() > 1e-3
