@@ -77,8 +77,18 @@ void ensure_hist(picsp_ctx *c, int s) {
     if (sp.hist_valid) return;
     const int nt = c->g.ntx * c->g.nty;
     PICSP_CUDA(cudaMemsetAsync(sp.hist, 0, sizeof(unsigned int) * nt, c->stream));
-    if (sp.n > 0)
-        PICSP_LAUNCH(c, k_tile_hist, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, (long long)sp.n, push_const(c, s), sp.hist);
+    if (sp.n > 0) {
+        // bins in shared memory up to 16384 of them (64 KB: 2048^2 cells), else global atomics;
+        // few, fat CTAs so that the flush (one atomic per non-zero bin and CTA) stays small beside the counting
+        const int nsmem = nt <= 16384 ? nt : 0;
+        if (nsmem > 12288 && !c->hist_smem_opted_in) {
+            PICSP_CUDA(cudaFuncSetAttribute(k_tile_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+            c->hist_smem_opted_in = true;
+        }
+        const int blocks = nsmem ? (int)std::min<long long>(c->num_sms * 2, (sp.n + 16383) / 16384) : particle_blocks(c, sp.n, 256);
+        PICSP_LAUNCH(c, k_tile_hist, std::max(blocks, 1), nsmem ? 1024 : 256, sizeof(unsigned int) * nsmem, sp.x, sp.y,
+                     (long long)sp.n, push_const(c, s), sp.hist, nsmem);
+    }
     sp.hist_valid = true;
 }
 bool tiled(const picsp_ctx *c) { return !(c->prm.flags & PICSP_FLAG_NO_SORT); }
@@ -523,6 +533,10 @@ void picsp_destroy(picsp_ctx *c) {
     cudaFree(c->d_red); cudaFree(c->d_scalars); cudaFree(c->d_sor_status); cudaFree(c->d_sor_progress); cudaFree(c->d_error); cudaFree(c->stage);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto &t : c->timers) for (auto e : t.pool) cudaEventDestroy(e);
+    if (c->copy_stream) {
+        cudaStreamDestroy(c->copy_stream);
+        for (int k = 0; k < 4; k++) cudaEventDestroy(c->ev_ready[k]);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -536,6 +550,12 @@ int picsp_sync(picsp_ctx *c) {
 }
 
 // ---- state exchange -------------------------------------------------------------------
+static void ensure_copy_stream(picsp_ctx *c) {
+    if (c->copy_stream) return;
+    PICSP_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 4; k++) PICSP_CUDA(cudaEventCreateWithFlags(&c->ev_ready[k], cudaEventDisableTiming));
+}
+
 int picsp_species_upload(picsp_ctx *c, int s, const double *x, const double *y, const double *vx, const double *vy, int64_t n) {
     PICSP_API_BEGIN
     check_ctx(c); check_species(s);
@@ -544,14 +564,25 @@ int picsp_species_upload(picsp_ctx *c, int s, const double *x, const double *y, 
     PICSP_REQUIRE(n >= 0 && n <= sp.cap, PICSP_ERR_INVALID, "particle count exceeds the capacity given to picsp_create");
     PICSP_REQUIRE(n == 0 || (x && y && vx && vy), PICSP_ERR_INVALID, "null particle array");
     const size_t bytes = sizeof(double) * (size_t)n;
-    PICSP_CUDA(cudaMemcpyAsync(sp.x, x, bytes, cudaMemcpyHostToDevice, c->stream));
-    PICSP_CUDA(cudaMemcpyAsync(sp.y, y, bytes, cudaMemcpyHostToDevice, c->stream));
-    PICSP_CUDA(cudaMemcpyAsync(sp.vx, vx, bytes, cudaMemcpyHostToDevice, c->stream));
-    PICSP_CUDA(cudaMemcpyAsync(sp.vy, vy, bytes, cudaMemcpyHostToDevice, c->stream));
+    // The copies run on the copy stream; the library stream is only waited for when work that may touch THIS species
+    // is still queued on it.  The first binning of the new load is enqueued before returning and not waited for, so
+    // it runs while the caller uploads the other species (a 5e8-particle binning is ~70 ms, an upload ~290 ms).
+    if (c->busy[s]) {
+        PICSP_CUDA(cudaStreamSynchronize(c->stream));
+        c->busy[0] = c->busy[1] = false;
+    }
+    ensure_copy_stream(c);
+    PICSP_CUDA(cudaMemcpyAsync(sp.x, x, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    PICSP_CUDA(cudaMemcpyAsync(sp.y, y, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    PICSP_CUDA(cudaMemcpyAsync(sp.vx, vx, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    PICSP_CUDA(cudaMemcpyAsync(sp.vy, vy, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    PICSP_CUDA(cudaStreamSynchronize(c->copy_stream));        // the caller's buffers are free again
+    const bool other_busy = c->busy[1 - s];
     if (sp.acc_valid) PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
-    PICSP_CUDA(cudaStreamSynchronize(c->stream));
     sp.n = n; sp.hist_valid = false; sp.acc_valid = false;
     sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0;
+    if (tiled(c) && n > 0) op_sort(c, s);
+    c->busy[s] = true; c->busy[1 - s] = other_busy;           // what was enqueued here touches species s only
     PICSP_API_END
 }
 
@@ -570,15 +601,24 @@ int picsp_species_download(picsp_ctx *c, int s, double *x, double *y, double *vx
     const size_t bytes = sizeof(double) * (size_t)sp.n;
     double *src[4] = {sp.x, sp.y, sp.vx, sp.vy};
     double *dst[4] = {x, y, vx, vy};
-    for (int k = 0; k < 4; k++) {
-        if (!dst[k] || sp.n == 0) continue;
-        if (sp.has_perm) {
-            ensure_stage(c, sp.n);
-            PICSP_LAUNCH(c, k_unpermute, particle_blocks(c, sp.n, 256), 256, 0, src[k], sp.id, c->stage, (long long)sp.n);
-            PICSP_CUDA(cudaMemcpyAsync(dst[k], c->stage, bytes, cudaMemcpyDeviceToHost, c->stream));
-        } else {
-            PICSP_CUDA(cudaMemcpyAsync(dst[k], src[k], bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (sp.has_perm && sp.n > 0) {
+        // Binned store: bring every array back to upload order on the device (out[id[slot]] = in[slot]) and copy it
+        // out.  The idle half of the sort's ping-pong buffers is the staging area (its contents are dead between
+        // sorts), one buffer per array, so the four un-permutes run back to back on the library stream while the
+        // device->host copies follow them on a second stream: only the first un-permute is exposed.
+        ensure_copy_stream(c);
+        double *stage[4] = {sp.x2, sp.y2, sp.vx2, sp.vy2};
+        for (int k = 0; k < 4; k++) {
+            if (!dst[k]) continue;
+            PICSP_LAUNCH(c, k_unpermute, particle_blocks(c, sp.n, 256), 256, 0, src[k], sp.id, stage[k], (long long)sp.n);
+            PICSP_CUDA(cudaEventRecord(c->ev_ready[k], c->stream));
+            PICSP_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_ready[k], 0));
+            PICSP_CUDA(cudaMemcpyAsync(dst[k], stage[k], bytes, cudaMemcpyDeviceToHost, c->copy_stream));
         }
+        PICSP_CUDA(cudaStreamSynchronize(c->copy_stream));
+    } else if (sp.n > 0) {
+        for (int k = 0; k < 4; k++)
+            if (dst[k]) PICSP_CUDA(cudaMemcpyAsync(dst[k], src[k], bytes, cudaMemcpyDeviceToHost, c->stream));
     }
     check_device_error(c);
     PICSP_API_END
@@ -725,9 +765,9 @@ int picsp_compute_ke(picsp_ctx *c, int s, double *ke) {
     Species &sp = c->sp[s];
     if (sp.has_perm && sp.n > 0) {
         // sorted store: reduce in upload order so the sum is reproducible regardless of the storage order
-        ensure_stage(c, sp.n);
-        PICSP_LAUNCH(c, k_ke_terms, particle_blocks(c, sp.n, 256), 256, 0, sp.vx, sp.vy, sp.id, (long long)sp.n, c->stage);
-        PICSP_LAUNCH(c, k_sum_partial, RED_BLOCKS, RED_THREADS, 0, c->stage, (long long)sp.n, c->d_red);
+        // (staging = the idle half of the sort's ping-pong buffers, dead between sorts)
+        PICSP_LAUNCH(c, k_ke_terms, particle_blocks(c, sp.n, 256), 256, 0, sp.vx, sp.vy, sp.id, (long long)sp.n, sp.x2);
+        PICSP_LAUNCH(c, k_sum_partial, RED_BLOCKS, RED_THREADS, 0, sp.x2, (long long)sp.n, c->d_red);
     } else {
         PICSP_LAUNCH(c, k_ke_partial, RED_BLOCKS, RED_THREADS, 0, sp.vx, sp.vy, (long long)sp.n, c->d_red);
     }

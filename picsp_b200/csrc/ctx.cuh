@@ -129,9 +129,17 @@ struct picsp_ctx {
     alignas(64) unsigned char tmapE[128];
     bool have_tmap = false;
     bool smem_opted_in = false;
+    bool hist_smem_opted_in = false;
 
-    // staging for un-permuted downloads
+    // staging for grid component uploads/downloads
     double *stage = nullptr; int64_t stage_cap = 0;
+    // particle downloads: device->host copies run on their own stream so that the un-permute of the next array
+    // overlaps the copy of the previous one
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_ready[4] = {nullptr, nullptr, nullptr, nullptr};
+    // busy[s]: kernels that may touch species s have been enqueued on `stream` since it was last synchronised
+    // (set conservatively by every launch; an upload of species s only has to wait when busy[s])
+    bool busy[2] = {false, false};
 
     // multi-GPU
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
@@ -187,6 +195,7 @@ inline int blocks_for(long long n, int threads, int max_blocks) {
     do {                                                                                    \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                    \
         (ctx)->launches++;                                                                  \
+        (ctx)->busy[0] = (ctx)->busy[1] = true;                                             \
         PICSP_CUDA(cudaGetLastError());                                                     \
     } while (0)
 

@@ -367,6 +367,32 @@ def test_full_size_cross_implementation_and_determinism():
     assert np.allclose(a["ke"], c["ke"], rtol=1e-12, atol=0)
 
 
+def test_config5_grid_cross_implementation():
+    """BASELINE config 5's grid (2048^2 cells: 16384 particle bins, the 64 KB shared-memory histogram, 2049^2-node
+    FFT) with a thin plasma: tiled/fused path vs the unsorted path after bootstrap + 3 steps, and exact charge
+    conservation of the deposit (sum of den * dx^2 / spwt == particle count, to round-off)."""
+    nm = normalise()
+    numx, n = 2048, 3_000_000
+    runs = []
+    for flags in (0, 2):
+        with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, flags=flags | 1)) as sim:   # CLEAR_DENSITY: den is one deposit
+            sim.fill_synthetic(ION, n, seed=5, vth=nm["vth_i"])
+            sim.fill_synthetic(ELECTRON, n, seed=6, vth=1.0, xdrift=nm["drift_e"])
+            sim.bootstrap(); sim.step(3)
+            runs.append({g: sim.grid(g) for g in GRIDS} | {"pe": np.stack(sim.get_species(ELECTRON))})
+    a, c = runs
+    for g in GRIDS:
+        assert_grid_close(a[g], c[g], numx + 1, numx + 1, 10 * RTOL, f"tiled vs unsorted {g}")
+    for k in range(4):
+        assert relerr(a["pe"][k], c["pe"][k]) <= 10 * RTOL
+    # den_e after the periodic fold: the unique periodic nodes carry every particle exactly once
+    with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n)) as sim:
+        want = n * sim.p.spwt[1] / nm["dx"] ** 2
+    for r in runs:
+        total = r["den_e"].reshape(numx + 1, numx + 1)[:-1, :-1].sum()
+        assert abs(total - want) <= 1e-12 * want
+
+
 def test_clear_density_extension_and_accumulate_default():
     nm = normalise()
     numx, n = 32, 5000
