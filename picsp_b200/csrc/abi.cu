@@ -122,8 +122,9 @@ void sort_prepare(picsp_ctx *c, int s) {
     ensure_hist(c, s);
     if (!sp.x2) {
         dalloc(&sp.x2, sp.cap + 2); dalloc(&sp.y2, sp.cap + 2); dalloc(&sp.vx2, sp.cap + 2); dalloc(&sp.vy2, sp.cap + 2);
-        dalloc(&sp.id, sp.cap); dalloc(&sp.id2, sp.cap);
+        dalloc(&sp.id, sp.cap + 8); dalloc(&sp.id2, sp.cap + 8);   // +8: bulk slices of ids are widened to multiples of 4
         dalloc((Chunk **)&sp.chunks2, (size_t)sp.max_chunks); dalloc(&sp.nchunks2, 1);
+        dalloc(&sp.chunk_cnt, (size_t)sp.max_chunks * 9); dalloc(&sp.chunk_base, (size_t)sp.max_chunks * 9);
     }
     sp.chunk2 = pick_chunk(c, sp.n);
     PICSP_LAUNCH(c, k_scan_tiles, 1, 1024, 0, sp.hist, nt, sp.tile_off, (Chunk *)sp.chunks2, sp.nchunks2, sp.cursor, sp.chunk2);
@@ -134,6 +135,7 @@ void sort_finish(picsp_ctx *c, int s) {
     std::swap(sp.x, sp.x2); std::swap(sp.y, sp.y2); std::swap(sp.vx, sp.vx2); std::swap(sp.vy, sp.vy2);
     std::swap(sp.id, sp.id2);
     sp.has_perm = true; sp.sorted = true; sp.steps_since_sort = 0;
+    sp.cnt_valid = false;          // new chunk table
 }
 
 void op_sort(picsp_ctx *c, int s) {
@@ -161,11 +163,14 @@ int mover_grid(const Species &sp) {
 template <int MODE> void launch_tile_mover(picsp_ctx *c, int s) {
     Species &sp = c->sp[s];
     RebinArgs rb = {};
-    if (MODE == 3) {
-        rb.id = sp.has_perm ? sp.id : (const uint32_t *)nullptr;
+    if (MODE == 3 || MODE == 4) {
+        PICSP_REQUIRE(sp.has_perm, PICSP_ERR_STATE, "internal: re-binning mover on a store without a slot map");
+        rb.id = sp.id;
         rb.tile_off = sp.tile_off; rb.cursor = sp.cursor;
         rb.x2 = sp.x2; rb.y2 = sp.y2; rb.vx2 = sp.vx2; rb.vy2 = sp.vy2; rb.id2 = sp.id2;
+        rb.chunk_base = sp.chunk_base;
     }
+    if (MODE == 0) rb.chunk_cnt = sp.chunk_cnt;      // nullptr until the first sort allocated it
     CUtensorMap tm;
     memcpy(&tm, c->tmapE, sizeof(tm));
     if (!c->smem_opted_in) {               // dynamic shared memory above 48 KB needs a per-function opt-in (per device)
@@ -173,6 +178,7 @@ template <int MODE> void launch_tile_mover(picsp_ctx *c, int s) {
         PICSP_CUDA(cudaFuncSetAttribute(k_tile_mover<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVER_SMEM_BYTES));
         PICSP_CUDA(cudaFuncSetAttribute(k_tile_mover<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVER_SMEM_BYTES));
         PICSP_CUDA(cudaFuncSetAttribute(k_tile_mover<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVER_SMEM_BYTES));
+        PICSP_CUDA(cudaFuncSetAttribute(k_tile_mover<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MOVER_SMEM_BYTES));
         c->smem_opted_in = true;
     }
     PICSP_LAUNCH(c, (k_tile_mover<MODE>), mover_grid(sp), MOVER_THREADS, MOVER_SMEM_BYTES, tm, sp.x, sp.y, sp.vx, sp.vy,
@@ -336,8 +342,14 @@ void op_push(picsp_ctx *c, int s) {
         PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
     if (sp.n > 0) {
         if (tile) {
-            if (rebin_in_mover) { launch_tile_mover<3>(c, s); sort_finish(c, s); }
-            else if (fuse) launch_tile_mover<0>(c, s);
+            if (rebin_in_mover && sp.cnt_valid) {
+                // the previous launch counted, per chunk, where its particles went: reserve the ranges up front
+                const long long q = 9ll * mover_grid(sp);
+                PICSP_LAUNCH(c, k_rebin_bases, (int)((q + 255) / 256), 256, 0, (const Chunk *)sp.chunks, sp.nchunks, c->g.ntx, c->g.nty,
+                             sp.chunk_cnt, sp.tile_off, sp.cursor, sp.chunk_base, c->d_error);
+                launch_tile_mover<4>(c, s); sort_finish(c, s);
+            } else if (rebin_in_mover) { launch_tile_mover<3>(c, s); sort_finish(c, s); }
+            else if (fuse) { launch_tile_mover<0>(c, s); sp.cnt_valid = sp.chunk_cnt != nullptr; }
             else launch_tile_mover<2>(c, s);
         } else {
             const int blocks = particle_blocks(c, sp.n, 256);
@@ -467,7 +479,7 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
             dalloc(&sp.den, g.nn); dalloc(&sp.acc, g.nn); dalloc(&sp.frac, 1); dalloc(&sp.frac_scratch, 2);
             dalloc(&sp.hist, (size_t)g.ntx * g.nty); dalloc(&sp.hist_next, (size_t)g.ntx * g.nty);
             dalloc(&sp.counters, 2);
-            sp.sort_period = (s == 0) ? 96 : 12;
+            sp.sort_period = (s == 0) ? 96 : 8;     // steps between re-binnings (ions barely move; electrons: profiles/r01_sweeps.md)
             sp.ntiles = g.ntx * g.nty;
             sp.max_chunks = sp.cap / 512 + (long long)g.ntx * g.nty + 1;   // 512 = smallest chunk pick_chunk() returns
             dalloc(&sp.tile_off, (size_t)g.ntx * g.nty + 1);
@@ -527,7 +539,7 @@ void picsp_destroy(picsp_ctx *c) {
         cudaFree(sp.den); cudaFree(sp.acc); cudaFree(sp.frac); cudaFree(sp.frac_scratch); cudaFree(sp.hist); cudaFree(sp.hist_next); cudaFree(sp.counters);
         cudaFree(sp.x2); cudaFree(sp.y2); cudaFree(sp.vx2); cudaFree(sp.vy2); cudaFree(sp.id2);
         cudaFree(sp.tile_off); cudaFree(sp.chunks); cudaFree(sp.nchunks); cudaFree(sp.cursor);
-        cudaFree(sp.chunks2); cudaFree(sp.nchunks2);
+        cudaFree(sp.chunks2); cudaFree(sp.nchunks2); cudaFree(sp.chunk_cnt); cudaFree(sp.chunk_base);
     }
     cudaFree(c->rho); cudaFree(c->phi); cudaFree(c->E_alloc); cudaFree(c->rhok); cudaFree(c->phik);
     cudaFree(c->d_red); cudaFree(c->d_scalars); cudaFree(c->d_sor_status); cudaFree(c->d_sor_progress); cudaFree(c->d_error); cudaFree(c->stage);
@@ -580,7 +592,7 @@ int picsp_species_upload(picsp_ctx *c, int s, const double *x, const double *y, 
     const bool other_busy = c->busy[1 - s];
     if (sp.acc_valid) PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
     sp.n = n; sp.hist_valid = false; sp.acc_valid = false;
-    sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0;
+    sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0; sp.cnt_valid = false;
     if (tiled(c) && n > 0) op_sort(c, s);
     c->busy[s] = true; c->busy[1 - s] = other_busy;           // what was enqueued here touches species s only
     PICSP_API_END
@@ -820,7 +832,7 @@ int picsp_straggler_count(picsp_ctx *c, int s, int64_t *n) {
 int picsp_set_sort_period(picsp_ctx *c, int s, int period) {
     PICSP_API_BEGIN
     check_ctx(c); check_species(s);
-    c->sp[s].sort_period = period > 0 ? period : (s == 0 ? 96 : 12);
+    c->sp[s].sort_period = period > 0 ? period : (s == 0 ? 96 : 8);
     PICSP_API_END
 }
 
@@ -860,7 +872,7 @@ int picsp_species_fill_synthetic(picsp_ctx *c, int s, int64_t n, int64_t first_i
                      (long long)first_index, seed, c->g.xl, c->g.yl, vth, xdrift);
     if (sp.acc_valid) PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
     sp.n = n; sp.hist_valid = false; sp.acc_valid = false;
-    sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0;
+    sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0; sp.cnt_valid = false;
     PICSP_CUDA(cudaStreamSynchronize(c->stream));
     PICSP_API_END
 }

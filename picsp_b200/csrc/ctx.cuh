@@ -93,6 +93,9 @@ struct Species {
     long long max_chunks = 0;
     int chunk = 4096;              // particles per CTA work item of the current binning (pick_chunk)
     int chunk2 = 4096;             // ... of the binning under construction
+    unsigned int *chunk_cnt = nullptr;   // [max_chunks][9] per-chunk neighbour-bin populations left by the last fused mover launch
+    unsigned int *chunk_base = nullptr;  // [max_chunks][9] ranges reserved from them for a re-binning launch
+    bool cnt_valid = false;        // chunk_cnt describes the stored positions under the current chunk table
     int ntiles = 0;
 };
 

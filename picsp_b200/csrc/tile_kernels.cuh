@@ -71,7 +71,9 @@ constexpr int MOVER_MIN_CTAS = PICSP_MOVER_MIN_CTAS;
 constexpr bool BULK_PIPE = PICSP_BULK_PIPE != 0;
 constexpr int STAGES = PICSP_STAGES;
 constexpr int STAGE_W = MOVER_THREADS + 2;          // doubles per array per stage (+2: a slice may start at an odd index)
-constexpr size_t MOVER_SMEM_BYTES = MOVER_WINDOW_BYTES + (BULK_PIPE ? sizeof(double) * (size_t)STAGES * 4 * STAGE_W : 0) + 64;
+constexpr int STAGE_IDW = MOVER_THREADS + 8;        // u32 ids per stage (+8: the slice is widened to a multiple of 4 ids at both ends)
+constexpr size_t MOVER_PIPE_BYTES = sizeof(double) * (size_t)STAGES * 4 * STAGE_W;
+constexpr size_t MOVER_SMEM_BYTES = MOVER_WINDOW_BYTES + (BULK_PIPE ? MOVER_PIPE_BYTES + sizeof(uint32_t) * (size_t)STAGES * STAGE_IDW : 0) + 64;
 
 struct __align__(16) Chunk {
     long long start;   // first particle (index into the species arrays)
@@ -296,9 +298,12 @@ __device__ __forceinline__ double2 interp_E(double2 f00, double2 f01, double2 f1
 // E at the position of a particle whose cell is outside its bin's window (it drifted since the last sort, or it
 // wrapped through the periodic boundary and is pushed again): same nodes from global memory, same arithmetic as the
 // window path.  i/j: the particle's cell, or -1 for a position outside the box (caller-supplied garbage; the mover
-// keeps particles inside), which takes the reference's flat-index gather with the zero guard band.  Rare: not inlined.
+// keeps particles inside), which takes the reference's flat-index gather with the zero guard band.
 struct Straggler { double ex, ey; int i, j; };     // returned by value: reference outputs would cost a stack frame
-__device__ __noinline__ Straggler gather_straggler(const double2 *__restrict__ E, double px, double py, double dx, double inv_dx,
+#ifndef PICSP_STRAGGLER_ATTR
+#define PICSP_STRAGGLER_ATTR __forceinline__   // a real call costs the hot loop 6 registers and 2.5 % (profiles/r01_sweeps.md)
+#endif
+__device__ PICSP_STRAGGLER_ATTR Straggler gather_straggler(const double2 *__restrict__ E, double px, double py, double dx, double inv_dx,
                                                    double xl, double yl, int nix, int niy, long long nn, long long guard) {
     // scalars, not the PushConst: taking the address of the kernel parameter would give every thread a stack copy
     PushConst c;
@@ -435,19 +440,46 @@ __device__ __forceinline__ bool deposit_one(double px, double py, const PushCons
 // ---------------------------------------------------------------------------
 // the fused chunk kernel.  MODE 0: push + deposit(next step); 1: deposit only
 // (standalone scatterSpecies); 2: push only (PICSP_FLAG_NO_FUSE);
-// MODE 3: MODE 0 that also RE-BINS: instead of writing the pushed particle back in place it writes it into
+// MODE 3 / 4: MODE 0 that also RE-BINS: instead of writing the pushed particle back in place it writes it into
 // the new binned layout (destination = bin of the position the push STARTED from, whose histogram is known
 // before the launch), so a periodic re-sort costs no extra pass over the particles.  The store is then
 // "binned as of one step ago", which the window halo absorbs like any other drift.
+//   MODE 4 (the normal case): the previous launch left, per chunk, how many of its particles ended in each of the
+//   9 neighbouring bins (chunk_cnt) — exactly the destination populations of this launch — and k_rebin_bases has
+//   turned them into one reserved range per (chunk, bin).  Slots are handed out from shared-memory counters: no
+//   global atomic, no extra barrier in the loop.
+//   MODE 3 (no counts available, e.g. re-sort on consecutive steps): one reservation per slice and bin; every
+//   slice then waits for a global atomic round trip (measured: the launch takes twice as long as MODE 0).
 // counters[0] = extra pushes, counters[1] = particles that deposited outside their window
 // ---------------------------------------------------------------------------
 struct RebinArgs {
-    const uint32_t *id;            // current slot -> upload index (nullptr: identity)
+    const uint32_t *id;            // current slot -> upload index (a binned store always has one)
     const long long *tile_off;     // offsets of the NEW layout
-    unsigned int *cursor;          // per-bin fill cursors of the NEW layout (zeroed)
+    unsigned int *cursor;          // per-bin fill cursors of the NEW layout
     double *x2, *y2, *vx2, *vy2;   // destination arrays
     uint32_t *id2;
+    const unsigned int *chunk_base;// MODE 4: [chunk][9] first slot (relative to the bin) reserved for this chunk
+    unsigned int *chunk_cnt;       // MODE 0: [chunk][9] particles of this chunk that ended in each neighbouring bin (or nullptr)
 };
+
+// one thread per (chunk, neighbour class): reserve the chunk's range in the destination bin
+__global__ void k_rebin_bases(const Chunk *__restrict__ chunks, const int *__restrict__ nchunks, int ntx, int nty,
+                              const unsigned int *__restrict__ chunk_cnt, const long long *__restrict__ tile_off,
+                              unsigned int *__restrict__ cursor, unsigned int *__restrict__ chunk_base, int *__restrict__ err) {
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= 9ll * *nchunks) return;
+    const int ch = (int)(q / 9), cls = (int)(q - 9ll * ch);
+    const unsigned cnt = chunk_cnt[q];
+    if (!cnt) return;
+    const int t = chunks[ch].tile;
+    const int tx = t / nty, ty = t - tx * nty;
+    const int ux = (tx + cls / 3 - 1 + ntx) % ntx, uy = (ty + cls % 3 - 1 + nty) % nty;
+    const int ut = ux * nty + uy;
+    const unsigned base = atomicAdd(&cursor[ut], cnt);
+    // bin sizes and chunk counts come from the same launch and the same bin function: this never fires
+    if ((long long)base + cnt > tile_off[ut + 1] - tile_off[ut]) atomicOr(err, ERR_BIT_REBIN);
+    chunk_base[q] = base;
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(MOVER_THREADS, MOVER_MIN_CTAS)
@@ -456,13 +488,15 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
              const int *__restrict__ nchunks, PushConst c, const double2 *__restrict__ E,
              long long *__restrict__ acc, const int *__restrict__ frac, unsigned int *__restrict__ hist_next,
              unsigned long long *__restrict__ counters, int *__restrict__ err, RebinArgs rb) {
-    static_assert(MODE != 3 || BULK_PIPE, "the re-binning mover is built on the bulk-copy pipeline");
+    constexpr bool REBIN = (MODE == 3 || MODE == 4);
+    static_assert(!REBIN || BULK_PIPE, "the re-binning mover is built on the bulk-copy pipeline");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *sE = reinterpret_cast<double2 *>(smem_raw);                               // REPL copies of E_COPY nodes
     unsigned *sLo = reinterpret_cast<unsigned *>(smem_raw + sizeof(double2) * (size_t)REPL * E_COPY);
     unsigned *sHi = sLo + (size_t)REPL * ACC_COPY;
     __shared__ unsigned sCnt[9];
-    __shared__ unsigned sRbCnt[9], sRbBase[9];     // MODE 3: per-slice population / reserved base of each neighbour bin
+    __shared__ unsigned sRbCnt[9], sRbBase[9];     // MODE 3: per-slice population / reserved base of each neighbour bin; MODE 4: running count / chunk base
+    __shared__ long long sDstOff[9];               // re-binning: first destination slot per neighbour class
     __shared__ __align__(8) unsigned long long sBar;
     __shared__ __align__(8) unsigned long long sFull[STAGES];
 
@@ -494,6 +528,12 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
     if (MODE != 2)
         for (int k = tid; k < REPL * ACC_COPY; k += MOVER_THREADS) { sLo[k] = 0u; sHi[k] = 0u; }
     if (tid < 9) { sCnt[tid] = 0u; sRbCnt[tid] = 0u; }
+    if (REBIN && tid < 9) {        // first slot of each neighbouring bin in the new layout (MODE 4: of this chunk's range in it)
+        const int ux = (tc.tx + tid / 3 - 1 + c.ntx) % c.ntx, uy = (tc.ty + tid % 3 - 1 + c.nty) % c.nty;
+        long long off = rb.tile_off[ux * c.nty + uy];
+        if (MODE == 4) off += rb.chunk_base[9ll * blockIdx.x + tid];
+        sDstOff[tid] = off;
+    }
 
     // chunk-local pointers: 32-bit indexing inside the loop
     double *__restrict__ cx = x + ck.start;
@@ -511,7 +551,7 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
         oi = oj = -1;
         if (MODE != 1) {
             extra += push_one(px, py, pvx, pvy, c, inv_dx, tc, sE, E, err, oi, oj);
-            if (MODE != 3) { cx[k] = px; cy[k] = py; cvx[k] = pvx; cvy[k] = pvy; }
+            if (!REBIN) { cx[k] = px; cy[k] = py; cvx[k] = pvx; cvy[k] = pvy; }
         }
         int ci = -1, cj = -1;
         if (MODE != 2) {
@@ -550,6 +590,7 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
 
     if (BULK_PIPE) {
         double *sP = reinterpret_cast<double *>(smem_raw + MOVER_WINDOW_BYTES);      // [STAGES][4][STAGE_W]
+        uint32_t *sI = reinterpret_cast<uint32_t *>(smem_raw + MOVER_WINDOW_BYTES + MOVER_PIPE_BYTES);   // [STAGES][STAGE_IDW]
         constexpr int NARR = (MODE == 1) ? 2 : 4;
         const int niter = (count + MOVER_THREADS - 1) / MOVER_THREADS;
         // slice `it` -> stage it % STAGES.  Bulk copies need 16-byte alignment: the slice is widened to even
@@ -561,7 +602,11 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
             const long long a0 = first & ~1ll, a1 = (first + cnt + 1) & ~1ll;
             const uint32_t bytes = (uint32_t)((a1 - a0) * sizeof(double));
             double *dst = sP + (size_t)st * 4 * STAGE_W;
-            mbar_expect_tx(&sFull[st], NARR * bytes);
+            // a re-binning launch also moves the slot -> upload-index map: it rides in the same pipeline stage
+            const long long i0 = first & ~3ll, i1 = (first + cnt + 3) & ~3ll;
+            const uint32_t ibytes = REBIN ? (uint32_t)((i1 - i0) * sizeof(uint32_t)) : 0u;
+            mbar_expect_tx(&sFull[st], NARR * bytes + ibytes);
+            if (REBIN) bulk_load(sI + (size_t)st * STAGE_IDW, rb.id + i0, ibytes, &sFull[st]);
             bulk_load(dst, x + a0, bytes, &sFull[st]);
             bulk_load(dst + STAGE_W, y + a0, bytes, &sFull[st]);
             if (MODE != 1) {
@@ -588,17 +633,22 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
                 if (MODE != 1) { pvx = src[2 * STAGE_W]; pvy = src[3 * STAGE_W]; }
                 process(k, px, py, pvx, pvy, oi, oj);
             }
-            if (MODE == 3) {
+            if (REBIN) {
                 // destination bin = bin of the position the push started from (same bin function as the histogram)
-                int cls = 15, tpre = 0;
+                // (no runtime integer division in the per-particle code: TILE is a power of two)
+                int cls = 15, tpx = 0, tpy = 0;
                 if (live) {
-                    tpre = oi >= 0 ? tile_of_cell(oi, oj, c) : 0;
-                    int ddx = tpre / c.nty - tc.tx, ddy = tpre % c.nty - tc.ty;
-                    if (ddx > 1) ddx -= c.ntx; else if (ddx < -1) ddx += c.ntx;
-                    if (ddy > 1) ddy -= c.nty; else if (ddy < -1) ddy += c.nty;
-                    cls = (nbr_ok && ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1) ? (ddx + 1) * 3 + (ddy + 1) : 9;
+                    if (oi >= 0) { tpx = min((int)((unsigned)oi / TILE), tc.ntx1); tpy = min((int)((unsigned)oj / TILE), tc.nty1); }
+                    int ddx = tpx - tc.tx, ddy = tpy - tc.ty;
+                    // mirrors the counting of the positions written by the previous launch (below): own bin, neighbour, far
+                    if ((ddx | ddy) == 0) cls = 4;
+                    else {
+                        if (ddx > 1) ddx -= c.ntx; else if (ddx < -1) ddx += c.ntx;
+                        if (ddy > 1) ddy -= c.nty; else if (ddy < -1) ddy += c.nty;
+                        cls = (nbr_ok && ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1) ? (ddx + 1) * 3 + (ddy + 1) : 9;
+                    }
                 }
-                // rank inside (slice, destination bin): warp-aggregated shared-memory counter
+                // rank inside (chunk or slice, destination bin): warp-aggregated shared-memory counter
                 const unsigned lane = tid & 31u;
                 const unsigned peers = __match_any_sync(0xffffffffu, cls);
                 const int leader = __ffs(peers) - 1;
@@ -606,28 +656,30 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
                 if (cls < 9 && (int)lane == leader) first = atomicAdd(&sRbCnt[cls], (unsigned)__popc(peers));
                 first = __shfl_sync(0xffffffffu, first, leader);
                 const unsigned rank = first + (unsigned)__popc(peers & ((1u << lane) - 1u));
-                __syncthreads();
-                if (tid < 9 && sRbCnt[tid]) {          // one contiguous reservation per destination bin and slice
-                    const int ux = (tc.tx + tid / 3 - 1 + c.ntx) % c.ntx, uy = (tc.ty + tid % 3 - 1 + c.nty) % c.nty;
-                    const int ut = ux * c.nty + uy;
-                    const unsigned base = atomicAdd(&rb.cursor[ut], sRbCnt[tid]);
-                    // the bin sizes come from the histogram taken by the previous launch: same bin function, so this never fires
-                    if ((long long)base + sRbCnt[tid] > rb.tile_off[ut + 1] - rb.tile_off[ut]) atomicOr(err, ERR_BIT_REBIN);
-                    sRbBase[tid] = base;
-                    sRbCnt[tid] = 0u;
+                if (MODE == 3) {
+                    __syncthreads();
+                    if (tid < 9 && sRbCnt[tid]) {      // one contiguous reservation per destination bin and slice
+                        const int ux = (tc.tx + tid / 3 - 1 + c.ntx) % c.ntx, uy = (tc.ty + tid % 3 - 1 + c.nty) % c.nty;
+                        const int ut = ux * c.nty + uy;
+                        const unsigned base = atomicAdd(&rb.cursor[ut], sRbCnt[tid]);
+                        // the bin sizes come from the histogram taken by the previous launch: same bin function, so this never fires
+                        if ((long long)base + sRbCnt[tid] > rb.tile_off[ut + 1] - rb.tile_off[ut]) atomicOr(err, ERR_BIT_REBIN);
+                        sRbBase[tid] = base;
+                        sRbCnt[tid] = 0u;
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
                 if (live) {
                     long long dst;
                     if (cls < 9) {
-                        const int ux = (tc.tx + cls / 3 - 1 + c.ntx) % c.ntx, uy = (tc.ty + cls % 3 - 1 + c.nty) % c.nty;
-                        dst = rb.tile_off[ux * c.nty + uy] + sRbBase[cls] + rank;
+                        dst = sDstOff[cls] + rank;
+                        if (MODE == 3) dst += sRbBase[cls];
                     } else {                           // far bin (straggler of stragglers): individual slot
+                        const int tpre = tpx * c.nty + tpy;
                         dst = rb.tile_off[tpre] + atomicAdd(&rb.cursor[tpre], 1u);
                     }
-                    const long long p = ck.start + k;
                     rb.x2[dst] = px; rb.y2[dst] = py; rb.vx2[dst] = pvx; rb.vy2[dst] = pvy;
-                    rb.id2[dst] = rb.id ? rb.id[p] : (uint32_t)p;
+                    rb.id2[dst] = sI[(size_t)st * STAGE_IDW + (int)((ck.start + (long long)it * MOVER_THREADS) & 3ll) + tid];
                 }
             }
             __syncthreads();
@@ -682,6 +734,8 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
             }
         }
     }
+    // where this chunk's particles are now, by neighbouring bin: the reservation sizes of a re-binning launch next step
+    if (MODE == 0 && rb.chunk_cnt && tid < 9) rb.chunk_cnt[9ll * blockIdx.x + tid] = sCnt[tid];
     if (MODE != 1 && tid < 9 && sCnt[tid]) {
         if (tid == 4) {
             atomicAdd(&hist_next[ck.tile], sCnt[4]);

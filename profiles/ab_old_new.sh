@@ -1,0 +1,20 @@
+#!/bin/bash
+# A/B on ONE box: the library of commit a5d85a4 (stand-alone re-sort every 12 steps) against the current build,
+# with and without the re-binning mover.  usage: bash profiles/ab_old_new.sh <old.so>
+run() {  # $1 = label, $2 = lib ('' = current), $3 = flags
+  python - "$2" "$3" <<'PY' > gpurun_out/ab_tmp.json 2> gpurun_out/ab_tmp.err
+import sys, runpy
+import picsp_b200.lib as l
+if sys.argv[1]: l.LIB_PATH = sys.argv[1]
+flags = sys.argv[2]
+sys.argv = ["bench.py", "--no-e2e", "--no-cpu-baseline", "--steps", "24", "--warmup", "3", "--flags", flags]
+runpy.run_path("bench.py", run_name="__main__")
+PY
+  python -c "
+import json;d=json.load(open('gpurun_out/ab_tmp.json'));print('$1', '%.4g'%d['value'], round(d['ms_per_step'],3), 'push', round(d['phases_ms_per_step']['push'],3), 'sort', round(d['phases_ms_per_step']['sort'],3), d['clocks']['sm_mhz'])"
+}
+for rep in 1 2; do
+  run old-separate-sort "$1" 0
+  run new-separate-sort "" 16
+  run new-rebin-mover "" 0
+done

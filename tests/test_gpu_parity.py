@@ -160,10 +160,12 @@ def test_sort_period_does_not_change_results(period):
                 assert relerr(got[k], want[k]) <= 100 * RTOL
 
 
-@pytest.mark.parametrize("numx,numy,period", [(64, 64, 1), (32, 48, 1), (100, 72, 2), (16, 16, 1)])
+@pytest.mark.parametrize("numx,numy,period", [(64, 64, 1), (32, 48, 1), (100, 72, 2), (16, 16, 1), (64, 64, 3), (32, 48, 2), (48, 32, 3),
+                                              (16, 16, 2)])
 def test_rebinning_mover_equals_separate_sort(numx, numy, period):
-    """A due re-sort rides on the mover itself (k_tile_mover<3>: the pushed particle is written straight into the
-    new binned layout).  Storage order is the only thing that may differ from the stand-alone re-sort
+    """A due re-sort rides on the mover itself (the pushed particle is written straight into the new binned layout):
+    k_tile_mover<4> with ranges reserved from the previous launch's per-chunk counts (period >= 2), k_tile_mover<3>
+    with per-slice reservations when there are none (period 1: re-sort on consecutive steps).  Storage order is the only thing that may differ from the stand-alone re-sort
     (PICSP_FLAG_SEPARATE_SORT): grids and the phase space in upload order must be bit-identical, and both must
     match the oracle.  Grids with fewer than 3 tiles per side take the individual-slot path."""
     nm = normalise()
