@@ -273,7 +273,9 @@ def main_ours(args, rank, world, local_rank):
         traffic = ncu_traffic_bytes_per_particle() * n_local     # per launch, like `achieved`
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
-                "kernel": "k_tile_mover<0> (leapfrog mover + CIC gather from a TMA-staged E tile + next-step CIC deposit)",
+                "kernel": "k_tile_mover<0> (leapfrog mover + CIC gather from a TMA-staged E tile + next-step CIC deposit); "
+                          "the average includes the re-binning launches k_tile_mover<4> (every 8th electron launch, "
+                          "73 B of DRAM traffic per particle instead of 64), charged at the same 64 algorithmic bytes",
                 "traffic_source": "profiles/ncu_traffic.json: ncu --set full dram bytes per particle x particles per launch",
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE_STEP * n_local,
                 "avg_launch_ms": per_launch_s * 1e3, "launches_timed": push_calls, "peak_source": peak_src,

@@ -95,10 +95,13 @@ const char *picsp_last_error(void);
 int  picsp_sync(picsp_ctx *ctx);
 
 /* ---- state exchange (host buffers; these are what parity tests use) --------- */
-/* Replaces filling Species::part_list (src/main.cpp:140,594,613): n particles in list order. */
+/* Replaces filling Species::part_list (src/main.cpp:140,594,613): n particles in list order.  The host buffers are
+ * free again when the call returns; the first binning of the new load is left running on the device, so that it
+ * overlaps the upload of the other species (every later call is ordered after it). */
 int picsp_species_upload(picsp_ctx *ctx, int species, const double *x, const double *y,
                          const double *vx, const double *vy, int64_t n);
-/* Particles come back in upload (list) order regardless of any internal sort. */
+/* Particles come back in upload (list) order regardless of any internal re-binning (any of the four outputs may
+ * be NULL).  Host-synchronous. */
 int picsp_species_download(picsp_ctx *ctx, int species, double *x, double *y, double *vx, double *vy);
 int picsp_species_count(picsp_ctx *ctx, int species, int64_t *n);
 /* Same, [n][4] rows of {x, y, vx, vy}: the layout writeSpecies dumps (src/main.cpp:1152-1162). */
