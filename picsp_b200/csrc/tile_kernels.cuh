@@ -470,7 +470,7 @@ __global__ void k_rebin_bases(const Chunk *__restrict__ chunks, const int *__res
     if (q >= 9ll * *nchunks) return;
     const int ch = (int)(q / 9), cls = (int)(q - 9ll * ch);
     const unsigned cnt = chunk_cnt[q];
-    if (!cnt) return;
+    if (!cnt) { chunk_base[q] = 0u; return; }
     const int t = chunks[ch].tile;
     const int tx = t / nty, ty = t - tx * nty;
     const int ux = (tx + cls / 3 - 1 + ntx) % ntx, uy = (ty + cls % 3 - 1 + nty) % nty;
