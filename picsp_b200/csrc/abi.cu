@@ -136,6 +136,7 @@ void sort_finish(picsp_ctx *c, int s) {
     std::swap(sp.id, sp.id2);
     sp.has_perm = true; sp.sorted = true; sp.steps_since_sort = 0;
     sp.cnt_valid = false;          // new chunk table
+    sp.staged_v_valid = false;     // the staging buffers are now the live ones
 }
 
 void op_sort(picsp_ctx *c, int s) {
@@ -324,6 +325,7 @@ void op_compute_ef(picsp_ctx *c) {
 
 void op_push(picsp_ctx *c, int s) {
     Species &sp = c->sp[s];
+    sp.staged_v_valid = false;
     const bool fuse = !(c->prm.flags & PICSP_FLAG_NO_FUSE);
     const bool tile = tiled(c);
     const bool due = tile && sp.sorted && sp.steps_since_sort >= sp.sort_period;
@@ -374,6 +376,7 @@ void op_push(picsp_ctx *c, int s) {
 void op_rewind(picsp_ctx *c, int s) {
     PhaseScope ph(c, PICSP_PHASE_PUSH);
     Species &sp = c->sp[s];
+    sp.staged_v_valid = false;
     if (sp.n > 0)
         PICSP_LAUNCH(c, k_rewind, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n,
                      push_const(c, s), c->E);
@@ -592,7 +595,7 @@ int picsp_species_upload(picsp_ctx *c, int s, const double *x, const double *y, 
     const bool other_busy = c->busy[1 - s];
     if (sp.acc_valid) PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
     sp.n = n; sp.hist_valid = false; sp.acc_valid = false;
-    sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0; sp.cnt_valid = false;
+    sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0; sp.cnt_valid = false; sp.staged_v_valid = false;
     if (tiled(c) && n > 0) op_sort(c, s);
     c->busy[s] = true; c->busy[1 - s] = other_busy;           // what was enqueued here touches species s only
     PICSP_API_END
@@ -628,6 +631,7 @@ int picsp_species_download(picsp_ctx *c, int s, double *x, double *y, double *vx
             PICSP_CUDA(cudaMemcpyAsync(dst[k], stage[k], bytes, cudaMemcpyDeviceToHost, c->copy_stream));
         }
         PICSP_CUDA(cudaStreamSynchronize(c->copy_stream));
+        sp.staged_v_valid = dst[2] && dst[3];     // a KE request right after the dump can reduce these directly
     } else if (sp.n > 0) {
         for (int k = 0; k < 4; k++)
             if (dst[k]) PICSP_CUDA(cudaMemcpyAsync(dst[k], src[k], bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -775,7 +779,10 @@ int picsp_compute_ke(picsp_ctx *c, int s, double *ke) {
     PICSP_REQUIRE(ke != nullptr, PICSP_ERR_INVALID, "null output");
     PICSP_CUDA(cudaSetDevice(c->prm.device));
     Species &sp = c->sp[s];
-    if (sp.has_perm && sp.n > 0) {
+    if (sp.has_perm && sp.n > 0 && sp.staged_v_valid) {
+        // the download that preceded this call left the velocities in upload order in the staging buffers
+        PICSP_LAUNCH(c, k_ke_partial, RED_BLOCKS, RED_THREADS, 0, sp.vx2, sp.vy2, (long long)sp.n, c->d_red);
+    } else if (sp.has_perm && sp.n > 0) {
         // sorted store: reduce in upload order so the sum is reproducible regardless of the storage order
         // (staging = the idle half of the sort's ping-pong buffers, dead between sorts)
         PICSP_LAUNCH(c, k_ke_terms, particle_blocks(c, sp.n, 256), 256, 0, sp.vx, sp.vy, sp.id, (long long)sp.n, sp.x2);
@@ -872,7 +879,7 @@ int picsp_species_fill_synthetic(picsp_ctx *c, int s, int64_t n, int64_t first_i
                      (long long)first_index, seed, c->g.xl, c->g.yl, vth, xdrift);
     if (sp.acc_valid) PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
     sp.n = n; sp.hist_valid = false; sp.acc_valid = false;
-    sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0; sp.cnt_valid = false;
+    sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0; sp.cnt_valid = false; sp.staged_v_valid = false;
     PICSP_CUDA(cudaStreamSynchronize(c->stream));
     PICSP_API_END
 }

@@ -96,6 +96,7 @@ struct Species {
     unsigned int *chunk_cnt = nullptr;   // [max_chunks][9] per-chunk neighbour-bin populations left by the last fused mover launch
     unsigned int *chunk_base = nullptr;  // [max_chunks][9] ranges reserved from them for a re-binning launch
     bool cnt_valid = false;        // chunk_cnt describes the stored positions under the current chunk table
+    bool staged_v_valid = false;   // vx2/vy2 hold the current velocities in upload order (left there by a download)
     int ntiles = 0;
 };
 

@@ -395,6 +395,29 @@ def test_config5_grid_cross_implementation():
         assert abs(total - want) <= 1e-12 * want
 
 
+def test_ke_after_a_dump_uses_the_staged_velocities_and_is_bit_identical():
+    """computeKE right after a download reduces the upload-order velocities the download left in the staging
+    buffers instead of re-ordering the terms again: same reduction tree, so the value is bit-identical to the
+    stand-alone path, before and after, and any push invalidates the shortcut."""
+    nm = normalise()
+    numx, n = 96, 300_000
+    with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n)) as sim:
+        sim.fill_synthetic(ION, n, seed=3, vth=nm["vth_i"])
+        sim.fill_synthetic(ELECTRON, n, seed=4, vth=1.0, xdrift=nm["drift_e"])
+        sim.bootstrap(); sim.step(3)
+        for s in (ION, ELECTRON):
+            before = sim.computeKE(s)
+            _, _, vx, vy = sim.get_species(s)
+            after = sim.computeKE(s)
+            assert before == after
+            mass = sim.p.massI if s == ION else 1.0          # KE = sum(v^2) + 0.5*spwt*m (main.cpp:1190-1203, Q10)
+            assert abs(after - 0.5 * sim.p.spwt[s] * mass - np.sum(vx * vx + vy * vy)) <= 1e-10 * after
+        sim.step(1)
+        ke1 = sim.computeKE(ELECTRON)
+        _, _, vx, vy = sim.get_species(ELECTRON)
+        assert ke1 == sim.computeKE(ELECTRON) and ke1 != after
+
+
 def test_clear_density_extension_and_accumulate_default():
     nm = normalise()
     numx, n = 32, 5000
