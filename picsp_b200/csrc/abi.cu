@@ -129,11 +129,13 @@ void sort_prepare(picsp_ctx *c, int s) {
     sp.chunk2 = pick_chunk(c, sp.n);
     PICSP_LAUNCH(c, k_scan_tiles, 1, 1024, 0, sp.hist, nt, sp.tile_off, (Chunk *)sp.chunks2, sp.nchunks2, sp.cursor, sp.chunk2);
 }
-void sort_finish(picsp_ctx *c, int s) {
+void sort_finish(picsp_ctx *c, int s, bool result_in_second_set = true) {
     Species &sp = c->sp[s];
     std::swap(sp.chunks, sp.chunks2); std::swap(sp.nchunks, sp.nchunks2); sp.chunk = sp.chunk2;
-    std::swap(sp.x, sp.x2); std::swap(sp.y, sp.y2); std::swap(sp.vx, sp.vx2); std::swap(sp.vy, sp.vy2);
-    std::swap(sp.id, sp.id2);
+    if (result_in_second_set) {
+        std::swap(sp.x, sp.x2); std::swap(sp.y, sp.y2); std::swap(sp.vx, sp.vx2); std::swap(sp.vy, sp.vy2);
+        std::swap(sp.id, sp.id2);
+    }
     sp.has_perm = true; sp.sorted = true; sp.steps_since_sort = 0;
     sp.cnt_valid = false;          // new chunk table
     sp.staged_v_valid = false;     // the staging buffers are now the live ones
@@ -144,6 +146,20 @@ void op_sort(picsp_ctx *c, int s) {
     Species &sp = c->sp[s];
     sort_prepare(c, s);
     const uint32_t *ids = sp.has_perm ? sp.id : (const uint32_t *)nullptr;
+    const int nt = c->g.ntx * c->g.nty;
+    if (!sp.sorted && sp.n >= 100000 && nt >= 256) {
+        // first binning of a large arbitrary load: coarse pass into the second set, fine pass back (k_sort_pass)
+        int shift = 0;
+        while ((((nt - 1) >> shift) + 1) > 64) shift++;
+        const int blocks = (int)((sp.n + SORT2_SLICE - 1) / SORT2_SLICE);
+        PICSP_LAUNCH(c, (k_sort_pass<true>), blocks, SORT2_THREADS, 0, sp.x, sp.y, sp.vx, sp.vy, ids, (long long)sp.n,
+                     push_const(c, s), shift, sp.tile_off, sp.cursor, sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2);
+        PICSP_CUDA(cudaMemsetAsync(sp.cursor, 0, sizeof(unsigned int) * nt, c->stream));
+        PICSP_LAUNCH(c, (k_sort_pass<false>), blocks, SORT2_THREADS, 0, sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2, (long long)sp.n,
+                     push_const(c, s), shift, sp.tile_off, sp.cursor, sp.x, sp.y, sp.vx, sp.vy, sp.id);
+        sort_finish(c, s, false);
+        return;
+    }
     if (sp.n > 0) {
         if (sp.sorted)
             PICSP_LAUNCH(c, k_resort_chunks, mover_grid(sp), RESORT_THREADS, 0, sp.x, sp.y, sp.vx, sp.vy, ids,
@@ -264,7 +280,7 @@ void op_grid_phase(picsp_ctx *c) {
             sp.acc_valid = false;
         }
         const int clear = (c->prm.flags & PICSP_FLAG_CLEAR_DENSITY) ? 1 : 0;
-        PICSP_LAUNCH(c, k_grid_phase, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, gs[0], gs[1], c->rho, g.nix, g.niy, clear);
+        PICSP_LAUNCH(c, k_grid_phase, blocks_for(g.nn, 256, c->num_sms * 32), 256, 0, gs[0], gs[1], c->rho, g.nix, g.niy, clear);   // one node per thread up to 1.2M nodes: latency-bound otherwise
     }
     if (c->comm) op_allreduce_rho(c);    // the folds are linear: folding the partial rho first commutes with the sum
 }

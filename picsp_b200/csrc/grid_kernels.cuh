@@ -82,8 +82,11 @@ __global__ void k_grid_phase(GridPhaseSpecies s0, GridPhaseSpecies s1, double *_
     const unsigned nn = (unsigned)nix * (unsigned)niy;      // <= 2^31 by the capacity of int node counts
     for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < nn; k += gridDim.x * blockDim.x) {
         const int i = (int)(k / (unsigned)niy), j = (int)(k - (unsigned)i * (unsigned)niy);
-        if (i > 0 && i < L && j > 0 && j < M) {              // interior node
-            const double di = finalize_node(s0, k, sc0, clear), de = finalize_node(s1, k, sc1, clear);
+        if (i > 0 && i < L && j > 0 && j < M) {              // interior node: all four loads in flight before the first store
+            const long long a0 = s0.acc[k], a1 = s1.acc[k];
+            const double d0 = clear ? 0.0 : s0.den[k], d1 = clear ? 0.0 : s1.den[k];
+            const double di = d0 + (double)a0 * sc0, de = d1 + (double)a1 * sc1;
+            s0.acc[k] = 0; s1.acc[k] = 0;
             s0.den[k] = di; s1.den[k] = de;
             rho[k] = s0.q * di + s1.q * de;
         } else if (i == 0 && j > 0 && j < M) {               // rows 0 and L: the (0,j) thread owns the pair

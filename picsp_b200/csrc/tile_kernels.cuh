@@ -162,6 +162,82 @@ k_sort_scatter(const double *__restrict__ x, const double *__restrict__ y, const
     }
 }
 
+// First binning of a LARGE arbitrary load in two passes.  A one-pass scatter of randomly ordered particles sends
+// every 8-byte store of a warp to a different bin: DRAM then works in 32-byte sectors it has to read, patch and write
+// back (56 ms for 5e8 particles, 0.64 TB/s).  Here pass A groups the particles by COARSE bin (up to 64 contiguous
+// ranges of bins; tpc = bins per coarse bin, a power of two) and pass B orders each coarse range by bin.  In both
+// passes one CTA takes 4096 consecutive source particles, which fall into few classes (<= 64 coarse bins; the
+// <= 2*tpc bins of the one or two coarse ranges the slice touches), ranks them per class in shared memory, reserves
+// ONE contiguous range per class with a single global atomic and writes runs of ~64 particles.  Pass A goes from the
+// primary arrays to the second set, pass B back: the result is in the primary arrays.
+constexpr int SORT2_THREADS = 256;
+constexpr int SORT2_SLICE = 4096;
+constexpr int SORT2_MAXCLS = 1024;            // shared-memory counters; classes beyond take an individual slot
+
+template <bool COARSE>
+__global__ void __launch_bounds__(SORT2_THREADS, 4)
+k_sort_pass(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ vx,
+            const double *__restrict__ vy, const uint32_t *__restrict__ id, long long n, PushConst c, int tpc_shift,
+            const long long *__restrict__ tile_off, unsigned int *__restrict__ cursor,
+            double *__restrict__ x2, double *__restrict__ y2, double *__restrict__ vx2, double *__restrict__ vy2,
+            uint32_t *__restrict__ id2) {
+    __shared__ unsigned s_cnt[SORT2_MAXCLS];
+    __shared__ unsigned s_base[SORT2_MAXCLS];
+    __shared__ unsigned s_code[SORT2_SLICE];      // class (low 12 bits... see below) and rank of every particle of the slice
+    __shared__ int s_first;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nt = c.ntx * c.nty;
+    const long long lo = (long long)blockIdx.x * SORT2_SLICE;
+    const int count = (int)min((long long)SORT2_SLICE, n - lo);
+    if (count <= 0) return;
+    const int ncls = COARSE ? min(SORT2_MAXCLS, ((nt - 1) >> tpc_shift) + 1) : min(SORT2_MAXCLS, 2 << tpc_shift);
+    for (int k = tid; k < ncls; k += SORT2_THREADS) s_cnt[k] = 0u;
+    // pass B: classes are bins relative to the first bin of the coarse range the slice starts in (the source is
+    // ordered by coarse range, so every particle of the slice is in that range or a later one)
+    if (!COARSE && tid == 0) s_first = (tile_of(x[lo], y[lo], c) >> tpc_shift) << tpc_shift;
+    __syncthreads();
+    const int first = COARSE ? 0 : s_first;
+
+    for (int k0 = 0; k0 < count; k0 += SORT2_THREADS) {          // warp-uniform trip count
+        const int k = k0 + tid;
+        const bool live = k < count;
+        int cls = -1;
+        if (live) {
+            const long long p = lo + k;
+            const int t = tile_of(x[p], y[p], c);
+            cls = COARSE ? (t >> tpc_shift) : (t - first);
+            if (cls >= ncls) {            // more classes than counters (tiny coarse ranges of a very non-uniform load): individual slot
+                const int u = COARSE ? (t >> tpc_shift) : t;          // cursor index: coarse range or bin
+                const long long base = COARSE ? tile_off[min(u << tpc_shift, nt)] : tile_off[t];
+                const long long dst = base + atomicAdd(&cursor[u], 1u);
+                x2[dst] = x[p]; y2[dst] = y[p]; vx2[dst] = vx[p]; vy2[dst] = vy[p];
+                id2[dst] = id ? id[p] : (uint32_t)p;
+                cls = -1;
+            }
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, cls);
+        const int leader = __ffs(peers) - 1;
+        unsigned r0 = 0;
+        if (cls >= 0 && lane == leader) r0 = atomicAdd(&s_cnt[cls], (unsigned)__popc(peers));
+        r0 = __shfl_sync(0xffffffffu, r0, leader);
+        if (live) s_code[k] = cls < 0 ? 0xFFFFFFFFu : ((unsigned)cls << 16) | (r0 + (unsigned)__popc(peers & ((1u << lane) - 1u)));   // rank < 4096 < 2^16
+    }
+    __syncthreads();
+    for (int k = tid; k < ncls; k += SORT2_THREADS)
+        if (s_cnt[k]) s_base[k] = atomicAdd(&cursor[COARSE ? k : first + k], s_cnt[k]);
+    __syncthreads();
+    for (int k = tid; k < count; k += SORT2_THREADS) {
+        const unsigned code = s_code[k];
+        if (code == 0xFFFFFFFFu) continue;
+        const int cls = (int)(code >> 16);
+        const long long p = lo + k;
+        const long long base = COARSE ? tile_off[min(cls << tpc_shift, nt)] : tile_off[first + cls];
+        const long long dst = base + s_base[cls] + (code & 0xFFFFu);
+        x2[dst] = x[p]; y2[dst] = y[p]; vx2[dst] = vx[p]; vy2[dst] = vy[p];
+        id2[dst] = id ? id[p] : (uint32_t)p;
+    }
+}
+
 // Re-sort of an already binned store: one CTA per source chunk.  Nearly every particle stays in its bin
 // or moves to one of the 8 neighbours, so the CTA first ranks its particles per destination class in shared
 // memory (warp-aggregated), reserves ONE contiguous range per destination bin with a single global atomic,

@@ -17,6 +17,7 @@ for s in range(2):
     t0 = time.perf_counter(); check(sim.L.picsp_species_download(sim.ctx, s, *(ptr(t) for t in host[s]))); print("download", s, time.perf_counter() - t0)
 for s in range(2):
     t0 = time.perf_counter(); check(sim.L.picsp_species_upload(sim.ctx, s, *(ptr(t) for t in host[s]), n)); print("upload", s, time.perf_counter() - t0)
+t0 = time.perf_counter(); sim.sync(); print("first binning still running after the last upload returned: ms", (time.perf_counter() - t0) * 1e3)
 sim.profile_enable(True)
 for k in range(3):
     sim.profile_reset(); t0 = time.perf_counter(); sim.step(1); sim.sync(); dt = time.perf_counter() - t0

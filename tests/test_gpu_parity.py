@@ -418,6 +418,44 @@ def test_ke_after_a_dump_uses_the_staged_velocities_and_is_bit_identical():
         assert ke1 == sim.computeKE(ELECTRON) and ke1 != after
 
 
+@pytest.mark.parametrize("numx,shape", [(512, "corner"), (1024, "uniform"), (256, "stripe")])
+def test_two_pass_first_binning(numx, shape):
+    """First binning of a large arbitrary load (k_sort_pass: coarse pass, fine pass).  'corner' puts 90 % of the
+    particles into one corner and spreads the rest thinly, so that a 4096-particle slice of the coarse-ordered store
+    spans many coarse ranges (individual-slot path); the binned store must hold exactly the uploaded particles
+    (download == upload, bit for bit, in upload order) and give the same step as the unsorted implementation."""
+    nm = normalise()
+    n = 250_000
+    rng = np.random.default_rng(17)
+    xl = numx * nm["dx"]
+    if shape == "corner":
+        x = np.where(rng.random(n) < 0.9, rng.random(n) * xl / 40, rng.random(n) * xl)
+        y = np.where(rng.random(n) < 0.9, rng.random(n) * xl / 40, rng.random(n) * xl)
+    elif shape == "stripe":
+        x = rng.random(n) * xl; y = (0.45 + 0.1 * rng.random(n)) * xl
+    else:
+        x = rng.random(n) * xl; y = rng.random(n) * xl
+    vx, vy = rng.standard_normal(n), rng.standard_normal(n)
+    runs = []
+    for flags in (0, 2):
+        with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, flags=flags)) as sim:
+            sim.set_species(ELECTRON, x, y, vx, vy)
+            sim.set_species(ION, x[::-1].copy(), y[::-1].copy(), 0.02 * vx, 0.02 * vy)
+            sim.scatterSpecies(ELECTRON)                       # forces the binning, leaves the particles alone
+            got = sim.get_species(ELECTRON)
+            for a, b in zip(got, (x, y, vx, vy)):
+                assert np.array_equal(a, b)
+            sim.bootstrap(); sim.step(2)
+            runs.append({g: sim.grid(g) for g in ("rho", "phi", "efx", "efy")} | {"pe": np.stack(sim.get_species(ELECTRON)),
+                                                                                   "pi": np.stack(sim.get_species(ION))})
+    a, b = runs
+    for g in ("rho", "phi", "efx", "efy"):
+        assert_grid_close(a[g], b[g], numx + 1, numx + 1, 10 * RTOL, f"tiled vs unsorted {g}")
+    for key in ("pe", "pi"):
+        for k in range(4):
+            assert relerr(a[key][k], b[key][k]) <= 10 * RTOL
+
+
 def test_clear_density_extension_and_accumulate_default():
     nm = normalise()
     numx, n = 32, 5000
