@@ -152,10 +152,15 @@ void op_sort(picsp_ctx *c, int s) {
         int shift = 0;
         while ((((nt - 1) >> shift) + 1) > 64) shift++;
         const int blocks = (int)((sp.n + SORT2_SLICE - 1) / SORT2_SLICE);
-        PICSP_LAUNCH(c, (k_sort_pass<true>), blocks, SORT2_THREADS, 0, sp.x, sp.y, sp.vx, sp.vy, ids, (long long)sp.n,
+        if (!c->sort2_opted_in) {
+            PICSP_CUDA(cudaFuncSetAttribute(k_sort_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT2_SMEM_BYTES));
+            PICSP_CUDA(cudaFuncSetAttribute(k_sort_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT2_SMEM_BYTES));
+            c->sort2_opted_in = true;
+        }
+        PICSP_LAUNCH(c, (k_sort_pass<true>), blocks, SORT2_THREADS, SORT2_SMEM_BYTES, sp.x, sp.y, sp.vx, sp.vy, ids, (long long)sp.n,
                      push_const(c, s), shift, sp.tile_off, sp.cursor, sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2);
         PICSP_CUDA(cudaMemsetAsync(sp.cursor, 0, sizeof(unsigned int) * nt, c->stream));
-        PICSP_LAUNCH(c, (k_sort_pass<false>), blocks, SORT2_THREADS, 0, sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2, (long long)sp.n,
+        PICSP_LAUNCH(c, (k_sort_pass<false>), blocks, SORT2_THREADS, SORT2_SMEM_BYTES, sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2, (long long)sp.n,
                      push_const(c, s), shift, sp.tile_off, sp.cursor, sp.x, sp.y, sp.vx, sp.vy, sp.id);
         sort_finish(c, s, false);
         return;

@@ -134,6 +134,7 @@ struct picsp_ctx {
     bool have_tmap = false;
     bool smem_opted_in = false;
     bool hist_smem_opted_in = false;
+    bool sort2_opted_in = false;
 
     // staging for grid component uploads/downloads
     double *stage = nullptr; int64_t stage_cap = 0;

@@ -163,28 +163,34 @@ k_sort_scatter(const double *__restrict__ x, const double *__restrict__ y, const
 }
 
 // First binning of a LARGE arbitrary load in two passes.  A one-pass scatter of randomly ordered particles sends
-// every 8-byte store of a warp to a different bin: DRAM then works in 32-byte sectors it has to read, patch and write
-// back (56 ms for 5e8 particles, 0.64 TB/s).  Here pass A groups the particles by COARSE bin (up to 64 contiguous
-// ranges of bins; tpc = bins per coarse bin, a power of two) and pass B orders each coarse range by bin.  In both
-// passes one CTA takes 4096 consecutive source particles, which fall into few classes (<= 64 coarse bins; the
-// <= 2*tpc bins of the one or two coarse ranges the slice touches), ranks them per class in shared memory, reserves
-// ONE contiguous range per class with a single global atomic and writes runs of ~64 particles.  Pass A goes from the
-// primary arrays to the second set, pass B back: the result is in the primary arrays.
-constexpr int SORT2_THREADS = 256;
+// every 8-byte store of a warp to a different bin: 2.5e9 single-sector writes for 5e8 particles (56 ms, 0.64 TB/s).
+// Here pass A groups the particles by COARSE range (up to 64 contiguous ranges of bins; tpc = bins per range, a
+// power of two) and pass B orders each range by bin.  In both passes one CTA takes 4096 consecutive source
+// particles, which fall into few classes (<= 64 coarse ranges; the <= 2*tpc bins of the one or two ranges the slice
+// touches); it ranks them per class (warp-aggregated shared-memory counters), reserves ONE contiguous range per
+// class with a single global atomic, and then moves each array through shared memory IN CLASS ORDER, so that
+// consecutive threads store to consecutive addresses (runs of ~64 particles).  Pass A goes from the primary arrays
+// to the second set, pass B back: the result is in the primary arrays.
+constexpr int SORT2_THREADS = 512;
 constexpr int SORT2_SLICE = 4096;
 constexpr int SORT2_MAXCLS = 1024;            // shared-memory counters; classes beyond take an individual slot
+constexpr size_t SORT2_SMEM_BYTES = sizeof(double) * SORT2_SLICE + sizeof(unsigned) * (2 * SORT2_SLICE + 3 * SORT2_MAXCLS);
 
 template <bool COARSE>
-__global__ void __launch_bounds__(SORT2_THREADS, 4)
+__global__ void __launch_bounds__(SORT2_THREADS, 2)
 k_sort_pass(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ vx,
             const double *__restrict__ vy, const uint32_t *__restrict__ id, long long n, PushConst c, int tpc_shift,
             const long long *__restrict__ tile_off, unsigned int *__restrict__ cursor,
             double *__restrict__ x2, double *__restrict__ y2, double *__restrict__ vx2, double *__restrict__ vy2,
             uint32_t *__restrict__ id2) {
-    __shared__ unsigned s_cnt[SORT2_MAXCLS];
-    __shared__ unsigned s_base[SORT2_MAXCLS];
-    __shared__ unsigned s_code[SORT2_SLICE];      // class (low 12 bits... see below) and rank of every particle of the slice
-    __shared__ int s_first;
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    double *s_val = reinterpret_cast<double *>(sort_smem);                  // [SLICE] one array of the slice, in class order
+    unsigned *s_dst = reinterpret_cast<unsigned *>(s_val + SORT2_SLICE);     // [SLICE] destination slot of class-ordered element q
+    unsigned *s_pos = s_dst + SORT2_SLICE;                                   // [SLICE] class | rank, later class-ordered position, of source element k
+    unsigned *s_cnt = s_pos + SORT2_SLICE;                                   // [MAXCLS]
+    unsigned *s_base = s_cnt + SORT2_MAXCLS;                                 // [MAXCLS] first slot reserved in the destination bin / range
+    unsigned *s_pref = s_base + SORT2_MAXCLS;                                // [MAXCLS] exclusive prefix of s_cnt
+    __shared__ int s_first, s_total;
     const int tid = threadIdx.x, lane = tid & 31;
     const int nt = c.ntx * c.nty;
     const long long lo = (long long)blockIdx.x * SORT2_SLICE;
@@ -198,6 +204,7 @@ k_sort_pass(const double *__restrict__ x, const double *__restrict__ y, const do
     __syncthreads();
     const int first = COARSE ? 0 : s_first;
 
+    // 1. class and rank of every particle
     for (int k0 = 0; k0 < count; k0 += SORT2_THREADS) {          // warp-uniform trip count
         const int k = k0 + tid;
         const bool live = k < count;
@@ -220,22 +227,48 @@ k_sort_pass(const double *__restrict__ x, const double *__restrict__ y, const do
         unsigned r0 = 0;
         if (cls >= 0 && lane == leader) r0 = atomicAdd(&s_cnt[cls], (unsigned)__popc(peers));
         r0 = __shfl_sync(0xffffffffu, r0, leader);
-        if (live) s_code[k] = cls < 0 ? 0xFFFFFFFFu : ((unsigned)cls << 16) | (r0 + (unsigned)__popc(peers & ((1u << lane) - 1u)));   // rank < 4096 < 2^16
+        if (live) s_pos[k] = cls < 0 ? 0xFFFFFFFFu : ((unsigned)cls << 16) | (r0 + (unsigned)__popc(peers & ((1u << lane) - 1u)));   // rank < 4096 < 2^16
     }
     __syncthreads();
+    // 2. one reservation per class; exclusive prefix of the class populations (warp 0: 32 classes per lane)
     for (int k = tid; k < ncls; k += SORT2_THREADS)
         if (s_cnt[k]) s_base[k] = atomicAdd(&cursor[COARSE ? k : first + k], s_cnt[k]);
+    if (tid < 32) {
+        const int per = (ncls + 31) / 32, k0 = tid * per, k1 = min(k0 + per, ncls);
+        unsigned sum = 0;
+        for (int k = k0; k < k1; k++) sum += s_cnt[k];
+        unsigned incl = sum;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        unsigned run = incl - sum;
+        for (int k = k0; k < k1; k++) { s_pref[k] = run; run += s_cnt[k]; }
+        if (tid == 31) s_total = (int)incl;
+    }
     __syncthreads();
+    // 3. class-ordered position of every source element and the destination slot of every position
     for (int k = tid; k < count; k += SORT2_THREADS) {
-        const unsigned code = s_code[k];
+        const unsigned code = s_pos[k];
         if (code == 0xFFFFFFFFu) continue;
         const int cls = (int)(code >> 16);
-        const long long p = lo + k;
+        const unsigned rank = code & 0xFFFFu;
         const long long base = COARSE ? tile_off[min(cls << tpc_shift, nt)] : tile_off[first + cls];
-        const long long dst = base + s_base[cls] + (code & 0xFFFFu);
-        x2[dst] = x[p]; y2[dst] = y[p]; vx2[dst] = vx[p]; vy2[dst] = vy[p];
-        id2[dst] = id ? id[p] : (uint32_t)p;
+        const unsigned q = s_pref[cls] + rank;
+        s_pos[k] = q;
+        s_dst[q] = (unsigned)(base + s_base[cls] + rank);       // < 2^32: per-rank species capacity
     }
+    __syncthreads();
+    // 4. each array: coalesced read -> shared memory in class order -> runs of consecutive stores
+    const int total = s_total;
+    auto move = [&](const double *__restrict__ src, double *__restrict__ dstp) {
+        for (int k = tid; k < count; k += SORT2_THREADS) { const unsigned q = s_pos[k]; if (q != 0xFFFFFFFFu) s_val[q] = src[lo + k]; }
+        __syncthreads();
+        for (int q = tid; q < total; q += SORT2_THREADS) dstp[s_dst[q]] = s_val[q];
+        __syncthreads();
+    };
+    move(x, x2); move(y, y2); move(vx, vx2); move(vy, vy2);
+    unsigned *s_ival = reinterpret_cast<unsigned *>(s_val);
+    for (int k = tid; k < count; k += SORT2_THREADS) { const unsigned q = s_pos[k]; if (q != 0xFFFFFFFFu) s_ival[q] = id ? id[lo + k] : (uint32_t)(lo + k); }
+    __syncthreads();
+    for (int q = tid; q < total; q += SORT2_THREADS) id2[s_dst[q]] = s_ival[q];
 }
 
 // Re-sort of an already binned store: one CTA per source chunk.  Nearly every particle stays in its bin
