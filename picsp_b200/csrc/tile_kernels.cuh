@@ -673,26 +673,34 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
         if (MODE != 1) {
             // histogram of the positions just written (bins of the next sort, bound of the next
             // scale); same bin function as tile_of(): out-of-box positions count in bin 0
-            const int ux = ci >= 0 ? min((int)((unsigned)ci / TILE), tc.ntx1) : 0;
-            const int uy = ci >= 0 ? min((int)((unsigned)cj / TILE), tc.nty1) : 0;
-            if (ux == tc.tx && uy == tc.ty) {
+            // common case in ONE test: the push started and ended in this chunk's own bin (cell - first cell of the
+            // bin < TILE for all four coordinates; -1 = outside the box fails it).  ci < ncx, so ci / TILE never
+            // exceeds ntx - 1 and the clamp of tile_of_cell() is the identity for it.
+            const int cx0 = tc.tx * TILE, cy0 = tc.ty * TILE;
+            if (((unsigned)(ci - cx0) | (unsigned)(cj - cy0) | (unsigned)(oi - cx0) | (unsigned)(oj - cy0)) < (unsigned)TILE) {
                 same++;
             } else {
-                int ddx = ux - tc.tx, ddy = uy - tc.ty;
-                if (ddx > 1) ddx -= c.ntx; else if (ddx < -1) ddx += c.ntx;      // periodic neighbours
-                if (ddy > 1) ddy -= c.nty; else if (ddy < -1) ddy += c.nty;
-                if (nbr_ok && ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1)
-                    atomicAdd(&sCnt[(ddx + 1) * 3 + (ddy + 1)], 1u);
-                else
-                    atomicAdd(&hist_next[ux * c.nty + uy], 1u);
-            }
-            // the fixed-point scale assumes no particle moves more than one tile in ONE step
-            const int ox = oi >= 0 ? min((int)((unsigned)oi / TILE), tc.ntx1) : 0;
-            const int oy = oi >= 0 ? min((int)((unsigned)oj / TILE), tc.nty1) : 0;
-            if (ox != ux || oy != uy) {
-                int ax = abs(ux - ox), ay = abs(uy - oy);
-                ax = min(ax, c.ntx - ax); ay = min(ay, c.nty - ay);
-                if (ax > 1 || ay > 1) atomicOr(err, ERR_BIT_DISPLACEMENT);
+                const int ux = ci >= 0 ? min((int)((unsigned)ci / TILE), tc.ntx1) : 0;
+                const int uy = ci >= 0 ? min((int)((unsigned)cj / TILE), tc.nty1) : 0;
+                if (ux == tc.tx && uy == tc.ty) {
+                    same++;
+                } else {
+                    int ddx = ux - tc.tx, ddy = uy - tc.ty;
+                    if (ddx > 1) ddx -= c.ntx; else if (ddx < -1) ddx += c.ntx;      // periodic neighbours
+                    if (ddy > 1) ddy -= c.nty; else if (ddy < -1) ddy += c.nty;
+                    if (nbr_ok && ddx >= -1 && ddx <= 1 && ddy >= -1 && ddy <= 1)
+                        atomicAdd(&sCnt[(ddx + 1) * 3 + (ddy + 1)], 1u);
+                    else
+                        atomicAdd(&hist_next[ux * c.nty + uy], 1u);
+                }
+                // the fixed-point scale assumes no particle moves more than one tile in ONE step
+                const int ox = oi >= 0 ? min((int)((unsigned)oi / TILE), tc.ntx1) : 0;
+                const int oy = oi >= 0 ? min((int)((unsigned)oj / TILE), tc.nty1) : 0;
+                if (ox != ux || oy != uy) {
+                    int ax = abs(ux - ox), ay = abs(uy - oy);
+                    ax = min(ax, c.ntx - ax); ay = min(ay, c.nty - ay);
+                    if (ax > 1 || ay > 1) atomicOr(err, ERR_BIT_DISPLACEMENT);
+                }
             }
         }
     };
