@@ -326,6 +326,7 @@ def run_e2e(sim, args, n_local, barrier, max_over_ranks, torch):
     ptr = lambda t: C.cast(t.data_ptr(), dp)  # noqa: E731
     for s in range(2):   # untimed: seed the host buffers with the current device state
         check(sim.L.picsp_species_download(sim.ctx, s, *(ptr(t) for t in host[s])))
+        sim.computeKE(s)   # untimed: NCCL sets up the small-message path of the KE all-reduce lazily on its first call (one-off, ~1 s at 8 ranks)
     steps = args.e2e_steps
     barrier()
     t0 = time.perf_counter()
