@@ -338,18 +338,22 @@ def run_e2e(sim, args, n_local, barrier, max_over_ranks, torch):
     t2 = time.perf_counter()
     for s in range(2):
         check(sim.L.picsp_species_download(sim.ctx, s, *(ptr(t) for t in host[s])))
+    t2b = time.perf_counter()
     for gid, t in zip((0, 1, 3), grids):
         check(sim.L.picsp_grid_download(sim.ctx, gid, ptr(t)))
     ke = [sim.computeKE(0), sim.computeKE(1)]
     t3 = time.perf_counter()
     barrier()
     dt = max_over_ranks(time.perf_counter() - t0)
+    slowest = {"upload": max_over_ranks(t1 - t0), "steps": max_over_ranks(t2 - t1),
+               "download": max_over_ranks(t2b - t2), "grids_and_ke": max_over_ranks(t3 - t2b)}
     h2d = 2 * 4 * 8 * n_local
     d2h = 2 * 4 * 8 * n_local + 3 * 8 * nn + 16
     return {"value": float(args.particles) * steps / dt, "unit": UNIT,
             "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps,
             "steps_per_call": steps, "seconds": dt, "pinned_host_memory": pinned,
             "seconds_rank0": {"upload": t1 - t0, "steps": t2 - t1, "download_and_diagnostics": t3 - t2},
+            "seconds_slowest_rank": slowest,
             "what": "picsp_species_upload x2 -> picsp_step(50) -> picsp_species_download x2 + den.i, den.e, phi + KE "
                     "(bytes are per rank, amortised over the dump period)", "ke_finite": bool(np.isfinite(ke).all())}
 
