@@ -51,6 +51,15 @@ template <class T> void dalloc(T **p, size_t count) {
     PICSP_CUDA(cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T)));
 }
 
+// One buffer set of a species = ONE allocation holding x, y, vx, vy back to back (x is its base).  +2: bulk slices
+// are widened to even indices; the stride is a multiple of 32 doubles so every array stays 256-byte aligned.  The
+// idle set doubles as a contiguous staging block of 4*cap doubles (row-layout dumps).
+void alloc_particle_set(double **x, double **y, double **vx, double **vy, int64_t cap) {
+    const size_t stride = (((size_t)cap + 2 + 31) / 32) * 32;
+    dalloc(x, 4 * stride);
+    *y = *x + stride; *vx = *x + 2 * stride; *vy = *x + 3 * stride;
+}
+
 int particle_blocks(const picsp_ctx *c, long long n, int threads) {
     return blocks_for(n, threads, c->num_sms * 16);
 }
@@ -121,7 +130,7 @@ void sort_prepare(picsp_ctx *c, int s) {
     const int nt = g.ntx * g.nty;
     ensure_hist(c, s);
     if (!sp.x2) {
-        dalloc(&sp.x2, sp.cap + 2); dalloc(&sp.y2, sp.cap + 2); dalloc(&sp.vx2, sp.cap + 2); dalloc(&sp.vy2, sp.cap + 2);
+        alloc_particle_set(&sp.x2, &sp.y2, &sp.vx2, &sp.vy2, sp.cap);
         dalloc(&sp.id, sp.cap + 8); dalloc(&sp.id2, sp.cap + 8);   // +8: bulk slices of ids are widened to multiples of 4
         dalloc((Chunk **)&sp.chunks2, (size_t)sp.max_chunks); dalloc(&sp.nchunks2, 1);
         dalloc(&sp.chunk_cnt, (size_t)sp.max_chunks * 9); dalloc(&sp.chunk_base, (size_t)sp.max_chunks * 9);
@@ -499,7 +508,7 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
         for (int s = 0; s < 2; s++) {
             Species &sp = c->sp[s];
             sp.cap = p->capacity[s]; sp.q = p->charge[s]; sp.m = p->mass[s]; sp.spwt = p->spwt[s];
-            dalloc(&sp.x, sp.cap + 2); dalloc(&sp.y, sp.cap + 2); dalloc(&sp.vx, sp.cap + 2); dalloc(&sp.vy, sp.cap + 2);   // +2: bulk slices are widened to even indices
+            alloc_particle_set(&sp.x, &sp.y, &sp.vx, &sp.vy, sp.cap);
             dalloc(&sp.den, g.nn); dalloc(&sp.acc, g.nn); dalloc(&sp.frac, 1); dalloc(&sp.frac_scratch, 2);
             dalloc(&sp.hist, (size_t)g.ntx * g.nty); dalloc(&sp.hist_next, (size_t)g.ntx * g.nty);
             dalloc(&sp.counters, 2);
@@ -559,9 +568,9 @@ void picsp_destroy(picsp_ctx *c) {
     if (c->have_plans) { cufftDestroy(c->plan_fwd); cufftDestroy(c->plan_inv); }
     for (int s = 0; s < 2; s++) {
         Species &sp = c->sp[s];
-        cudaFree(sp.x); cudaFree(sp.y); cudaFree(sp.vx); cudaFree(sp.vy); cudaFree(sp.id);
+        cudaFree(sp.x); cudaFree(sp.id);            // x is the base of the set's single allocation
         cudaFree(sp.den); cudaFree(sp.acc); cudaFree(sp.frac); cudaFree(sp.frac_scratch); cudaFree(sp.hist); cudaFree(sp.hist_next); cudaFree(sp.counters);
-        cudaFree(sp.x2); cudaFree(sp.y2); cudaFree(sp.vx2); cudaFree(sp.vy2); cudaFree(sp.id2);
+        cudaFree(sp.x2); cudaFree(sp.id2);
         cudaFree(sp.tile_off); cudaFree(sp.chunks); cudaFree(sp.nchunks); cudaFree(sp.cursor);
         cudaFree(sp.chunks2); cudaFree(sp.nchunks2); cudaFree(sp.chunk_cnt); cudaFree(sp.chunk_base);
     }
@@ -665,14 +674,25 @@ int picsp_species_download_rows(picsp_ctx *c, int s, double *rows) {
     PICSP_API_BEGIN
     check_ctx(c); check_species(s);
     PICSP_REQUIRE(rows != nullptr, PICSP_ERR_INVALID, "null rows");
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
     Species &sp = c->sp[s];
-    std::vector<double> tmp((size_t)sp.n * 4);
-    double *a = tmp.data();
-    int rc = picsp_species_download(c, s, a, a + sp.n, a + 2 * sp.n, a + 3 * sp.n);
-    if (rc != PICSP_OK) return rc;
-    for (int64_t p = 0; p < sp.n; p++) {   // writeSpecies row layout {x, y, vx, vy}, src/main.cpp:1156-1159
-        rows[4 * p + 0] = a[p]; rows[4 * p + 1] = a[sp.n + p];
-        rows[4 * p + 2] = a[2 * sp.n + p]; rows[4 * p + 3] = a[3 * sp.n + p];
+    if (sp.n > 0 && sp.x2) {
+        // writeSpecies row layout {x, y, vx, vy} (src/main.cpp:1156-1159) built on the device: every particle's 32 bytes
+        // go to row id[slot] of the idle buffer set (one whole sector per particle), then one device->host copy
+        PICSP_LAUNCH(c, k_rows_unpermute, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy,
+                     sp.has_perm ? sp.id : (const uint32_t *)nullptr, (long long)sp.n, reinterpret_cast<double2 *>(sp.x2));
+        sp.staged_v_valid = false;                  // the staging block has been overwritten
+        PICSP_CUDA(cudaMemcpyAsync(rows, sp.x2, sizeof(double) * 4 * (size_t)sp.n, cudaMemcpyDeviceToHost, c->stream));
+        check_device_error(c);
+    } else if (sp.n > 0) {                          // store without a second buffer set (PICSP_FLAG_NO_SORT): interleave on the host
+        std::vector<double> tmp((size_t)sp.n * 4);
+        double *a = tmp.data();
+        int rc = picsp_species_download(c, s, a, a + sp.n, a + 2 * sp.n, a + 3 * sp.n);
+        if (rc != PICSP_OK) return rc;
+        for (int64_t p = 0; p < sp.n; p++) {
+            rows[4 * p + 0] = a[p]; rows[4 * p + 1] = a[sp.n + p];
+            rows[4 * p + 2] = a[2 * sp.n + p]; rows[4 * p + 3] = a[3 * sp.n + p];
+        }
     }
     PICSP_API_END
 }

@@ -287,4 +287,15 @@ __global__ void k_unpermute(const double *__restrict__ in, const uint32_t *__res
         out[id[p]] = in[p];
 }
 
+// row-layout dump: rows[id[slot]] = {x, y, vx, vy}[slot] (id == nullptr: identity); 32 contiguous bytes per particle
+__global__ void k_rows_unpermute(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ vx,
+                                 const double *__restrict__ vy, const uint32_t *__restrict__ id, long long n,
+                                 double2 *__restrict__ rows) {
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const long long r = id ? (long long)id[p] : p;
+        rows[2 * r] = make_double2(x[p], y[p]);
+        rows[2 * r + 1] = make_double2(vx[p], vy[p]);
+    }
+}
+
 }  // namespace picsp

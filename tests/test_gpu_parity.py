@@ -456,6 +456,25 @@ def test_two_pass_first_binning(numx, shape):
             assert relerr(a[key][k], b[key][k]) <= 10 * RTOL
 
 
+@pytest.mark.parametrize("flags", [0, 2], ids=["tiled", "unsorted"])
+def test_row_layout_dump_equals_array_download(flags):
+    """picsp_species_download_rows (the [n][4] layout writeSpecies dumps, main.cpp:1152-1162) is built on the device
+    in the idle buffer set; it must equal the four-array download, and must not disturb a later KE or download."""
+    nm = normalise()
+    numx, n = 80, 123_457
+    with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, flags=flags)) as sim:
+        sim.fill_synthetic(ION, n, seed=8, vth=nm["vth_i"])
+        sim.fill_synthetic(ELECTRON, n, seed=9, vth=1.0, xdrift=nm["drift_e"])
+        sim.bootstrap(); sim.step(3)
+        for s in (ION, ELECTRON):
+            cols = np.stack(sim.get_species(s))
+            ke = sim.computeKE(s)                      # staged-velocity shortcut (tiled store)
+            rows = sim.get_species_rows(s)
+            assert rows.shape == (n, 4) and np.array_equal(rows.T, cols)
+            assert sim.computeKE(s) == ke              # the row dump overwrote the staging block: full path, same value
+            assert np.array_equal(np.stack(sim.get_species(s)), cols)
+
+
 def test_clear_density_extension_and_accumulate_default():
     nm = normalise()
     numx, n = 32, 5000
