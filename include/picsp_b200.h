@@ -67,7 +67,8 @@ enum {
     PICSP_FLAG_NO_SORT       = 1 << 1,  /* keep particles in upload order (no periodic tile sort) */
     PICSP_FLAG_NO_FUSE       = 1 << 2,  /* push does not pre-accumulate the next step's deposit */
     PICSP_FLAG_SOR_SINGLE_CTA = 1 << 3, /* SOR: use the single-CTA anti-diagonal kernel for every sweep (cross-check path) */
-    PICSP_FLAG_SEPARATE_SORT  = 1 << 4  /* periodic re-binning as a stand-alone pass instead of inside the mover (cross-check path) */
+    PICSP_FLAG_SEPARATE_SORT  = 1 << 4, /* periodic re-binning as a stand-alone pass instead of inside the mover (cross-check path) */
+    PICSP_FLAG_NO_GRAPH       = 1 << 5  /* picsp_step never replays captured CUDA graphs (cross-check path) */
 };
 
 /* Normalised quantities, i.e. the reference's globals after parse_ini_file

@@ -578,6 +578,7 @@ void picsp_destroy(picsp_ctx *c) {
     cudaFree(c->d_red); cudaFree(c->d_scalars); cudaFree(c->d_sor_status); cudaFree(c->d_sor_progress); cudaFree(c->d_error); cudaFree(c->stage);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto &t : c->timers) for (auto e : t.pool) cudaEventDestroy(e);
+    if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
     if (c->copy_stream) {
         cudaStreamDestroy(c->copy_stream);
         for (int k = 0; k < 4; k++) cudaEventDestroy(c->ev_ready[k]);
@@ -798,17 +799,82 @@ int picsp_bootstrap(picsp_ctx *c) {   // src/main.cpp:453-472
              op_rewind(c, 0); op_rewind(c, 1))
 }
 
+static void one_step(picsp_ctx *c) {
+    op_grid_phase(c);           // scatterSpecies x2 + computeRho (src/main.cpp:482-490)
+    op_solve(c);
+    op_compute_ef(c);
+    op_push(c, 0); op_push(c, 1);
+}
+
+// -- CUDA graph of a pair of steps (launch-bound populations only) ----------------------------------
+constexpr long long STEP_GRAPH_MAX_PARTICLES = 1ll << 26;   // above this a step is >= 1 ms of kernels and the launches hide behind them
+
+static bool step_graph_eligible(const picsp_ctx *c) {
+    if (c->profiling || c->comm || (c->prm.flags & (PICSP_FLAG_NO_GRAPH | PICSP_FLAG_NO_FUSE | PICSP_FLAG_NO_SORT))) return false;
+    if (c->sp[0].n + c->sp[1].n > STEP_GRAPH_MAX_PARTICLES) return false;
+    for (int s = 0; s < 2; s++) {
+        const Species &sp = c->sp[s];
+        // steady state of the fused loop, and no re-binning due in either of the two steps
+        if (!sp.sorted || !sp.acc_valid || !sp.hist_valid || sp.n <= 0 || !sp.chunk_cnt) return false;
+        if (sp.steps_since_sort + 1 >= sp.sort_period) return false;
+    }
+    return c->smem_opted_in;    // the per-function attributes must not be set during a capture
+}
+
+static picsp_ctx::StepGraphKey step_graph_key(const picsp_ctx *c) {
+    picsp_ctx::StepGraphKey k;
+    memset(&k, 0, sizeof(k));
+    int q = 0;
+    for (int s = 0; s < 2; s++) {
+        const Species &sp = c->sp[s];
+        k.ptr[q++] = sp.x; k.ptr[q++] = sp.hist; k.ptr[q++] = sp.hist_next; k.ptr[q++] = sp.chunks; k.ptr[q++] = sp.nchunks;
+        k.ptr[q++] = sp.chunk_cnt; k.ptr[q++] = sp.acc;
+        k.n[s] = sp.n; k.chunk[s] = sp.chunk;
+    }
+    return k;
+}
+
+static void step_pair_graph(picsp_ctx *c) {
+    const picsp_ctx::StepGraphKey key = step_graph_key(c);
+    if (c->step_graph && memcmp(&key, &c->step_key, sizeof(key)) == 0) {
+        PICSP_CUDA(cudaGraphLaunch(c->step_graph, c->stream));
+        for (int s = 0; s < 2; s++) {       // the host-side bookkeeping of two steps (the buffer swaps cancel out)
+            c->sp[s].steps_since_sort += 2;
+            c->sp[s].staged_v_valid = false;
+        }
+        c->launches += c->step_graph_launches;
+        c->busy[0] = c->busy[1] = true;
+        return;
+    }
+    if (c->step_graph) { cudaGraphExecDestroy(c->step_graph); c->step_graph = nullptr; }
+    const int64_t launches0 = c->launches;
+    cudaGraph_t graph = nullptr;
+    PICSP_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+        one_step(c); one_step(c);          // enqueues nothing yet: the launches are recorded; the host state advances
+    } catch (...) {
+        cudaStreamEndCapture(c->stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+    }
+    PICSP_CUDA(cudaStreamEndCapture(c->stream, &graph));
+    const cudaError_t e = cudaGraphInstantiate(&c->step_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { c->step_graph = nullptr; throw Error(PICSP_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    c->step_graph_launches = c->launches - launches0;
+    c->step_key = key;                     // a pair leaves every pointer of the key where it was
+    PICSP_CUDA(cudaGraphLaunch(c->step_graph, c->stream));
+}
+
 int picsp_step(picsp_ctx *c, int nsteps) {   // src/main.cpp:481-504
     PICSP_API_BEGIN
     check_ctx(c);
     PICSP_REQUIRE(nsteps >= 0, PICSP_ERR_INVALID, "negative step count");
     PICSP_CUDA(cudaSetDevice(c->prm.device));
     PhaseScope whole(c, PICSP_PHASE_STEP);
-    for (int it = 0; it < nsteps; it++) {
-        op_grid_phase(c);           // scatterSpecies x2 + computeRho (src/main.cpp:482-490)
-        op_solve(c);
-        op_compute_ef(c);
-        op_push(c, 0); op_push(c, 1);
+    for (int it = 0; it < nsteps;) {
+        if (nsteps - it >= 2 && step_graph_eligible(c)) { step_pair_graph(c); it += 2; }
+        else { one_step(c); it++; }
     }
     PICSP_API_END
 }

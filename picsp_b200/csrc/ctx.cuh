@@ -146,6 +146,14 @@ struct picsp_ctx {
     // (set conservatively by every launch; an upload of species s only has to wait when busy[s])
     bool busy[2] = {false, false};
 
+    // Small populations are launch-bound (~20 launches per step, 0.15-0.35 ms per step): between re-binnings two
+    // consecutive steps (the histogram buffers alternate, so a PAIR returns to the same pointers) are captured once
+    // into a CUDA graph and replayed.  The key lists everything the captured launches have baked in.
+    struct StepGraphKey { const void *ptr[14]; long long n[2]; int chunk[2]; };
+    cudaGraphExec_t step_graph = nullptr;
+    StepGraphKey step_key = {};
+    int64_t step_graph_launches = 0;
+
     // multi-GPU
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
 

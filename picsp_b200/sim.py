@@ -18,7 +18,7 @@ from .lib import CParams, check, load_library
 ION, ELECTRON = 0, 1
 GRID_IDS = {"den_i": 0, "den_e": 1, "rho": 2, "phi": 3, "efx": 4, "efy": 5}
 PHASES = ("deposit", "rho", "allreduce", "solve", "ef", "push", "sort", "step")
-FLAG_CLEAR_DENSITY, FLAG_NO_SORT, FLAG_NO_FUSE, FLAG_SOR_SINGLE_CTA, FLAG_SEPARATE_SORT = 1, 2, 4, 8, 16
+FLAG_CLEAR_DENSITY, FLAG_NO_SORT, FLAG_NO_FUSE, FLAG_SOR_SINGLE_CTA, FLAG_SEPARATE_SORT, FLAG_NO_GRAPH = 1, 2, 4, 8, 16, 32
 
 _dp = C.POINTER(C.c_double)
 

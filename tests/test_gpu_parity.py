@@ -11,7 +11,7 @@ import pytest
 import picsp_b200
 from oracle.oracle import ELECTRON, ION, Oracle, normalise
 from picsp_b200 import Params, Simulation
-from picsp_b200.sim import FLAG_SEPARATE_SORT
+from picsp_b200.sim import FLAG_NO_GRAPH, FLAG_SEPARATE_SORT
 from tests.helpers import GRIDS, RTOL, assert_grid_close, load_golden, relerr
 
 pytestmark = pytest.mark.gpu
@@ -473,6 +473,35 @@ def test_row_layout_dump_equals_array_download(flags):
             assert rows.shape == (n, 4) and np.array_equal(rows.T, cols)
             assert sim.computeKE(s) == ke              # the row dump overwrote the staging block: full path, same value
             assert np.array_equal(np.stack(sim.get_species(s)), cols)
+
+
+@pytest.mark.parametrize("solver", [1, 2])
+def test_graph_replay_of_step_pairs_is_bit_identical(solver):
+    """Launch-bound populations replay a captured CUDA graph of two consecutive steps between re-binnings.  The graph
+    contains exactly the launches of the plain path, so 37 steps (odd count, several re-binnings of both species, a
+    second picsp_step call that reuses the graph, a single picsp_push in between that flips the histogram buffers
+    and so invalidates it) must give bit-identical grids, phase space, KE and launch count with and without it."""
+    nm = normalise()
+    numx, n = 64, 30_000
+    runs = []
+    for flags in (0, FLAG_NO_GRAPH):
+        with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, solverType=solver, flags=flags)) as sim:
+            sim.set_sort_period(ION, 11); sim.set_sort_period(ELECTRON, 5)
+            sim.fill_synthetic(ION, n, seed=31, vth=nm["vth_i"])
+            sim.fill_synthetic(ELECTRON, n, seed=32, vth=1.5, xdrift=nm["drift_e"])
+            sim.bootstrap()
+            l0 = sim.kernel_launches()
+            sim.step(21); sim.step(16)
+            launches = sim.kernel_launches() - l0
+            sim.scatterSpecies(ION); sim.scatterSpecies(ELECTRON); sim.computeRho(); sim.solve(); sim.computeEF()
+            sim.pushSpecies(ION); sim.pushSpecies(ELECTRON)          # one step through the per-function calls
+            sim.step(6)
+            runs.append({g: sim.grid(g) for g in GRIDS} | {"pi": np.stack(sim.get_species(ION)), "pe": np.stack(sim.get_species(ELECTRON)),
+                                                            "ke": np.array([sim.computeKE(ION), sim.computeKE(ELECTRON)]),
+                                                            "launches": np.array([launches])})
+    a, b = runs
+    for k in a:
+        assert np.array_equal(a[k], b[k]), f"{k}: graph replay differs from the plain path"
 
 
 def test_clear_density_extension_and_accumulate_default():
