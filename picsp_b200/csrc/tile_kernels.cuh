@@ -597,8 +597,7 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
              const int *__restrict__ nchunks, PushConst c, const double2 *__restrict__ E,
              long long *__restrict__ acc, const int *__restrict__ frac, unsigned int *__restrict__ hist_next,
              unsigned long long *__restrict__ counters, int *__restrict__ err, RebinArgs rb) {
-    constexpr bool REBIN = (MODE == 3 || MODE == 4);
-    static_assert(!REBIN || BULK_PIPE, "the re-binning mover is built on the bulk-copy pipeline");
+    constexpr bool REBIN = (MODE == 3 || MODE == 4);     // built on the bulk-copy pipeline; never launched without it (op_push)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *sE = reinterpret_cast<double2 *>(smem_raw);                               // REPL copies of E_COPY nodes
     unsigned *sLo = reinterpret_cast<unsigned *>(smem_raw + sizeof(double2) * (size_t)REPL * E_COPY);
@@ -803,6 +802,7 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
         }
     } else {
         // per-thread register prefetch: the next particle's loads are in flight while the current one is processed
+        if (REBIN) __trap();               // the host only selects a re-binning launch when BULK_PIPE is on
         const int last = count - 1;
         int k = tid;
         double px, py, pvx = 0, pvy = 0;
