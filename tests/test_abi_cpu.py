@@ -68,3 +68,16 @@ def test_product_never_touches_the_oracle():
                 assert "oracle" not in src.lower(), os.path.join(d, f)
     out = subprocess.run(["ldd", pl.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out and "picsp_ref" not in out
+
+
+@pytest.mark.parametrize("define", ["-DPICSP_BULK_PIPE=0", "-DPICSP_REPL=4"])
+def test_ab_build_switches_still_compile(define, tmp_path):
+    """The A/B switches documented in DESIGN.md section 3.1 (register-prefetch mover, replicated window) must keep
+    compiling for sm_100a, or the recorded sweeps cannot be repeated."""
+    import subprocess
+    from picsp_b200 import build as b
+    out = tmp_path / "abi.o"
+    cmd = [b.NVCC, *b.ARCH, "-O1", "-std=c++17", "-Xcompiler", "-fPIC", "-I", os.path.join(b.ROOT, "include"), define,
+           "-c", os.path.join(b.CSRC, "abi.cu"), "-o", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
