@@ -69,6 +69,8 @@ void check_device_error(picsp_ctx *c) {
     int *h = reinterpret_cast<int *>(c->h_pinned + 8);
     PICSP_CUDA(cudaMemcpyAsync(h, c->d_error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     PICSP_CUDA(cudaStreamSynchronize(c->stream));
+    for (cudaGraphExec_t g : c->retired_graphs) cudaGraphExecDestroy(g);     // nothing is in flight any more
+    c->retired_graphs.clear();
     if (*h) {
         int v = *h;
         PICSP_CUDA(cudaMemsetAsync(c->d_error, 0, sizeof(int), c->stream));
@@ -578,7 +580,8 @@ void picsp_destroy(picsp_ctx *c) {
     cudaFree(c->d_red); cudaFree(c->d_scalars); cudaFree(c->d_sor_status); cudaFree(c->d_sor_progress); cudaFree(c->d_error); cudaFree(c->stage);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto &t : c->timers) for (auto e : t.pool) cudaEventDestroy(e);
-    if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+    for (int g = 0; g < c->step_graph_count; g++) cudaGraphExecDestroy(c->step_graphs[g].exec);
+    for (cudaGraphExec_t g : c->retired_graphs) cudaGraphExecDestroy(g);
     if (c->copy_stream) {
         cudaStreamDestroy(c->copy_stream);
         for (int k = 0; k < 4; k++) cudaEventDestroy(c->ev_ready[k]);
@@ -836,34 +839,47 @@ static picsp_ctx::StepGraphKey step_graph_key(const picsp_ctx *c) {
 
 static void step_pair_graph(picsp_ctx *c) {
     const picsp_ctx::StepGraphKey key = step_graph_key(c);
-    if (c->step_graph && memcmp(&key, &c->step_key, sizeof(key)) == 0) {
-        PICSP_CUDA(cudaGraphLaunch(c->step_graph, c->stream));
-        for (int s = 0; s < 2; s++) {       // the host-side bookkeeping of two steps (the buffer swaps cancel out)
-            c->sp[s].steps_since_sort += 2;
-            c->sp[s].staged_v_valid = false;
+    for (int g = 0; g < c->step_graph_count; g++) {
+        picsp_ctx::StepGraph &sg = c->step_graphs[g];
+        if (memcmp(&key, &sg.key, sizeof(key)) != 0) continue;
+        PICSP_CUDA(cudaGraphLaunch(sg.exec, c->stream));
+        for (int s = 0; s < 2; s++) {       // the host-side bookkeeping of two fused steps (the buffer swaps cancel out)
+            Species &sp = c->sp[s];
+            sp.steps_since_sort += 2;
+            sp.staged_v_valid = false;
+            sp.cnt_valid = true;            // the replayed movers left their per-chunk counts like any other launch
+            sp.acc_valid = true; sp.hist_valid = true;
         }
-        c->launches += c->step_graph_launches;
+        c->launches += sg.launches;
         c->busy[0] = c->busy[1] = true;
         return;
     }
-    if (c->step_graph) { cudaGraphExecDestroy(c->step_graph); c->step_graph = nullptr; }
+    // not cached: record the launches of two ordinary steps (nothing runs yet; the host state advances), instantiate, launch
     const int64_t launches0 = c->launches;
     cudaGraph_t graph = nullptr;
     PICSP_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     try {
-        one_step(c); one_step(c);          // enqueues nothing yet: the launches are recorded; the host state advances
+        one_step(c); one_step(c);
     } catch (...) {
         cudaStreamEndCapture(c->stream, &graph);
         if (graph) cudaGraphDestroy(graph);
         throw;
     }
     PICSP_CUDA(cudaStreamEndCapture(c->stream, &graph));
-    const cudaError_t e = cudaGraphInstantiate(&c->step_graph, graph, 0);
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { c->step_graph = nullptr; throw Error(PICSP_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
-    c->step_graph_launches = c->launches - launches0;
-    c->step_key = key;                     // a pair leaves every pointer of the key where it was
-    PICSP_CUDA(cudaGraphLaunch(c->step_graph, c->stream));
+    if (e != cudaSuccess) throw Error(PICSP_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    int slot;
+    if (c->step_graph_count < picsp_ctx::STEP_GRAPH_CACHE) slot = c->step_graph_count++;
+    else {                                 // evict round robin; the old graph may still be running
+        slot = c->step_graph_next; c->step_graph_next = (slot + 1) % picsp_ctx::STEP_GRAPH_CACHE;
+        c->retired_graphs.push_back(c->step_graphs[slot].exec);
+    }
+    c->step_graphs[slot].key = key;        // a pair leaves every pointer of the key where it was
+    c->step_graphs[slot].exec = exec;
+    c->step_graphs[slot].launches = c->launches - launches0;
+    PICSP_CUDA(cudaGraphLaunch(exec, c->stream));
 }
 
 int picsp_step(picsp_ctx *c, int nsteps) {   // src/main.cpp:481-504

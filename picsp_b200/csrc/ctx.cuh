@@ -149,10 +149,13 @@ struct picsp_ctx {
     // Small populations are launch-bound (~20 launches per step, 0.15-0.35 ms per step): between re-binnings two
     // consecutive steps (the histogram buffers alternate, so a PAIR returns to the same pointers) are captured once
     // into a CUDA graph and replayed.  The key lists everything the captured launches have baked in.
+    // A re-binning swaps buffer sets and chunk tables, so the same few keys recur: the instantiated graphs are cached.
     struct StepGraphKey { const void *ptr[14]; long long n[2]; int chunk[2]; };
-    cudaGraphExec_t step_graph = nullptr;
-    StepGraphKey step_key = {};
-    int64_t step_graph_launches = 0;
+    struct StepGraph { StepGraphKey key; cudaGraphExec_t exec; int64_t launches; };
+    static constexpr int STEP_GRAPH_CACHE = 8;
+    StepGraph step_graphs[STEP_GRAPH_CACHE] = {};
+    int step_graph_count = 0, step_graph_next = 0;
+    std::vector<cudaGraphExec_t> retired_graphs;    // evicted while possibly still in flight: destroyed at the next synchronisation
 
     // multi-GPU
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;

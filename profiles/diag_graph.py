@@ -6,7 +6,7 @@ from picsp_b200 import ELECTRON, ION, Params, Simulation
 from picsp_b200.sim import FLAG_NO_GRAPH
 nm = physical_normalisation()
 for name, cells, n, solver, steps in (("config1 64^2 1e4+1e4 SOR", 64, 10_000, 2, 2000), ("config2 256^2 6.55e6/species spectral", 256, 6_553_600, 1, 400),
-                                      ("256^2 1e6/species spectral", 256, 1_000_000, 1, 1000), ("config3 512^2 5.2e7/species SOR", 512, 52_428_800, 2, 40)):
+                                      ("256^2 1e6/species spectral", 256, 1_000_000, 1, 1000)):
     for rep in range(2):
         for flags, tag in ((FLAG_NO_GRAPH, "plain"), (0, "graph")):
             with Simulation(Params(cells, cells, nm["dx"], nm["dt"], nm["mass_i"], n, n, solverType=solver, flags=flags)) as sim:
