@@ -127,7 +127,7 @@ int picsp_compute_ke(picsp_ctx *ctx, int species, double *ke);        /* compute
 int picsp_delta_phi(picsp_ctx *ctx, double *max_phi, double *phi0);   /* max(phi), phi[0]  src/main.cpp:509-516 */
 int picsp_repush_count(picsp_ctx *ctx, int species, int64_t *n);      /* extra pushes done by the last picsp_push (main.cpp:807-845) */
 int picsp_straggler_count(picsp_ctx *ctx, int species, int64_t *n);   /* particles of the last push/deposit that fell outside their tile window */
-/* Steps between two tile sorts of a species (default: electrons 12, ions 96; <= 0 restores the default). */
+/* Steps between two tile sorts of a species (default: electrons 8, ions 96; <= 0 restores the default). */
 int picsp_set_sort_period(picsp_ctx *ctx, int species, int period);
 
 /* ---- multi-GPU: particles sharded by index range, grid replicated ------------ */

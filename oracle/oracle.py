@@ -26,6 +26,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libpicsp_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libpicsp_ref.so")
 REF_O0_SO = os.path.join(HERE, "_ref", "libpicsp_ref_O0.so")
+REF_GPU_SO = os.path.join(HERE, "_ref", "libpicsp_ref_gpu.so")              # patched reference TU, per-function ABI calls
+REF_GPU_FUSED_SO = os.path.join(HERE, "_ref", "libpicsp_ref_gpu_fused.so")  # same with picsp_step
 REFERENCE_ROOT = os.environ.get("PICSP_REFERENCE_ROOT", "/root/reference")
 
 ION, ELECTRON = 0, 1
@@ -39,6 +41,9 @@ def build(ref: bool | None = None) -> None:
         ref = os.path.isfile(os.path.join(REFERENCE_ROOT, "src", "main.cpp"))
     if ref:
         subprocess.check_call(["make", "-s", "-C", HERE, "ref", f"REFERENCE={REFERENCE_ROOT}"])
+        # the boundary proof (reference TU + INTEGRATION.md patch, linked against the product library)
+        if os.path.isfile(os.path.join(os.path.dirname(HERE), "picsp_b200", "libpicsp_b200.so")):
+            subprocess.check_call(["make", "-s", "-C", HERE, "refgpu", f"REFERENCE={REFERENCE_ROOT}"])
 
 
 def have_reference() -> bool:

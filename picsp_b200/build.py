@@ -48,7 +48,9 @@ def _stale(target):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     cu, cpp = _sources()
+    rebuilt = False
     if force or _stale(LIB):
+        rebuilt = True
         extra = os.environ.get("PICSP_NVCC_DEFINES", "").split()     # e.g. "-DPICSP_CHUNK=4096" for tuning sweeps
         cmd = [NVCC, *ARCH, *COMMON, *extra, "-shared", "-o", LIB, *cu, *cpp, "-lcufft", "-ldl",
                "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
@@ -57,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
     main_cpp = os.path.join(CSRC, "host", "main.cpp")
-    if os.path.isfile(main_cpp) and (force or _stale(HOST_EXE)):
+    if os.path.isfile(main_cpp) and (force or rebuilt or _stale(HOST_EXE)):   # never keep an executable older than the library
         cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", HOST_EXE, main_cpp,
                "-L", PKG, "-lpicsp_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,/usr/local/cuda/lib64"]
         if verbose:

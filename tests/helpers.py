@@ -4,6 +4,7 @@ import os
 import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GRIDS = ("den_i", "den_e", "rho", "phi", "efx", "efy")
 
 # north_star: single-step density, potential and phase space within 1e-12 relative (max-norm)

@@ -81,3 +81,43 @@ def test_ab_build_switches_still_compile(define, tmp_path):
            "-c", os.path.join(b.CSRC, "abi.cu"), "-o", str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+# ---- the boundary proof (oracle/gpu_patch.py + oracle/ref_gpu_harness.cpp) -------------------------------------
+REFERENCE_MAIN = "/root/reference/src/main.cpp"
+
+
+@pytest.mark.skipif(not os.path.isfile(REFERENCE_MAIN), reason="needs the reference tree (build container only)")
+def test_integration_patch_applies_to_the_reference_and_binds_only_the_abi(tmp_path):
+    """INTEGRATION.md section 2 as code: every anchor of the patch is found in the reference's main(), the patched TU
+    compiles against the shims + include/picsp_b200.h, and the only picsp_* symbols it needs are exported by the
+    product library."""
+    from oracle import gpu_patch, oracle as orc
+    patched = gpu_patch.patch(open(REFERENCE_MAIN).read())
+    for call in ("picsp_create", "picsp_species_upload", "picsp_deposit(gpu, 0)", "picsp_compute_rho", "picsp_solve_spectral",
+                 "picsp_solve_sor", "picsp_compute_ef", "picsp_push(gpu, 1)", "picsp_rewind(gpu, 0)", "picsp_step(gpu, 1)",
+                 "picsp_species_download_rows", "picsp_grid_download", "picsp_compute_ke", "picsp_destroy"):
+        assert call in patched, call
+    body = patched[patched.index("int main(int argc"):patched.index("void init(Species")]
+    for gone in ("scatterSpecies(&ions);", "pushSpecies(&ions, efx, efy);", "computeRho(rho, &ions, &electrons);"):
+        assert gone not in body.replace("/* ", "").replace("//", ""), gone
+    orc.build()
+    for so in (orc.REF_GPU_SO, orc.REF_GPU_FUSED_SO):
+        assert os.path.isfile(so)
+        out = subprocess.run(["nm", "-D", "--undefined-only", so], capture_output=True, text=True, check=True).stdout
+        needed = {ln.split()[-1] for ln in out.splitlines() if "picsp_" in ln}
+        assert needed and needed <= set(picsp_b200.abi_symbols()), needed
+    fused = subprocess.run(["nm", "-D", "--undefined-only", orc.REF_GPU_FUSED_SO], capture_output=True, text=True).stdout
+    assert "picsp_step" in fused
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_patched_reference_fails_loudly_without_a_gpu(tmp_path):
+    from oracle import oracle as orc
+    if not os.path.isfile(orc.REF_GPU_SO):
+        pytest.skip("oracle/_ref/libpicsp_ref_gpu.so not built")
+    ini = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "input_ini_shipped.ini")
+    code = ("import ctypes as C, os, sys; os.makedirs('output', exist_ok=True); L = C.CDLL(sys.argv[1]); "
+            "L.picsp_refgpu_main.argtypes = [C.c_char_p]; sys.exit(L.picsp_refgpu_main(os.fsencode(sys.argv[2])))")
+    r = subprocess.run([os.sys.executable, "-c", code, orc.REF_GPU_SO, ini], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr
