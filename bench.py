@@ -13,8 +13,10 @@ replicated and the per-rank partial charge densities are summed with one NCCL al
 One JSON line on stdout (rank 0).  `value` = particle-steps/s with the state resident in
 HBM, timed with CUDA events on the library's stream (max over ranks).  `e2e` = the same
 metric through the C ABI with HOST buffers: upload of the particle state from pinned host
-memory, one dump period (50 steps, the reference's diagnostic cadence, main.cpp:507) and the
-download of everything the reference dumps (phase space, den, phi).  `roofline` is for the
+memory, then --e2e-periods dump periods of 50 steps (the reference's diagnostic cadence,
+main.cpp:507), each followed by the dump of everything the reference writes (phase space of
+both species, den.i, den.e, phi, KE) through picsp_dump_begin / picsp_dump_wait, i.e. copied
+out while the next period steps; the timed region ends when the last dump has landed.  `roofline` is for the
 dominant kernel (the mover fused with the next step's deposit): 64 algorithmic bytes per
 particle-step.  `cpu_baseline` / `--impl reference` time the UNMODIFIED reference
 translation unit (oracle/_ref) on one host core (the reference is single-threaded).
@@ -109,8 +111,21 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the UNMODIFIED reference TU on one host core
 # ------------------------------------------------------------------------------------------
+def synthetic_state(n, seed, xl, vth, xdrift):
+    """The bench workload's particle distribution (uniform positions, v = vth*sqrt(2)*(r1+r2+r3-1.5), +-xdrift
+    alternating in x: what picsp_species_fill_synthetic produces on the device), drawn with numpy for the CPU arm."""
+    rng = np.random.default_rng(seed)
+    x, y = rng.random(n) * xl, rng.random(n) * xl
+    sgn = np.where(np.arange(n) & 1, -1.0, 1.0)
+    vx = vth * np.sqrt(2.0) * (rng.random(n) + rng.random(n) + rng.random(n) - 1.5) + sgn * xdrift
+    vy = vth * np.sqrt(2.0) * (rng.random(n) + rng.random(n) + rng.random(n) - 1.5)
+    return x, y, vx, vy
+
+
 def run_reference_cpu(cells, n_per_species, steps, warmup):
-    """Times the reference's own loop body (main.cpp:481-504) on a bounded sample of the workload.
+    """Times the reference's own loop body (main.cpp:481-504) on a bounded sample of the workload: the same grid,
+    the same particle distribution (two-stream electrons + cold ions, uniform in the box), fewer particles
+    (throughput is per particle).
 
     Returns (value, info).  value = particle-steps/s over deposit + rho + EF + push, i.e. the
     reference's own functions; the Poisson solve is timed but reported separately because
@@ -122,12 +137,14 @@ def run_reference_cpu(cells, n_per_species, steps, warmup):
     nm = physical_normalisation()
     kind = "reference" if orc.have_reference() else "port"
     t0 = time.perf_counter()
+    xl = cells * nm["dx"]
+    ions = synthetic_state(n_per_species, 1, xl, nm["vth_i"], 0.0)
+    electrons = synthetic_state(n_per_species, 2, xl, nm["vth_e"], nm["drift_e"])
     if kind == "reference":
         r = orc.Reference(cells, cells, nm["dx"], nm["dt"], nm["mass_i"], n_per_species, n_per_species,
                           vth_i=nm["vth_i"], vth_e=nm["vth_e"], solver=1)
         r.L.picsp_ref_set_fft_mode(3)
-        r.seed(0)
-        r.init_both(1)
+        r.set_species(0, *ions); r.set_species(1, *electrons)
         r.bootstrap()
         if warmup:
             r.step(warmup, with_dead_vel=True)
@@ -139,7 +156,7 @@ def run_reference_cpu(cells, n_per_species, steps, warmup):
         o = orc.Oracle(cells, cells, nm["dx"], nm["dt"], nm["mass_i"], n_per_species, n_per_species,
                        vth_i=nm["vth_i"], vth_e=nm["vth_e"], solver=1)
         orc.Oracle.lib().oracle_set_fft_mode(3)
-        o.seed(0); o.init(0, 1); o.init(1, 1)
+        o.set_species(0, *ions); o.set_species(1, *electrons)
         o.bootstrap()
         ph = dict(deposit=0.0, dead_vel_deposit=0.0, rho=0.0, solve=0.0, ef=0.0, push=0.0)
 
@@ -157,13 +174,15 @@ def run_reference_cpu(cells, n_per_species, steps, warmup):
     value = psteps / path_s
     info = {
         "value": value, "unit": UNIT, "cores": 1, "kind": kind,
-        "sample": (f"{cells}x{cells} cells, {n_per_species} particles/species (Maxwellian, reference loader seed 0), "
-                   f"{steps} steps after {warmup} warm-up, 1 of {os.cpu_count()} host cores (reference is single-threaded), "
-                   f"g++ -O2 (the reference's own makefile uses -O0, ~3x slower); value counts deposit+rho+EF+push; "
-                   f"per-step seconds: deposit {ph['deposit'] / steps:.3f}, push {ph['push'] / steps:.3f}, "
+        "sample": (f"bounded sample of the workload: same {cells}x{cells}-cell grid, same particle distribution (two-stream "
+                   f"electrons + cold ions, uniform positions), {n_per_species} particles/species instead of the full count "
+                   f"(throughput is per particle); {steps} steps after {warmup} warm-up, 1 of {os.cpu_count()} host cores "
+                   f"(the reference is single-threaded), g++ -O2 (the reference's own makefile uses -O0, ~3x slower); value "
+                   f"counts deposit+rho+EF+push; per-step seconds: deposit {ph['deposit'] / steps:.3f}, push {ph['push'] / steps:.3f}, "
                    f"rho+EF {(ph['rho'] + ph['ef']) / steps:.4f}; excluded: Poisson solve {ph['solve'] / steps:.3f} s/step "
                    f"(shim FFT, not FFTW) and the reference's dead velocity deposit {ph['dead_vel_deposit'] / steps:.3f} s/step"),
         "ms_per_step": 1e3 * path_s / steps, "wall_s": time.perf_counter() - t0,
+        "sample_particles_per_species": int(n_per_species),
     }
     return value, info
 
@@ -176,7 +195,10 @@ def main_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, None),
+        "config": dict(workload_config(args, None),
+                       sample=f"each step is a bounded sample of this workload: {info['sample_particles_per_species']} particles per species "
+                              f"of the same distribution on the same grid, on 1 host core (see cpu_baseline.sample)",
+                       sample_particles_total=2 * info["sample_particles_per_species"]),
         "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -185,10 +207,14 @@ def main_reference(args, rank):
 
 
 def workload_config(args, n_local):
+    load = ("synthetic two-stream electrons + cold ions uniform in the box (bench-only device loader)" if args.load == "synthetic" else
+            "the reference's own loadType-2 two-stream load (main.cpp:597-615, host loader picsp_host_loader_fill): every particle "
+            "on the domain diagonal")
     cfg = {
-        "workload": (f"two-stream electrons + cold ions, {args.cells}x{args.cells} cells periodic "
+        "workload": (f"{load}, {args.cells}x{args.cells} cells periodic "
                      f"({args.cells + 1}^2 nodes), spectral solver, {args.particles:.3g} particles total "
                      f"({args.particles // 2} per species), BASELINE.json configs[3]"),
+        "load": args.load,
         "cells": args.cells, "particles_total": int(args.particles), "solver": "spectral (cuFFT D2Z/Z2D)",
         "sharding": f"particles by index range over {args.gpus} rank(s), grid replicated, 1 NCCL all-reduce of rho per step",
         "l2_policy": "inputs exceed L2 (particle state per rank >> 126 MB); no explicit flush",
@@ -231,8 +257,26 @@ def main_ours(args, rank, world, local_rank):
     n_local = hi - lo
     sim = Simulation(Params(args.cells, args.cells, nm["dx"], nm["dt"], nm["mass_i"], n_species, n_species,
                             solverType=1, device=local_rank, capacity=(n_local, n_local), flags=args.flags))
-    sim.fill_synthetic(ION, n_local, first_index=lo, seed=1, vth=nm["vth_i"], xdrift=0.0)
-    sim.fill_synthetic(ELECTRON, n_local, first_index=lo, seed=2, vth=nm["vth_e"], xdrift=nm["drift_e"])
+    if args.load == "synthetic":
+        sim.fill_synthetic(ION, n_local, first_index=lo, seed=1, vth=nm["vth_i"], xdrift=0.0)
+        sim.fill_synthetic(ELECTRON, n_local, first_index=lo, seed=2, vth=nm["vth_e"], xdrift=nm["drift_e"])
+    else:
+        # the reference's loadType 2 through the product's host loader: a sequential recurrence over ALL particles
+        # (ions first, the stale x carried into the electrons); every rank generates it and keeps its range
+        from picsp_b200 import host
+        from picsp_b200.lib import CRunConfig
+        cfg = CRunConfig()
+        cfg.numxCells = cfg.numyCells = args.cells
+        cfg.nParticlesI = cfg.nParticlesE = n_species
+        cfg.loadType, cfg.solverType = 2, 1
+        cfg.stepSize, cfg.timeStep = nm["dx"], nm["dt"]
+        cfg.vthI, cfg.vthE, cfg.driftI, cfg.driftE = nm["vth_i"], nm["vth_e"], 0.0, nm["drift_e"]
+        t_load = time.perf_counter()
+        loaded = host.load_species(cfg, seed=0)
+        for s_ in (ION, ELECTRON):
+            sim.set_species(s_, *(a[lo:hi] for a in loaded[s_]))
+        del loaded
+        print(f"[bench] reference loadType-2 load generated and uploaded in {time.perf_counter() - t_load:.1f} s", file=sys.stderr)
     if world > 1:
         uid = [Simulation.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -241,6 +285,10 @@ def main_ours(args, rank, world, local_rank):
         sim.set_sort_period(ELECTRON, args.sort_period_e)
     if args.sort_period_i > 0:
         sim.set_sort_period(ION, args.sort_period_i)
+    if args.cell_period_e >= 0:
+        sim.set_cell_sort_period(ELECTRON, args.cell_period_e)
+    if args.cell_period_i >= 0:
+        sim.set_cell_sort_period(ION, args.cell_period_i)
     sim.bootstrap()
     sim.profile_enable(True)
     sim.step(args.warmup)
@@ -282,10 +330,19 @@ def main_ours(args, rank, world, local_rank):
                 "share_of_step": push_ms / prof["step"][0] if prof["step"][0] else None}
     phases_ms = {k: v[0] / args.steps for k, v in prof.items()}
 
+    # ---- parity probe: state after bootstrap + warm-up + timed steps.  The device loader is keyed by the GLOBAL
+    # particle index, so the state is the same for every rank count up to summation order: the N = 1/2/4/8 lines can be
+    # compared with each other (agreement expected to ~1e-12 relative; chaotic growth over these few steps is negligible)
+    rho_g, phi_g = sim.grid("rho"), sim.grid("phi")
+    parity_probe = {"steps_total": args.warmup + args.steps, "sum_abs_rho": float(np.abs(rho_g).sum()),
+                    "l2_phi": float(np.sqrt((phi_g * phi_g).sum())), "ke_i": sim.computeKE(ION), "ke_e": sim.computeKE(ELECTRON),
+                    "tolerance": "lines of different rank counts agree to 1e-10 relative (summation order of the partial densities "
+                                 "and of the KE partial sums only)"}
+
     # ---- end to end through the C ABI with host buffers ---------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(sim, args, n_local, barrier, max_over_ranks, torch)
+        e2e = run_e2e(sim, args, n_local, barrier, max_over_ranks, torch, rank)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -302,60 +359,77 @@ def main_ours(args, rank, world, local_rank):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_local),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "parity_probe": parity_probe,
             "clocks": clocks, "phases_ms_per_step": phases_ms, "wall_ms_per_step": 1e3 * t_wall / args.steps,
         }
         emit(line)
     return 0
 
 
-def run_e2e(sim, args, n_local, barrier, max_over_ranks, torch):
-    """Upload the particle state from pinned host memory, run one dump period, read back what the
-    reference dumps (phase space of both species, den.i, den.e, phi) — all through the C ABI."""
+def run_e2e(sim, args, n_local, barrier, max_over_ranks, torch, rank=0):
+    """Upload the particle state from pinned host memory, then run --e2e-periods dump periods: 50 steps followed by
+    the dump of what the reference writes every 50 steps (phase space of both species as [n][4] rows, den.i, den.e,
+    phi, the two kinetic energies; main.cpp:507-527), all through the C ABI.  A dump is snapshot on the device and
+    copied out on a second stream while the next period steps (picsp_dump_begin / picsp_dump_wait); the timed region
+    ends when the last dump has landed in host memory.  With N ranks den.i / den.e are reduced to rank 0."""
     import ctypes as C
     from picsp_b200.lib import check
     dp = C.POINTER(C.c_double)
     nn = sim.nix * sim.niy
     pinned = True
     try:
-        host = [[torch.empty(n_local, dtype=torch.float64, pin_memory=True) for _ in range(4)] for _ in range(2)]
+        # one page-locked block of 4*n doubles per species: four arrays for the upload, [n][4] rows for the dumps
+        blocks = [torch.empty(4 * n_local, dtype=torch.float64, pin_memory=True) for _ in range(2)]
         grids = [torch.empty(nn, dtype=torch.float64, pin_memory=True) for _ in range(3)]
+        ke = torch.empty(2, dtype=torch.float64, pin_memory=True)
     except RuntimeError:
         pinned = False
-        host = [[torch.empty(n_local, dtype=torch.float64) for _ in range(4)] for _ in range(2)]
+        blocks = [torch.empty(4 * n_local, dtype=torch.float64) for _ in range(2)]
         grids = [torch.empty(nn, dtype=torch.float64) for _ in range(3)]
+        ke = torch.empty(2, dtype=torch.float64)
     ptr = lambda t: C.cast(t.data_ptr(), dp)  # noqa: E731
+    quarters = [[b[k * n_local:(k + 1) * n_local] for k in range(4)] for b in blocks]
     for s in range(2):   # untimed: seed the host buffers with the current device state
-        check(sim.L.picsp_species_download(sim.ctx, s, *(ptr(t) for t in host[s])))
+        check(sim.L.picsp_species_download(sim.ctx, s, *(ptr(t) for t in quarters[s])))
         sim.computeKE(s)   # untimed: NCCL sets up the small-message path of the KE all-reduce lazily on its first call (one-off, ~1 s at 8 ranks)
-    steps = args.e2e_steps
+    steps, periods = args.e2e_steps, args.e2e_periods
+    root = rank == 0
+    null = dp()
     barrier()
     t0 = time.perf_counter()
     for s in range(2):
-        check(sim.L.picsp_species_upload(sim.ctx, s, *(ptr(t) for t in host[s]), n_local))
+        check(sim.L.picsp_species_upload(sim.ctx, s, *(ptr(t) for t in quarters[s]), n_local))
     t1 = time.perf_counter()
-    check(sim.L.picsp_step(sim.ctx, steps))
-    sim.sync()                 # only to attribute the time below; the downloads would wait for the steps anyway
+    wait_s = 0.0
+    for p in range(periods):
+        check(sim.L.picsp_step(sim.ctx, steps))            # enqueued; returns at once
+        tw = time.perf_counter()
+        check(sim.L.picsp_dump_wait(sim.ctx))              # the previous dump must have landed before its buffers are reused
+        wait_s += time.perf_counter() - tw
+        check(sim.L.picsp_dump_begin(sim.ctx, ptr(blocks[0]), ptr(blocks[1]), ptr(grids[0]) if root else null,
+                                     ptr(grids[1]) if root else null, ptr(grids[2]) if root else null, ptr(ke)))
     t2 = time.perf_counter()
-    for s in range(2):
-        check(sim.L.picsp_species_download(sim.ctx, s, *(ptr(t) for t in host[s])))
-    t2b = time.perf_counter()
-    for gid, t in zip((0, 1, 3), grids):
-        check(sim.L.picsp_grid_download(sim.ctx, gid, ptr(t)))
-    ke = [sim.computeKE(0), sim.computeKE(1)]
+    check(sim.L.picsp_dump_wait(sim.ctx))
+    sim.sync()
     t3 = time.perf_counter()
     barrier()
     dt = max_over_ranks(time.perf_counter() - t0)
-    slowest = {"upload": max_over_ranks(t1 - t0), "steps": max_over_ranks(t2 - t1),
-               "download": max_over_ranks(t2b - t2), "grids_and_ke": max_over_ranks(t3 - t2b)}
+    upload = max_over_ranks(t1 - t0)
+    steady = max_over_ranks(t3 - t1)
     h2d = 2 * 4 * 8 * n_local
-    d2h = 2 * 4 * 8 * n_local + 3 * 8 * nn + 16
-    return {"value": float(args.particles) * steps / dt, "unit": UNIT,
-            "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps,
-            "steps_per_call": steps, "seconds": dt, "pinned_host_memory": pinned,
-            "seconds_rank0": {"upload": t1 - t0, "steps": t2 - t1, "download_and_diagnostics": t3 - t2},
-            "seconds_slowest_rank": slowest,
-            "what": "picsp_species_upload x2 -> picsp_step(50) -> picsp_species_download x2 + den.i, den.e, phi + KE "
-                    "(bytes are per rank, amortised over the dump period)", "ke_finite": bool(np.isfinite(ke).all())}
+    d2h = periods * (2 * 4 * 8 * n_local + (3 * 8 * nn if root else 0) + 16)
+    total_steps = steps * periods
+    return {"value": float(args.particles) * total_steps / dt, "unit": UNIT,
+            "h2d_bytes_per_step": h2d / total_steps, "d2h_bytes_per_step": d2h / total_steps,
+            "steps_per_dump": steps, "dump_periods": periods, "seconds": dt, "pinned_host_memory": pinned,
+            "upload_seconds": upload, "steady_state_seconds": steady,
+            "steady_state_value": float(args.particles) * total_steps / steady,
+            "seconds_rank0": {"upload": t1 - t0, "periods_enqueue_and_dump_waits": t2 - t1, "waiting_for_dumps": wait_s,
+                              "last_dump_drain": t3 - t2},
+            "what": f"picsp_species_upload x2 (one-off, inside the timed region) -> {periods} x [picsp_step({steps}) -> picsp_dump_begin "
+                    "(rows of both species, den.i, den.e, phi, KE; copied out while the next period steps)] -> picsp_dump_wait; "
+                    "bytes are per rank, amortised over all steps; steady_state_* excludes the one-off upload",
+            "ke_finite": bool(np.isfinite(ke.numpy()).all())}
 
 
 _REAL_STDOUT = None
@@ -385,7 +459,12 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--cells", type=int, default=1024)
     ap.add_argument("--particles", type=float, default=1e9, help="total particles (both species, all ranks)")
-    ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--e2e-steps", type=int, default=50, help="steps per dump period (the reference dumps every 50 steps, main.cpp:507)")
+    ap.add_argument("--e2e-periods", type=int, default=10, help="dump periods of the end-to-end measurement")
+    ap.add_argument("--load", choices=["synthetic", "ref2"], default="synthetic",
+                    help="particle load: bench-only device loader (uniform two-stream) or the reference's loadType 2 (diagonal) from the host loader")
+    ap.add_argument("--cell-period-e", type=int, default=-1, help="steps between electron cell orderings (-1: library default, 0: never)")
+    ap.add_argument("--cell-period-i", type=int, default=-1, help="steps between ion cell orderings (-1: library default, 0: never)")
     ap.add_argument("--sort-period-e", type=int, default=0, help="steps between electron tile sorts (0: library default)")
     ap.add_argument("--sort-period-i", type=int, default=0, help="steps between ion tile sorts (0: library default)")
     ap.add_argument("--flags", type=int, default=0, help="PICSP_FLAG_* bits for A/B runs (16: stand-alone re-sort instead of the re-binning mover)")

@@ -24,6 +24,7 @@
 #ifndef PICSP_B200_H
 #define PICSP_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -108,7 +109,26 @@ int picsp_species_count(picsp_ctx *ctx, int species, int64_t *n);
 /* Same, [n][4] rows of {x, y, vx, vy}: the layout writeSpecies dumps (src/main.cpp:1152-1162). */
 int picsp_species_download_rows(picsp_ctx *ctx, int species, double *rows);
 int picsp_grid_upload(picsp_ctx *ctx, int which, const double *host);
+/* With a communicator attached, PICSP_DEN_I / PICSP_DEN_E are the SUM over ranks of the per-rank partial densities
+ * (each rank accumulates the deposit of its own particles): the call is then a collective, every rank must make it and
+ * every rank receives the global density.  rho, phi, efx, efy are global on every rank already. */
 int picsp_grid_download(picsp_ctx *ctx, int which, double *host);
+
+/* Asynchronous dump: everything the reference writes at a diagnostics step (writeSpecies x2, writePot, computeKE x2;
+ * src/main.cpp:507-527) without stalling the time loop.  picsp_dump_begin snapshots, stream-ordered after the steps
+ * enqueued so far, the phase space of both species as [n][4] rows {x, y, vx, vy} in list order, den.i, den.e, phi and
+ * the two kinetic energies on the device, and starts copying them into the caller's buffers on a second stream; it
+ * returns at once, and steps enqueued afterwards run concurrently with the copies.  The buffers must stay valid (and
+ * unread) until picsp_dump_wait returns; pass page-locked memory (picsp_host_alloc) or the copies will block the call.
+ * Any pointer may be NULL (that item is skipped).  With a communicator attached both calls are collectives: den.i /
+ * den.e are the SUM over ranks and arrive on rank 0 only (other ranks may pass NULL), phi is written on rank 0 only,
+ * ke2 is the global value on every rank, rows are this rank's particles.  If the device has no room for the snapshot
+ * (4*capacity doubles per species) the dump is done synchronously inside picsp_dump_begin. */
+int picsp_dump_begin(picsp_ctx *ctx, double *rows_i, double *rows_e, double *den_i, double *den_e, double *phi, double *ke2);
+int picsp_dump_wait(picsp_ctx *ctx);
+/* Page-locked host memory for the asynchronous paths (NULL on failure). */
+void *picsp_host_alloc(size_t bytes);
+void picsp_host_free(void *p);
 
 /* ---- the hot path, one entry per reference function -------------------------- */
 int picsp_deposit(picsp_ctx *ctx, int species);     /* scatterSpecies            src/main.cpp:684-721 (+scatter :655-668) */
@@ -129,6 +149,10 @@ int picsp_repush_count(picsp_ctx *ctx, int species, int64_t *n);      /* extra p
 int picsp_straggler_count(picsp_ctx *ctx, int species, int64_t *n);   /* particles of the last push/deposit that fell outside their tile window */
 /* Steps between two tile sorts of a species (default: electrons 8, ions 96; <= 0 restores the default). */
 int picsp_set_sort_period(picsp_ctx *ctx, int species, int period);
+/* Steps between two orderings of the particles by CELL inside their tile (makes the mover's field gathers broadcast and
+ * its deposits warp-aggregated; storage order only, results are bit-identical).  0 = never; default: ions 64,
+ * electrons 0 (thermal electrons lose the order within 2-3 steps); < 0 restores the default. */
+int picsp_set_cell_sort_period(picsp_ctx *ctx, int species, int period);
 
 /* ---- multi-GPU: particles sharded by index range, grid replicated ------------ */
 /* One communicator per rank; id is an NCCL unique id (128 bytes) created by rank 0

@@ -74,6 +74,7 @@ void check_device_error(picsp_ctx *c) {
     if (*h) {
         int v = *h;
         PICSP_CUDA(cudaMemsetAsync(c->d_error, 0, sizeof(int), c->stream));
+        *c->h_error_mapped = 0;
         if (v & ERR_BIT_REBIN)
             throw Error(PICSP_ERR_STATE, "internal: a re-binning mover overflowed a bin (histogram and bin function disagree)");
         if (v & ERR_BIT_RUNAWAY)
@@ -188,6 +189,37 @@ void op_sort(picsp_ctx *c, int s) {
     sort_finish(c, s);
 }
 
+// Cell order inside every bin (stand-alone; see tile_kernels.cuh).  Particles stay in their bin's range; the result is
+// left in the second buffer set, which becomes the live one.
+void op_cell_sort(picsp_ctx *c, int s) {
+    PhaseScope ph(c, PICSP_PHASE_SORT);
+    Species &sp = c->sp[s];
+    if (!sp.sorted || sp.n <= 0 || !sp.x2) return;
+    const int grid = mover_grid(sp);
+    if (sp.cell_cnt_chunks < grid) {
+        cudaFree(sp.cell_cnt); sp.cell_cnt = nullptr;
+        dalloc(&sp.cell_cnt, (size_t)grid * CELLKEYS);
+        sp.cell_cnt_chunks = grid;
+    }
+    if (!sp.tile_chunk0) dalloc(&sp.tile_chunk0, (size_t)sp.ntiles);
+    if (!c->cellsort_opted_in) {
+        PICSP_CUDA(cudaFuncSetAttribute(k_cell_permute, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CELLSORT_SMEM_BYTES));
+        c->cellsort_opted_in = true;
+    }
+    const PushConst pc = push_const(c, s);
+    PICSP_LAUNCH(c, k_cell_count, grid, 256, 0, sp.x, sp.y, (const Chunk *)sp.chunks, sp.nchunks, pc, sp.cell_cnt, sp.tile_chunk0);
+    PICSP_LAUNCH(c, k_cell_scan, sp.ntiles, CELLKEYS, 0, sp.tile_off, sp.tile_chunk0, sp.chunk, sp.cell_cnt);
+    PICSP_LAUNCH(c, k_cell_permute, grid, SORT2_THREADS, CELLSORT_SMEM_BYTES, sp.x, sp.y, sp.vx, sp.vy,
+                 sp.has_perm ? sp.id : (const uint32_t *)nullptr, (const Chunk *)sp.chunks, sp.nchunks, pc, sp.tile_off, sp.cell_cnt,
+                 sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2);
+    std::swap(sp.x, sp.x2); std::swap(sp.y, sp.y2); std::swap(sp.vx, sp.vx2); std::swap(sp.vy, sp.vy2);
+    std::swap(sp.id, sp.id2);
+    sp.has_perm = true;
+    sp.cnt_valid = false;          // the per-chunk neighbour counts described the old order
+    sp.staged_v_valid = false;
+    sp.steps_since_cellsort = 0;
+}
+
 int mover_grid(const Species &sp) {
     long long b = sp.n / sp.chunk + sp.ntiles + 1;   // upper bound on the number of chunks
     return (int)std::max<long long>(1, std::min<long long>(b, sp.max_chunks));
@@ -296,7 +328,8 @@ void op_grid_phase(picsp_ctx *c) {
             sp.acc_valid = false;
         }
         const int clear = (c->prm.flags & PICSP_FLAG_CLEAR_DENSITY) ? 1 : 0;
-        PICSP_LAUNCH(c, k_grid_phase, blocks_for(g.nn, 256, c->num_sms * 32), 256, 0, gs[0], gs[1], c->rho, g.nix, g.niy, clear);   // one node per thread up to 1.2M nodes: latency-bound otherwise
+        PICSP_LAUNCH(c, k_grid_phase, blocks_for(g.nn, 256, c->num_sms * 32), 256, 0, gs[0], gs[1], c->rho, g.nix, g.niy, clear,
+                     c->d_error, c->h_error_mapped);   // one node per thread up to 1.2M nodes: latency-bound otherwise
     }
     if (c->comm) op_allreduce_rho(c);    // the folds are linear: folding the partial rho first commutes with the sum
 }
@@ -365,6 +398,8 @@ void op_push(picsp_ctx *c, int s) {
     // the first binning of an arbitrary load, and the unfused mover, use the stand-alone sort
     const bool rebin_in_mover = due && fuse && BULK_PIPE && sp.n > 0 && !(c->prm.flags & PICSP_FLAG_SEPARATE_SORT);
     if (tile && (!sp.sorted || (due && !rebin_in_mover))) op_sort(c, s);
+    // cell order inside the bins: a pass of its own on the steps where no re-binning is due
+    if (tile && sp.sorted && !due && sp.cell_period > 0 && sp.steps_since_cellsort >= sp.cell_period && BULK_PIPE) op_cell_sort(c, s);
     if (rebin_in_mover) { PhaseScope phs(c, PICSP_PHASE_SORT); sort_prepare(c, s); }
     if (fuse || tile) ensure_hist(c, s);   // histogram of the positions about to be pushed -> bound for acc
     if (fuse) compute_frac(c, s);
@@ -403,6 +438,7 @@ void op_push(picsp_ctx *c, int s) {
     }
     sp.acc_valid = fuse;
     sp.steps_since_sort++;
+    sp.steps_since_cellsort++;
 }
 
 void op_rewind(picsp_ctx *c, int s) {
@@ -426,6 +462,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
@@ -439,10 +476,11 @@ NcclApi &nccl() {
         api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
         api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
         api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+        api.Reduce = (decltype(api.Reduce))dlsym(api.handle, "ncclReduce");
         api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
         api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
     });
-    PICSP_REQUIRE(api.handle && api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy,
+    PICSP_REQUIRE(api.handle && api.GetUniqueId && api.CommInitRank && api.AllReduce && api.Reduce && api.CommDestroy,
                   PICSP_ERR_NCCL, "libnccl.so.2 could not be loaded");
     return api;
 }
@@ -515,6 +553,8 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
             dalloc(&sp.hist, (size_t)g.ntx * g.nty); dalloc(&sp.hist_next, (size_t)g.ntx * g.nty);
             dalloc(&sp.counters, 2);
             sp.sort_period = (s == 0) ? 96 : 8;     // steps between re-binnings (ions barely move; electrons: profiles/r01_sweeps.md)
+            sp.cell_period = (s == 0) ? 64 : 0;     // steps between cell orderings inside the bins (thermal electrons lose the order in 2-3 steps)
+            sp.steps_since_cellsort = sp.cell_period;   // the first push after a load orders it
             sp.ntiles = g.ntx * g.nty;
             sp.max_chunks = sp.cap / 512 + (long long)g.ntx * g.nty + 1;   // 512 = smallest chunk pick_chunk() returns
             dalloc(&sp.tile_off, (size_t)g.ntx * g.nty + 1);
@@ -540,6 +580,8 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
         PICSP_CUDA(cudaMemsetAsync(c->d_sor_status, 0, sizeof(long long) * 2, c->stream));
         PICSP_CUDA(cudaMemsetAsync(c->d_error, 0, sizeof(int), c->stream));
         PICSP_CUDA(cudaMallocHost((void **)&c->h_pinned, 64 * sizeof(double)));
+        PICSP_CUDA(cudaHostAlloc((void **)&c->h_error_mapped, sizeof(int), cudaHostAllocMapped));   // same address on the device (UVA)
+        *c->h_error_mapped = 0;
 
         if (p->solverType == PICSP_SOLVER_SPECTRAL) {
             const size_t nk = (size_t)g.nix * (g.niy / 2 + 1);
@@ -566,6 +608,7 @@ void picsp_destroy(picsp_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->prm.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->comm) { try { nccl().CommDestroy(c->comm); } catch (...) {} }
     if (c->have_plans) { cufftDestroy(c->plan_fwd); cufftDestroy(c->plan_inv); }
     for (int s = 0; s < 2; s++) {
@@ -575,10 +618,15 @@ void picsp_destroy(picsp_ctx *c) {
         cudaFree(sp.x2); cudaFree(sp.id2);
         cudaFree(sp.tile_off); cudaFree(sp.chunks); cudaFree(sp.nchunks); cudaFree(sp.cursor);
         cudaFree(sp.chunks2); cudaFree(sp.nchunks2); cudaFree(sp.chunk_cnt); cudaFree(sp.chunk_base);
+        cudaFree(sp.cell_cnt); cudaFree(sp.tile_chunk0);
     }
     cudaFree(c->rho); cudaFree(c->phi); cudaFree(c->E_alloc); cudaFree(c->rhok); cudaFree(c->phik);
     cudaFree(c->d_red); cudaFree(c->d_scalars); cudaFree(c->d_sor_status); cudaFree(c->d_sor_progress); cudaFree(c->d_error); cudaFree(c->stage);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_error_mapped) cudaFreeHost(c->h_error_mapped);
+    cudaFree(c->snap_rows[0]); cudaFree(c->snap_rows[1]); cudaFree(c->snap_grids); cudaFree(c->snap_ke);
+    if (c->ev_snap) cudaEventDestroy(c->ev_snap);
+    if (c->ev_dump_done) cudaEventDestroy(c->ev_dump_done);
     for (auto &t : c->timers) for (auto e : t.pool) cudaEventDestroy(e);
     for (int g = 0; g < c->step_graph_count; g++) cudaGraphExecDestroy(c->step_graphs[g].exec);
     for (cudaGraphExec_t g : c->retired_graphs) cudaGraphExecDestroy(g);
@@ -630,6 +678,7 @@ int picsp_species_upload(picsp_ctx *c, int s, const double *x, const double *y, 
     if (sp.acc_valid) PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
     sp.n = n; sp.hist_valid = false; sp.acc_valid = false;
     sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0; sp.cnt_valid = false; sp.staged_v_valid = false;
+    sp.steps_since_cellsort = sp.cell_period;
     if (tiled(c) && n > 0) op_sort(c, s);
     c->busy[s] = true; c->busy[1 - s] = other_busy;           // what was enqueued here touches species s only
     PICSP_API_END
@@ -758,6 +807,13 @@ int picsp_grid_download(picsp_ctx *c, int which, double *host) {
         PICSP_LAUNCH(c, k_ef_get_component, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, c->E, c->stage, g.nn,
                      which == PICSP_EFY ? 1 : 0);
         src = c->stage;
+    } else if (c->comm && (which == PICSP_DEN_I || which == PICSP_DEN_E)) {
+        // Sharded run: every rank accumulates the density of ITS particles only (deposit and fold are linear, so the
+        // per-rank accumulation commutes with the sum).  What the reference dumps is the sum over ranks:
+        // the download is a collective and every rank receives the global density.
+        ensure_stage(c, g.nn);
+        PICSP_NCCL(nccl().AllReduce(src, c->stage, (size_t)g.nn, ncclFloat64, ncclSum, c->comm, c->stream));
+        src = c->stage;
     }
     PICSP_CUDA(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     check_device_error(c);
@@ -813,13 +869,14 @@ static void one_step(picsp_ctx *c) {
 constexpr long long STEP_GRAPH_MAX_PARTICLES = 1ll << 26;   // above this a step is >= 1 ms of kernels and the launches hide behind them
 
 static bool step_graph_eligible(const picsp_ctx *c) {
-    if (c->profiling || c->comm || (c->prm.flags & (PICSP_FLAG_NO_GRAPH | PICSP_FLAG_NO_FUSE | PICSP_FLAG_NO_SORT))) return false;
+    if (c->profiling || c->comm || c->graphs_disabled || (c->prm.flags & (PICSP_FLAG_NO_GRAPH | PICSP_FLAG_NO_FUSE | PICSP_FLAG_NO_SORT))) return false;
     if (c->sp[0].n + c->sp[1].n > STEP_GRAPH_MAX_PARTICLES) return false;
     for (int s = 0; s < 2; s++) {
         const Species &sp = c->sp[s];
         // steady state of the fused loop, and no re-binning due in either of the two steps
         if (!sp.sorted || !sp.acc_valid || !sp.hist_valid || sp.n <= 0 || !sp.chunk_cnt) return false;
         if (sp.steps_since_sort + 1 >= sp.sort_period) return false;
+        if (sp.cell_period > 0 && sp.steps_since_cellsort + 1 >= sp.cell_period) return false;
     }
     return c->smem_opted_in;    // the per-function attributes must not be set during a capture
 }
@@ -846,6 +903,7 @@ static void step_pair_graph(picsp_ctx *c) {
         for (int s = 0; s < 2; s++) {       // the host-side bookkeeping of two fused steps (the buffer swaps cancel out)
             Species &sp = c->sp[s];
             sp.steps_since_sort += 2;
+            sp.steps_since_cellsort += 2;
             sp.staged_v_valid = false;
             sp.cnt_valid = true;            // the replayed movers left their per-chunk counts like any other launch
             sp.acc_valid = true; sp.hist_valid = true;
@@ -854,22 +912,37 @@ static void step_pair_graph(picsp_ctx *c) {
         c->busy[0] = c->busy[1] = true;
         return;
     }
-    // not cached: record the launches of two ordinary steps (nothing runs yet; the host state advances), instantiate, launch
+    // not cached: record the launches of two ordinary steps (nothing runs yet; the host state advances), instantiate, launch.
+    // Recording advances the host-side bookkeeping (buffer swaps, validity flags, counters) of a device that has not
+    // run anything yet: if the capture or the instantiation fails, that bookkeeping is put back, graphs are switched
+    // off for this context and the two steps are enqueued the plain way.
     const int64_t launches0 = c->launches;
+    const Species saved_sp[2] = {c->sp[0], c->sp[1]};
+    const bool saved_busy[2] = {c->busy[0], c->busy[1]};
+    auto give_up = [&]() {
+        c->sp[0] = saved_sp[0]; c->sp[1] = saved_sp[1];
+        c->busy[0] = saved_busy[0]; c->busy[1] = saved_busy[1];
+        c->launches = launches0;
+        c->graphs_disabled = true;
+        cudaGetLastError();
+        one_step(c); one_step(c);
+    };
     cudaGraph_t graph = nullptr;
-    PICSP_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { give_up(); return; }
+    bool recorded = true;
     try {
         one_step(c); one_step(c);
     } catch (...) {
-        cudaStreamEndCapture(c->stream, &graph);
-        if (graph) cudaGraphDestroy(graph);
-        throw;
+        recorded = false;
     }
-    PICSP_CUDA(cudaStreamEndCapture(c->stream, &graph));
+    const cudaError_t ec = cudaStreamEndCapture(c->stream, &graph);
     cudaGraphExec_t exec = nullptr;
-    const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    if (!recorded || ec != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        give_up();
+        return;
+    }
     cudaGraphDestroy(graph);
-    if (e != cudaSuccess) throw Error(PICSP_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
     int slot;
     if (c->step_graph_count < picsp_ctx::STEP_GRAPH_CACHE) slot = c->step_graph_count++;
     else {                                 // evict round robin; the old graph may still be running
@@ -887,6 +960,9 @@ int picsp_step(picsp_ctx *c, int nsteps) {   // src/main.cpp:481-504
     check_ctx(c);
     PICSP_REQUIRE(nsteps >= 0, PICSP_ERR_INVALID, "negative step count");
     PICSP_CUDA(cudaSetDevice(c->prm.device));
+    // a violation flagged by the movers of an EARLIER call (mirrored into mapped host memory by the grid phase of
+    // the step that followed it) is reported here, before anything else is enqueued
+    if (*(volatile int *)c->h_error_mapped) check_device_error(c);
     PhaseScope whole(c, PICSP_PHASE_STEP);
     for (int it = 0; it < nsteps;) {
         if (nsteps - it >= 2 && step_graph_eligible(c)) { step_pair_graph(c); it += 2; }
@@ -894,6 +970,120 @@ int picsp_step(picsp_ctx *c, int nsteps) {   // src/main.cpp:481-504
     }
     PICSP_API_END
 }
+
+// ---- asynchronous dumps -------------------------------------------------------------------------
+// What the reference writes every 50 steps (writeSpecies x2, writePot, computeKE x2; src/main.cpp:507-527) is first
+// SNAPSHOT on the device, stream-ordered with the time loop (un-permute into [n][4] rows in list order, copies of
+// den / phi, the KE sums), and then copied to the caller's buffers on the copy stream while the next steps run.
+static bool ensure_snapshot(picsp_ctx *c) {
+    if (c->snapshot_unavailable) return false;
+    const Geom &g = c->g;
+    if (!c->snap_grids) {
+        if (cudaMalloc((void **)&c->snap_grids, sizeof(double) * 3 * (size_t)g.nn) != cudaSuccess ||
+            cudaMalloc((void **)&c->snap_ke, sizeof(double) * 2) != cudaSuccess) {
+            cudaGetLastError(); c->snapshot_unavailable = true; return false;
+        }
+    }
+    for (int s = 0; s < 2; s++) {
+        const Species &sp = c->sp[s];
+        if (c->snap_rows_cap[s] >= sp.n) continue;
+        cudaFree(c->snap_rows[s]); c->snap_rows[s] = nullptr; c->snap_rows_cap[s] = 0;
+        const int64_t cap = std::max<int64_t>(sp.cap, 1);
+        if (cudaMalloc((void **)&c->snap_rows[s], sizeof(double) * 4 * (size_t)cap) != cudaSuccess) {
+            cudaGetLastError(); c->snapshot_unavailable = true; return false;   // e.g. 4e9 particles on one GPU: synchronous dumps
+        }
+        c->snap_rows_cap[s] = cap;
+    }
+    if (!c->ev_snap) {
+        PICSP_CUDA(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+        PICSP_CUDA(cudaEventCreateWithFlags(&c->ev_dump_done, cudaEventDisableTiming));
+    }
+    return true;
+}
+
+int picsp_dump_wait(picsp_ctx *c) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    if (!c->dump_in_flight) return PICSP_OK;
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    PICSP_CUDA(cudaEventSynchronize(c->ev_dump_done));
+    c->dump_in_flight = false;
+    if (c->dump_ke_host)
+        for (int s = 0; s < 2; s++)      // src/main.cpp:1198: 0.5*spwt*mass is ADDED (Q10); chargeE == 1 (:1201)
+            c->dump_ke_host[s] = (c->h_pinned[32 + s] + 0.5 * (c->sp[s].spwt * c->sp[s].m)) / 1.0;
+    c->dump_ke_host = nullptr;
+    PICSP_API_END
+}
+
+int picsp_dump_begin(picsp_ctx *c, double *rows_i, double *rows_e, double *den_i, double *den_e, double *phi, double *ke2) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    if (c->dump_in_flight) { int rc = picsp_dump_wait(c); if (rc != PICSP_OK) return rc; }
+    const Geom &g = c->g;
+    double *rows[2] = {rows_i, rows_e};
+    double *den[2] = {den_i, den_e};
+    const bool root = !c->comm || c->rank == 0;
+    if (!ensure_snapshot(c)) {
+        // no room for a snapshot: the same dump, synchronously, through the ordinary downloads
+        for (int s = 0; s < 2; s++) {
+            if (rows[s]) { int rc = picsp_species_download_rows(c, s, rows[s]); if (rc != PICSP_OK) return rc; }
+            if (den[s] || c->comm) {
+                ensure_stage(c, g.nn);
+                std::vector<double> tmp;
+                double *dst = den[s];
+                if (!dst) { tmp.resize((size_t)g.nn); dst = tmp.data(); }     // the density download is a collective
+                int rc = picsp_grid_download(c, s == 0 ? PICSP_DEN_I : PICSP_DEN_E, dst); if (rc != PICSP_OK) return rc;
+            }
+            if (ke2) { int rc = picsp_compute_ke(c, s, &ke2[s]); if (rc != PICSP_OK) return rc; }
+        }
+        if (phi) { int rc = picsp_grid_download(c, PICSP_PHI, phi); if (rc != PICSP_OK) return rc; }
+        return PICSP_OK;
+    }
+    ensure_copy_stream(c);
+    const size_t gbytes = sizeof(double) * (size_t)g.nn;
+    for (int s = 0; s < 2; s++) {
+        Species &sp = c->sp[s];
+        if ((rows[s] || ke2) && sp.n > 0)
+            PICSP_LAUNCH(c, k_rows_unpermute, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy,
+                         sp.has_perm ? sp.id : (const uint32_t *)nullptr, (long long)sp.n, reinterpret_cast<double2 *>(c->snap_rows[s]));
+        if (ke2) {
+            PICSP_LAUNCH(c, k_ke_rows_partial, RED_BLOCKS, RED_THREADS, 0, c->snap_rows[s], (long long)sp.n, c->d_red);
+            PICSP_LAUNCH(c, k_sum_final, 1, 1024, 0, c->d_red, RED_BLOCKS, c->snap_ke + s);
+        }
+        // density: the sum over ranks lands on rank 0 only ("at dump steps only: reduce den_i, den_e to rank 0")
+        if (c->comm)
+            PICSP_NCCL(nccl().Reduce(sp.den, c->snap_grids + (size_t)s * g.nn, (size_t)g.nn, ncclFloat64, ncclSum, 0, c->comm, c->stream));
+        else if (den[s])
+            PICSP_CUDA(cudaMemcpyAsync(c->snap_grids + (size_t)s * g.nn, sp.den, gbytes, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (ke2 && c->comm) PICSP_NCCL(nccl().AllReduce(c->snap_ke, c->snap_ke, 2, ncclFloat64, ncclSum, c->comm, c->stream));
+    if (phi && root) PICSP_CUDA(cudaMemcpyAsync(c->snap_grids + 2 * (size_t)g.nn, c->phi, gbytes, cudaMemcpyDeviceToDevice, c->stream));
+    c->busy[0] = c->busy[1] = true;
+    PICSP_CUDA(cudaEventRecord(c->ev_snap, c->stream));
+    PICSP_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_snap, 0));
+    // small things first, so that a caller polling the grids does not wait behind 32 GB of phase space
+    if (ke2) PICSP_CUDA(cudaMemcpyAsync(c->h_pinned + 32, c->snap_ke, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (root) {
+        for (int s = 0; s < 2; s++)
+            if (den[s]) PICSP_CUDA(cudaMemcpyAsync(den[s], c->snap_grids + (size_t)s * g.nn, gbytes, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (phi) PICSP_CUDA(cudaMemcpyAsync(phi, c->snap_grids + 2 * (size_t)g.nn, gbytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    for (int s = 0; s < 2; s++)
+        if (rows[s] && c->sp[s].n > 0)
+            PICSP_CUDA(cudaMemcpyAsync(rows[s], c->snap_rows[s], sizeof(double) * 4 * (size_t)c->sp[s].n, cudaMemcpyDeviceToHost, c->copy_stream));
+    PICSP_CUDA(cudaEventRecord(c->ev_dump_done, c->copy_stream));
+    c->dump_in_flight = true;
+    c->dump_ke_host = ke2;
+    PICSP_API_END
+}
+
+void *picsp_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void picsp_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 // ---- diagnostics -------------------------------------------------------------------------
 int picsp_compute_ke(picsp_ctx *c, int s, double *ke) {
@@ -966,6 +1156,14 @@ int picsp_set_sort_period(picsp_ctx *c, int s, int period) {
     PICSP_API_END
 }
 
+int picsp_set_cell_sort_period(picsp_ctx *c, int s, int period) {
+    PICSP_API_BEGIN
+    check_ctx(c); check_species(s);
+    c->sp[s].cell_period = period >= 0 ? period : (s == 0 ? 64 : 0);
+    c->sp[s].steps_since_cellsort = c->sp[s].cell_period;       // due at the next push
+    PICSP_API_END
+}
+
 // ---- multi-GPU ---------------------------------------------------------------------------
 int picsp_comm_unique_id(void *id128) {
     PICSP_API_BEGIN
@@ -1003,6 +1201,7 @@ int picsp_species_fill_synthetic(picsp_ctx *c, int s, int64_t n, int64_t first_i
     if (sp.acc_valid) PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
     sp.n = n; sp.hist_valid = false; sp.acc_valid = false;
     sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0; sp.cnt_valid = false; sp.staged_v_valid = false;
+    sp.steps_since_cellsort = sp.cell_period;
     PICSP_CUDA(cudaStreamSynchronize(c->stream));
     PICSP_API_END
 }

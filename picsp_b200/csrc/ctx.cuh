@@ -97,6 +97,12 @@ struct Species {
     unsigned int *chunk_base = nullptr;  // [max_chunks][9] ranges reserved from them for a re-binning launch
     bool cnt_valid = false;        // chunk_cnt describes the stored positions under the current chunk table
     bool staged_v_valid = false;   // vx2/vy2 hold the current velocities in upload order (left there by a download)
+    // cell order inside a bin (k_cell_count / k_cell_scan / k_cell_permute)
+    int cell_period = 0;           // steps between two cell orderings (0: never)
+    int steps_since_cellsort = 0;
+    unsigned int *cell_cnt = nullptr;    // [chunks][CELLKEYS] populations, then first slots
+    long long cell_cnt_chunks = 0;
+    int *tile_chunk0 = nullptr;          // [ntiles] first chunk of every bin
     int ntiles = 0;
 };
 
@@ -135,6 +141,7 @@ struct picsp_ctx {
     bool smem_opted_in = false;
     bool hist_smem_opted_in = false;
     bool sort2_opted_in = false;
+    bool cellsort_opted_in = false;
 
     // staging for grid component uploads/downloads
     double *stage = nullptr; int64_t stage_cap = 0;
@@ -159,6 +166,22 @@ struct picsp_ctx {
 
     // multi-GPU
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+
+    // asynchronous dumps (picsp_dump_begin / picsp_dump_wait): device-side snapshot of what the reference dumps
+    // (writeSpecies / writePot, src/main.cpp:1142-1216), copied out on the copy stream while the time loop goes on
+    double *snap_rows[2] = {nullptr, nullptr};   // [n][4] rows in upload order
+    int64_t snap_rows_cap[2] = {0, 0};
+    double *snap_grids = nullptr;                // den_i | den_e | phi, nn each
+    double *snap_ke = nullptr;                   // [2] sum(vx^2+vy^2) per species (summed over ranks)
+    cudaEvent_t ev_snap = nullptr, ev_dump_done = nullptr;
+    bool dump_in_flight = false;
+    double *dump_ke_host = nullptr;              // caller's [2]: the Q10 constant is added in picsp_dump_wait
+    bool snapshot_unavailable = false;           // not enough memory for a snapshot: dumps are synchronous
+
+    // device-side error flag mirrored into mapped host memory at the start of every step, so that picsp_step can
+    // report a violation of the previous steps without synchronising
+    int *h_error_mapped = nullptr;
+    bool graphs_disabled = false;                // a capture / instantiation failed once: plain launches from then on
 
     // instrumentation
     bool profiling = false;

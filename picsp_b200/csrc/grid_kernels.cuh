@@ -76,8 +76,12 @@ __device__ __forceinline__ double finalize_node(const GridPhaseSpecies &sp, long
     return (clear ? 0.0 : sp.den[k]) + (double)a * scale;
 }
 
-__global__ void k_grid_phase(GridPhaseSpecies s0, GridPhaseSpecies s1, double *__restrict__ rho, int nix, int niy, int clear) {
+__global__ void k_grid_phase(GridPhaseSpecies s0, GridPhaseSpecies s1, double *__restrict__ rho, int nix, int niy, int clear,
+                             const int *__restrict__ err, int *__restrict__ err_host) {
     const int L = nix - 1, M = niy - 1;
+    // mirror the sticky device error flag (set by the movers of the previous steps) into mapped host memory:
+    // picsp_step reads it without synchronising and reports the violation from its next call
+    if (blockIdx.x == 0 && threadIdx.x == 0 && *err) *err_host = *err;
     const double sc0 = s0.weight * exp2((double)(-*s0.frac)), sc1 = s1.weight * exp2((double)(-*s1.frac));
     const unsigned nn = (unsigned)nix * (unsigned)niy;      // <= 2^31 by the capacity of int node counts
     for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < nn; k += gridDim.x * blockDim.x) {
@@ -469,6 +473,18 @@ __global__ void k_ke_terms(const double *__restrict__ vx, const double *__restri
                            long long n, double *__restrict__ terms) {
     for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x)
         terms[id ? (long long)id[p] : p] = vx[p] * vx[p] + vy[p] * vy[p];
+}
+// KE terms of a row-layout snapshot ([n][4] rows {x, y, vx, vy} in upload order): fixed grid, fixed tree
+__global__ void k_ke_rows_partial(const double *__restrict__ rows, long long n, double *__restrict__ partial) {
+    __shared__ double s_red[32];
+    double s = 0.0;
+    const double2 *r2 = reinterpret_cast<const double2 *>(rows);
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const double2 v = r2[2 * p + 1];
+        s += v.x * v.x + v.y * v.y;
+    }
+    double t = block_sum(s, s_red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
 __global__ void k_sum_partial(const double *__restrict__ a, long long n, double *__restrict__ partial) {
     __shared__ double s_red[32];

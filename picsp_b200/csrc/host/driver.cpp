@@ -13,6 +13,14 @@ struct Guard {
     picsp_ctx *c = nullptr;
     ~Guard() { if (c) picsp_destroy(c); }
 };
+// page-locked host buffer (picsp_host_alloc): device->host copies into it do not block the caller
+struct Pinned {
+    double *p = nullptr;
+    explicit Pinned(size_t n) : p((double *)picsp_host_alloc(sizeof(double) * (n ? n : 1))) {}
+    ~Pinned() { picsp_host_free(p); }
+    Pinned(const Pinned &) = delete;
+    Pinned &operator=(const Pinned &) = delete;
+};
 #define HOST_CHECK(call)                                                          \
     do {                                                                          \
         int rc__ = (call);                                                        \
@@ -85,32 +93,49 @@ int run(const std::string &ini_path, const std::string &out_path, int max_steps,
     const int dp = cfg.dumpPeriod > 0 ? cfg.dumpPeriod : 1;
     const size_t nT = (size_t)(cfg.nTimeSteps / dp) + 1;
     std::vector<double> energy(2 * nT, 0.0);
-    std::vector<double> rows, grid((size_t)nix * niy);
-    int ti = 0;
     const int last = max_steps >= 0 && max_steps < cfg.nTimeSteps ? max_steps : cfg.nTimeSteps;
-    for (int ts = 0; ts <= last; ts++) {                                // for (ts = 0; ts < nTimeSteps+1; ts++)
-        HOST_CHECK(picsp_step(g.c, 1));
-        if (ts % 50 == 0) {
+
+    // One set of page-locked dump buffers: a dump is snapshot on the device and copied out while the steps of the next
+    // period run (picsp_dump_begin / picsp_dump_wait); it is written to the file when the next dump is due.
+    const size_t nn = (size_t)nix * niy;
+    Pinned rows_i(4 * (size_t)nI), rows_e(4 * (size_t)nE), den_i(nn), den_e(nn), phi(nn), ke(2);
+    if (!rows_i.p || !rows_e.p || !den_i.p || !den_e.p || !phi.p || !ke.p) {
+        if (err) *err = "cannot allocate page-locked dump buffers";
+        return PICSP_ERR_CUDA;
+    }
+    int pending_ts = -1, ti = 0;
+    auto flush_pending = [&]() -> int {           // writeSpecies x2, writePot, energy row (main.cpp:518-525)
+        if (pending_ts < 0) return PICSP_OK;
+        int rc = picsp_dump_wait(g.c);
+        if (rc != PICSP_OK) return rc;
+        const std::string t = std::to_string(pending_ts);
+        h5.write_dataset_f64("/particle.i/" + t, rows_i.p, nI, 4);
+        h5.write_dataset_f64("/den.i/" + t, den_i.p, nix, niy);
+        h5.write_dataset_f64("/particle.e/" + t, rows_e.p, nE, 4);
+        h5.write_dataset_f64("/den.e/" + t, den_e.p, nix, niy);
+        h5.write_dataset_f64("/phi/" + t, phi.p, nix, niy);
+        if ((size_t)ti < nT) { energy[2 * ti] = ke.p[0]; energy[2 * ti + 1] = ke.p[1]; }
+        ti++;
+        pending_ts = -1;
+        return PICSP_OK;
+    };
+    // for (ts = 0; ts < nTimeSteps+1; ts++) { body; if (ts % 50 == 0) diagnostics }  (main.cpp:479-531): the bodies
+    // between two diagnostics are enqueued by ONE picsp_step call (small runs replay CUDA graphs of step pairs)
+    for (int ts = 0; ts <= last;) {
+        const int next_diag = ((ts + 49) / 50) * 50;
+        const int upto = next_diag <= last ? next_diag : last;        // index of the last body of this batch
+        HOST_CHECK(picsp_step(g.c, upto - ts + 1));
+        ts = upto + 1;
+        if (upto % 50 == 0) {
             double max_phi = 0, phi0 = 0;
             HOST_CHECK(picsp_delta_phi(g.c, &max_phi, &phi0));
-            if (!quiet) std::printf("TS: %i \t delta_phi: %.3g\n", ts, max_phi - phi0);
-            for (int s = 0; s < 2; s++) {                               // writeSpecies, main.cpp:1142-1175
-                const int64_t n = s == 0 ? nI : nE;
-                rows.resize((size_t)4 * n);
-                HOST_CHECK(picsp_species_download_rows(g.c, s, rows.data()));
-                h5.write_dataset_f64(std::string(s == 0 ? "/particle.i/" : "/particle.e/") + std::to_string(ts), rows.data(), n, 4);
-                HOST_CHECK(picsp_grid_download(g.c, s == 0 ? PICSP_DEN_I : PICSP_DEN_E, grid.data()));
-                h5.write_dataset_f64(std::string(s == 0 ? "/den.i/" : "/den.e/") + std::to_string(ts), grid.data(), nix, niy);
-            }
-            HOST_CHECK(picsp_grid_download(g.c, PICSP_PHI, grid.data()));  // writePot, main.cpp:1205-1216
-            h5.write_dataset_f64("/phi/" + std::to_string(ts), grid.data(), nix, niy);
-            double ke_i = 0, ke_e = 0;
-            HOST_CHECK(picsp_compute_ke(g.c, 0, &ke_i));
-            HOST_CHECK(picsp_compute_ke(g.c, 1, &ke_e));
-            if ((size_t)ti < nT) { energy[2 * ti] = ke_i; energy[2 * ti + 1] = ke_e; }
-            ti++;
+            if (!quiet) std::printf("TS: %i \t delta_phi: %.3g\n", upto, max_phi - phi0);
+            HOST_CHECK(flush_pending());
+            HOST_CHECK(picsp_dump_begin(g.c, rows_i.p, rows_e.p, den_i.p, den_e.p, phi.p, ke.p));
+            pending_ts = upto;
         }
     }
+    HOST_CHECK(flush_pending());
     h5.write_dataset_f64("/timedata/energy", energy.data(), nT, 2);     // writeKE, main.cpp:1179-1188
     if (!h5.close(err)) return PICSP_ERR_INVALID;
     if (!quiet) {

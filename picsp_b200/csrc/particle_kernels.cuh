@@ -101,7 +101,11 @@ __device__ __forceinline__ void scatter_fixed(long long *__restrict__ acc, const
     double lx = to_logical(x, c.dx), ly = to_logical(y, c.dx);
     int i = __double2int_rz(lx), j = __double2int_rz(ly);
     double di = lx - i, dj = ly - j;
-    if (i < 0 || i > c.nix - 2 || j < 0 || j > c.niy - 2) return;   // cannot happen for 0 <= pos < xl (main.cpp:807-824 guarantees it)
+    if (i < 0 || j < 0 || i > c.nix - 1 || j > c.niy - 1) return;   // cannot happen for 0 <= pos < xl (main.cpp:807-824 guarantees it)
+    // pos within an ulp below xl: the quotient rounds to ncx and the reference puts the whole weight on the last
+    // node row (di == 0), i.e. on the (ncx-1, di = 1) corner pair of the last real cell
+    if (i > c.nix - 2) { i = c.nix - 2; di = 1.0; }
+    if (j > c.niy - 2) { j = c.niy - 2; dj = 1.0; }
     long long b = (long long)i * c.niy + j;
     unsigned long long *a = reinterpret_cast<unsigned long long *>(acc);
     atomicAdd(&a[b],             (unsigned long long)__double2ll_rn((1 - di) * (1 - dj) * scale));

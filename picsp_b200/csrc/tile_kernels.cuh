@@ -341,6 +341,153 @@ k_resort_chunks(const double *__restrict__ x, const double *__restrict__ y, cons
 }
 
 // ---------------------------------------------------------------------------
+// Cell order inside a bin (periodic, stand-alone; slow species only).
+//
+// The mover's shared-memory traffic is dominated by bank conflicts of RANDOM in-tile addresses (E gather 2.7-way,
+// accumulator atomics 3.7-way: profiles/r01_v5_rebinning_mover.md).  When the particles of a bin are stored in cell
+// order, the lanes of a warp sit in the same cell: the four corner loads broadcast and deposit_commit() combines the
+// warp's weights before it touches the accumulators.  Ions move ~0.007 cells per step, so the order survives tens
+// of steps; thermal electrons (0.23 cells per step) lose it in two or three, so it is off for them by default.
+//
+// The bin's range [tile_off[t], tile_off[t+1]) keeps its particles; they are permuted inside it by a counting
+// sort on the cell of the bin's WINDOW (stragglers outside the bin are clamped into the ring), in three kernels:
+//   k_cell_count   per chunk: population per window cell                       (reads x, y)
+//   k_cell_scan    per bin:   first slot of every (chunk, cell) run in the bin (cells major, chunks minor)
+//   k_cell_permute per chunk: rank inside (chunk, cell), arrays staged through shared memory in cell order so that
+//                  consecutive threads store consecutive slots, written to the second buffer set
+// Chunk table, bin offsets and histogram are unchanged.  Any order inside a bin is correct: the step's result is
+// bit-identical with and without this pass (tested).
+// ---------------------------------------------------------------------------
+constexpr int CELLW = TILE + 2 * PICSP_HALO;                 // window edge in cells (24)
+constexpr int CELLKEYS = CELLW * CELLW;                      // 576
+static_assert(CELLKEYS <= 1024, "cell keys must fit the staging kernel's class counters");
+
+__device__ __forceinline__ int cell_key(double x, double y, const PushConst &c, int tx, int ty) {
+    if (!in_box(x, y, c)) return 0;
+    const double inv_dx = 1.0 / c.dx;
+    double fi, fj;
+    const int ci = floor_nonneg(to_logical_fast(x, c.dx, inv_dx), fi);
+    const int cj = floor_nonneg(to_logical_fast(y, c.dx, inv_dx), fj);
+    const int li = min(max(ci - (tx * TILE - PICSP_HALO), 0), CELLW - 1);
+    const int lj = min(max(cj - (ty * TILE - PICSP_HALO), 0), CELLW - 1);
+    return li * CELLW + lj;
+}
+
+__global__ void __launch_bounds__(256)
+k_cell_count(const double *__restrict__ x, const double *__restrict__ y, const Chunk *__restrict__ chunks,
+             const int *__restrict__ nchunks, PushConst c, unsigned int *__restrict__ cnt, int *__restrict__ tile_chunk0) {
+    __shared__ unsigned s_cnt[CELLKEYS];
+    const int b = blockIdx.x;
+    if (b >= *nchunks) return;
+    const Chunk ck = chunks[b];
+    if (threadIdx.x == 0 && (b == 0 || chunks[b - 1].tile != ck.tile)) tile_chunk0[ck.tile] = b;   // chunks are listed bin by bin
+    for (int k = threadIdx.x; k < CELLKEYS; k += blockDim.x) s_cnt[k] = 0u;
+    __syncthreads();
+    const int tx = ck.tile / c.nty, ty = ck.tile - tx * c.nty;
+    for (int k = threadIdx.x; k < ck.count; k += blockDim.x)
+        atomicAdd(&s_cnt[cell_key(x[ck.start + k], y[ck.start + k], c, tx, ty)], 1u);
+    __syncthreads();
+    for (int k = threadIdx.x; k < CELLKEYS; k += blockDim.x) cnt[(size_t)b * CELLKEYS + k] = s_cnt[k];
+}
+
+// one CTA per bin; thread = cell key.  cnt[chunk][key] -> first slot (relative to the bin) of that run
+__global__ void __launch_bounds__(CELLKEYS)
+k_cell_scan(const long long *__restrict__ tile_off, const int *__restrict__ tile_chunk0, int chunk, unsigned int *__restrict__ cnt) {
+    __shared__ unsigned s_warp[CELLKEYS / 32];
+    const int t = blockIdx.x, key = threadIdx.x, lane = key & 31, w = key >> 5;
+    const long long pop = tile_off[t + 1] - tile_off[t];
+    if (pop <= 0) return;
+    const int nch = (int)((pop + chunk - 1) / chunk);
+    unsigned int *p = cnt + (size_t)tile_chunk0[t] * CELLKEYS + key;
+    unsigned total = 0;
+    for (int q = 0; q < nch; q++) total += p[(size_t)q * CELLKEYS];
+    // exclusive scan of the per-key totals over the CELLKEYS threads
+    unsigned incl = total;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        unsigned v = lane < CELLKEYS / 32 ? s_warp[lane] : 0u, inc2 = v;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += u; }
+        if (lane < CELLKEYS / 32) s_warp[lane] = inc2 - v;
+    }
+    __syncthreads();
+    unsigned run = s_warp[w] + incl - total;
+    for (int q = 0; q < nch; q++) { const unsigned v = p[(size_t)q * CELLKEYS]; p[(size_t)q * CELLKEYS] = run; run += v; }
+}
+
+constexpr size_t CELLSORT_SMEM_BYTES = sizeof(double) * CHUNK + sizeof(unsigned) * (2 * CHUNK + 2 * CELLKEYS);
+
+__global__ void __launch_bounds__(SORT2_THREADS, 2)
+k_cell_permute(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ vx,
+               const double *__restrict__ vy, const uint32_t *__restrict__ id, const Chunk *__restrict__ chunks,
+               const int *__restrict__ nchunks, PushConst c, const long long *__restrict__ tile_off,
+               const unsigned int *__restrict__ base, double *__restrict__ x2, double *__restrict__ y2,
+               double *__restrict__ vx2, double *__restrict__ vy2, uint32_t *__restrict__ id2) {
+    extern __shared__ __align__(16) unsigned char cs_smem[];
+    double *s_val = reinterpret_cast<double *>(cs_smem);                    // [CHUNK] one array of the chunk, in cell order
+    unsigned *s_dst = reinterpret_cast<unsigned *>(s_val + CHUNK);           // [CHUNK] destination slot (relative to the bin) of cell-ordered element q
+    unsigned *s_pos = s_dst + CHUNK;                                         // [CHUNK] key | rank, later the cell-ordered position, of source element k
+    unsigned *s_cnt = s_pos + CHUNK;                                         // [CELLKEYS]
+    unsigned *s_pref = s_cnt + CELLKEYS;                                     // [CELLKEYS] exclusive prefix of s_cnt
+    const int b = blockIdx.x;
+    if (b >= *nchunks) return;
+    const Chunk ck = chunks[b];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tx = ck.tile / c.nty, ty = ck.tile - tx * c.nty;
+    for (int k = tid; k < CELLKEYS; k += SORT2_THREADS) s_cnt[k] = 0u;
+    __syncthreads();
+    // 1. key and rank (inside chunk and key) of every particle; warp-aggregated counters
+    for (int k0 = 0; k0 < ck.count; k0 += SORT2_THREADS) {        // warp-uniform trip count
+        const int k = k0 + tid;
+        const bool live = k < ck.count;
+        const int key = live ? cell_key(x[ck.start + k], y[ck.start + k], c, tx, ty) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(peers) - 1;
+        unsigned r0 = 0;
+        if (live && lane == leader) r0 = atomicAdd(&s_cnt[key], (unsigned)__popc(peers));
+        r0 = __shfl_sync(0xffffffffu, r0, leader);
+        if (live) s_pos[k] = ((unsigned)key << 16) | (r0 + (unsigned)__popc(peers & ((1u << lane) - 1u)));   // rank < 4096 < 2^16
+    }
+    __syncthreads();
+    // 2. exclusive prefix of the key populations (warp 0: CELLKEYS / 32 keys per lane)
+    if (tid < 32) {
+        const int per = (CELLKEYS + 31) / 32, k0 = tid * per, k1 = min(k0 + per, CELLKEYS);
+        unsigned sum = 0;
+        for (int k = k0; k < k1; k++) sum += s_cnt[k];
+        unsigned incl = sum;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        unsigned run = incl - sum;
+        for (int k = k0; k < k1; k++) { s_pref[k] = run; run += s_cnt[k]; }
+    }
+    __syncthreads();
+    // 3. cell-ordered position of every source element, destination slot of every position
+    const unsigned int *mybase = base + (size_t)b * CELLKEYS;
+    for (int k = tid; k < ck.count; k += SORT2_THREADS) {
+        const unsigned code = s_pos[k];
+        const int key = (int)(code >> 16);
+        const unsigned rank = code & 0xFFFFu;
+        const unsigned q = s_pref[key] + rank;
+        s_pos[k] = q;
+        s_dst[q] = mybase[key] + rank;
+    }
+    __syncthreads();
+    // 4. each array: coalesced read -> shared memory in cell order -> runs of consecutive stores
+    const long long t0 = tile_off[ck.tile];
+    auto move = [&](const double *__restrict__ src, double *__restrict__ dstp) {
+        for (int k = tid; k < ck.count; k += SORT2_THREADS) s_val[s_pos[k]] = src[ck.start + k];
+        __syncthreads();
+        for (int q = tid; q < ck.count; q += SORT2_THREADS) dstp[t0 + s_dst[q]] = s_val[q];
+        __syncthreads();
+    };
+    move(x, x2); move(y, y2); move(vx, vx2); move(vy, vy2);
+    unsigned *s_ival = reinterpret_cast<unsigned *>(s_val);
+    for (int k = tid; k < ck.count; k += SORT2_THREADS) s_ival[s_pos[k]] = id ? id[ck.start + k] : (uint32_t)(ck.start + k);
+    __syncthreads();
+    for (int q = tid; q < ck.count; q += SORT2_THREADS) id2[t0 + s_dst[q]] = s_ival[q];
+}
+
+// ---------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA tensor load
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -501,15 +648,23 @@ __device__ __forceinline__ void add64_limbs(unsigned *sLo, unsigned *sHi, int k,
     atomicAdd(&sHi[k], hi + carry);
 }
 
-// fixed-point CIC deposit of one particle into the window limbs, or the global grid.
+// fixed-point CIC deposit of one particle into the window limbs, or the global grid, in two halves:
+// deposit_prepare() is per-particle arithmetic, deposit_commit() is warp-cooperative (every live lane of the warp
+// must call it, with the same `act` mask).
+struct Deposit {
+    unsigned long long w00, w10, w01, w11;   // fixed-point corner weights (< 2^52)
+    int k;                                   // window node index of the cell's (i, j) corner
+    int i, j;                                // cell (global path)
+    int mode;                                // 0: nothing (position outside the box), 1: window, 2: global grid
+};
+
 // ci/cj return the particle's cell (or -1 when the position is outside the box: skipped).
-// returns true when the deposit stayed inside the shared-memory window.
-__device__ __forceinline__ bool deposit_one(double px, double py, const PushConst &c, double inv_dx, const TileCtx &tc,
-                                            unsigned *sLo, unsigned *sHi, long long *__restrict__ acc, double scale,
-                                            int &ci, int &cj) {
+__device__ __forceinline__ void deposit_prepare(double px, double py, const PushConst &c, double inv_dx, const TileCtx &tc,
+                                                double scale, Deposit &dp, int &ci, int &cj) {
     ci = cj = -1;
+    dp.mode = 0; dp.k = -1; dp.i = dp.j = 0; dp.w00 = dp.w10 = dp.w01 = dp.w11 = 0ull;
     if (!(in_range_bits(px, tc.xl_bits) && in_range_bits(py, tc.yl_bits))) {
-        if (!in_box(px, py, c)) return false;    // -0.0 is inside the box; everything else here is not
+        if (!in_box(px, py, c)) return;          // -0.0 is inside the box; everything else here is not
     }
     double lx = to_logical_fast(px, c.dx, inv_dx), ly = to_logical_fast(py, c.dx, inv_dx);
     double fi, fj;
@@ -519,31 +674,88 @@ __device__ __forceinline__ bool deposit_one(double px, double py, const PushCons
     double a = (1 - di) * scale, d = di * scale, b = 1 - dj;
     const double magic = 4503599627370496.0;   // 2^52: the mantissa of (w + 2^52) is w rounded to nearest-even
     const unsigned long long mm = 0xFFFFFFFFFFFFFull;
-    unsigned long long w00 = (unsigned long long)__double_as_longlong(fma(a, b, magic)) & mm;
-    unsigned long long w10 = (unsigned long long)__double_as_longlong(fma(d, b, magic)) & mm;
-    unsigned long long w01 = (unsigned long long)__double_as_longlong(fma(a, dj, magic)) & mm;
-    unsigned long long w11 = (unsigned long long)__double_as_longlong(fma(d, dj, magic)) & mm;
+    dp.w00 = (unsigned long long)__double_as_longlong(fma(a, b, magic)) & mm;
+    dp.w10 = (unsigned long long)__double_as_longlong(fma(d, b, magic)) & mm;
+    dp.w01 = (unsigned long long)__double_as_longlong(fma(a, dj, magic)) & mm;
+    dp.w11 = (unsigned long long)__double_as_longlong(fma(d, dj, magic)) & mm;
     if ((unsigned)(i - tc.ilo) <= tc.ispan && (unsigned)(j - tc.jlo) <= tc.jspan) {
-        int k = (i - tc.wx0) * WIN + (j - tc.wy0);
+        dp.k = (i - tc.wx0) * WIN + (j - tc.wy0);
+        dp.mode = 1;
+        return;
+    }
+    if (i > c.nix - 2 || j > c.niy - 2) {
+        // A position within an ulp below xl (yl) rounds to the cell index ncx (ncy).  The reference then deposits the
+        // whole weight on the last node row with di == 0 (src/main.cpp:657-667), which the fold adds to row 0; that is
+        // the corner pair (ncx-1, di = 1) of the last real cell.
+        if (i > c.nix - 2) { i = c.nix - 2; di = 1.0; }
+        if (j > c.niy - 2) { j = c.niy - 2; dj = 1.0; }
+        a = (1 - di) * scale; d = di * scale; b = 1 - dj;
+        dp.w00 = (unsigned long long)__double_as_longlong(fma(a, b, magic)) & mm;
+        dp.w10 = (unsigned long long)__double_as_longlong(fma(d, b, magic)) & mm;
+        dp.w01 = (unsigned long long)__double_as_longlong(fma(a, dj, magic)) & mm;
+        dp.w11 = (unsigned long long)__double_as_longlong(fma(d, dj, magic)) & mm;
+    }
+    dp.i = i; dp.j = j; dp.mode = 2;
+}
+
+// Exact sum of a 52-bit quantity over the lanes of `m` out of two 32-bit warp reductions (REDUX.SUM): the 26-bit
+// halves each sum to < 32 * 2^26 = 2^31.
+__device__ __forceinline__ unsigned long long warp_sum52(unsigned m, unsigned long long w) {
+    const unsigned lo = (unsigned)w & 0x3FFFFFFu, hi = (unsigned)(w >> 26);
+    return (unsigned long long)__reduce_add_sync(m, lo) + ((unsigned long long)__reduce_add_sync(m, hi) << 26);
+}
+
+#ifndef PICSP_AGG_MIN
+#define PICSP_AGG_MIN 4        // lanes of a warp in one cell from which their deposits are combined before touching shared memory
+#endif
+#ifndef PICSP_AGG_ROUNDS
+#define PICSP_AGG_ROUNDS 3     // cells per warp that get combined; lanes of further cells deposit individually
+#endif
+
+// Warp-aggregated commit.  Lanes of a warp whose particles sit in the SAME cell would hit the same eight
+// shared-memory words and serialise (a cell-ordered store, or the reference's own diagonal two-stream load with
+// ~5e5 particles per occupied cell): one MATCH finds the lanes per cell, the fixed-point weights of a
+// group are summed exactly with REDUX and its first lane alone touches the accumulators.  Integer sums: the
+// result is bit-identical to the lane-by-lane deposit.  Returns true when the deposit stayed inside the window.
+__device__ __forceinline__ bool deposit_commit(const Deposit &dp, unsigned act, const PushConst &c, unsigned *sLo, unsigned *sHi,
+                                               long long *__restrict__ acc) {
+    unsigned long long v00 = dp.w00, v10 = dp.w10, v01 = dp.w01, v11 = dp.w11;
+    bool own = dp.mode == 1;
+    if (PICSP_AGG_ROUNDS > 0 && act == 0xffffffffu) {       // full warps only; the tail slice of a chunk takes the plain path
+        const unsigned lane = threadIdx.x & 31u;
+        const int key = dp.mode == 1 ? dp.k : -1 - (int)lane;                 // lanes without a window deposit match nobody
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        unsigned big = __ballot_sync(0xffffffffu, __popc(peers) >= PICSP_AGG_MIN);
+#pragma unroll 1
+        for (int r = 0; r < PICSP_AGG_ROUNDS && big; r++) {
+            const int ld = __ffs(big) - 1;
+            const unsigned m = __shfl_sync(0xffffffffu, peers, ld);
+            if ((m >> lane) & 1u) {
+                v00 = warp_sum52(m, dp.w00); v10 = warp_sum52(m, dp.w10);
+                v01 = warp_sum52(m, dp.w01); v11 = warp_sum52(m, dp.w11);
+                own = (int)lane == ld;
+            }
+            big &= ~m;
+        }
+    }
+    if (own) {
+        int k = dp.k;
         if (REPL > 1) {
             // lanes whose node index is congruent to mine mod 8 share my banks; the r-th of them takes copy r
-            const unsigned act = __activemask();
-            const unsigned peers = __match_any_sync(act, k & 7);
+            const unsigned peers = __match_any_sync(__activemask(), k & 7);
             const int rank = __popc(peers & ((1u << (threadIdx.x & 31u)) - 1u));
             const int r = (((k & 7) + 8 * (rank & 3) - k) >> 3) & 3;            // bank (k + 8r) mod 32 == class + 8*rank
             k += r * ACC_COPY;
         }
-        add64_limbs(sLo, sHi, k, w00);
-        add64_limbs(sLo, sHi, k + WIN, w10);
-        add64_limbs(sLo, sHi, k + 1, w01);
-        add64_limbs(sLo, sHi, k + WIN + 1, w11);
-        return true;
+        add64_limbs(sLo, sHi, k, v00);
+        add64_limbs(sLo, sHi, k + WIN, v10);
+        add64_limbs(sLo, sHi, k + 1, v01);
+        add64_limbs(sLo, sHi, k + WIN + 1, v11);
+    } else if (dp.mode == 2) {
+        unsigned long long *g = reinterpret_cast<unsigned long long *>(acc) + ((long long)dp.i * c.niy + dp.j);
+        atomicAdd(g, dp.w00); atomicAdd(g + c.niy, dp.w10); atomicAdd(g + 1, dp.w01); atomicAdd(g + c.niy + 1, dp.w11);
     }
-    if (i <= c.nix - 2 && j <= c.niy - 2) {
-        unsigned long long *g = reinterpret_cast<unsigned long long *>(acc) + ((long long)i * c.niy + j);
-        atomicAdd(g, w00); atomicAdd(g + c.niy, w10); atomicAdd(g + 1, w01); atomicAdd(g + c.niy + 1, w11);
-    }
-    return false;
+    return dp.mode == 1;
 }
 
 // ---------------------------------------------------------------------------
@@ -655,7 +867,8 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
     unsigned extra = 0, outside = 0, same = 0;
 
     // everything that happens to particle k of the chunk
-    auto process = [&](int k, double &px, double &py, double &pvx, double &pvy, int &oi, int &oj) {
+    // act: the lanes of this warp that process a particle in this iteration (warp-cooperative deposit), 0 = unknown
+    auto process = [&](int k, double &px, double &py, double &pvx, double &pvy, int &oi, int &oj, unsigned act) {
         oi = oj = -1;
         if (MODE != 1) {
             extra += push_one(px, py, pvx, pvy, c, inv_dx, tc, sE, E, err, oi, oj);
@@ -663,7 +876,9 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
         }
         int ci = -1, cj = -1;
         if (MODE != 2) {
-            if (!deposit_one(px, py, c, inv_dx, tc, sLo, sHi, acc, scale, ci, cj)) outside++;
+            Deposit dp;
+            deposit_prepare(px, py, c, inv_dx, tc, scale, dp, ci, cj);
+            if (!deposit_commit(dp, act, c, sLo, sHi, acc)) outside++;
         } else if (in_box(px, py, c)) {
             double fi, fj;
             ci = floor_nonneg(to_logical_fast(px, c.dx, inv_dx), fi);
@@ -741,13 +956,14 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
             mbar_wait(&sFull[st], (uint32_t)((it / STAGES) & 1));
             const int k = it * MOVER_THREADS + tid;
             const bool live = k < count;
+            const unsigned act = __ballot_sync(0xffffffffu, live);
             double px = 0, py = 0, pvx = 0, pvy = 0;
             int oi = -1, oj = -1;
             if (live) {
                 const double *src = sP + (size_t)st * 4 * STAGE_W + (int)((ck.start + (long long)it * MOVER_THREADS) & 1ll) + tid;
                 px = src[0]; py = src[STAGE_W];
                 if (MODE != 1) { pvx = src[2 * STAGE_W]; pvy = src[3 * STAGE_W]; }
-                process(k, px, py, pvx, pvy, oi, oj);
+                process(k, px, py, pvx, pvy, oi, oj, act);
             }
             if (REBIN) {
                 // destination bin = bin of the position the push started from (same bin function as the histogram)
@@ -821,7 +1037,7 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
                 if (MODE != 1) { nvx = cvx[kn]; nvy = cvy[kn]; }
             }
             int oi, oj;
-            process(k, px, py, pvx, pvy, oi, oj);
+            process(k, px, py, pvx, pvy, oi, oj, 0u);       // per-thread trip counts: no warp-cooperative deposit here
             k = kn; px = nx; py = ny; pvx = nvx; pvy = nvy;
         }
     }

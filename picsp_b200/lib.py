@@ -68,6 +68,10 @@ def load_library():
         "picsp_species_download_rows": ([ctx, C.c_int, _dp], C.c_int),
         "picsp_grid_upload": ([ctx, C.c_int, _dp], C.c_int),
         "picsp_grid_download": ([ctx, C.c_int, _dp], C.c_int),
+        "picsp_dump_begin": ([ctx, _dp, _dp, _dp, _dp, _dp, _dp], C.c_int),
+        "picsp_dump_wait": ([ctx], C.c_int),
+        "picsp_host_alloc": ([C.c_size_t], C.c_void_p),
+        "picsp_host_free": ([C.c_void_p], None),
         "picsp_deposit": ([ctx, C.c_int], C.c_int),
         "picsp_compute_rho": ([ctx], C.c_int),
         "picsp_solve": ([ctx], C.c_int),
@@ -83,6 +87,7 @@ def load_library():
         "picsp_repush_count": ([ctx, C.c_int, _i64p], C.c_int),
         "picsp_straggler_count": ([ctx, C.c_int, _i64p], C.c_int),
         "picsp_set_sort_period": ([ctx, C.c_int, C.c_int], C.c_int),
+        "picsp_set_cell_sort_period": ([ctx, C.c_int, C.c_int], C.c_int),
         "picsp_comm_unique_id": ([C.c_void_p], C.c_int),
         "picsp_comm_attach": ([ctx, C.c_void_p, C.c_int, C.c_int], C.c_int),
         "picsp_species_fill_synthetic": ([ctx, C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_double], C.c_int),

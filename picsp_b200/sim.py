@@ -111,6 +111,27 @@ class Simulation:
         check(self.L.picsp_grid_download(self.ctx, GRID_IDS[name], _ptr(out)))
         return out
 
+    def dump_begin(self, rows_i=None, rows_e=None, den_i=None, den_e=None, phi=None, ke=None):
+        """picsp_dump_begin on caller-owned float64 buffers (numpy arrays or torch pinned tensors via .numpy());
+        they must stay alive and untouched until dump_wait()."""
+        self._dump_keep = (rows_i, rows_e, den_i, den_e, phi, ke)
+        args = [(_ptr(a) if a is not None else None) for a in self._dump_keep]
+        check(self.L.picsp_dump_begin(self.ctx, *args))
+
+    def dump_wait(self):
+        check(self.L.picsp_dump_wait(self.ctx))
+        self._dump_keep = None
+
+    def dump(self, root=True):
+        """One whole diagnostics dump (what writeSpecies x2 + writePot + computeKE x2 produce, main.cpp:507-527)."""
+        nn = self.nix * self.niy
+        out = {"rows_i": np.empty((self.count(ION), 4)), "rows_e": np.empty((self.count(ELECTRON), 4)), "ke": np.empty(2)}
+        if root:
+            out.update(den_i=np.empty(nn), den_e=np.empty(nn), phi=np.empty(nn))
+        self.dump_begin(out["rows_i"], out["rows_e"], out.get("den_i"), out.get("den_e"), out.get("phi"), out["ke"])
+        self.dump_wait()
+        return out
+
     def fill_synthetic(self, s, n, first_index=0, seed=0, vth=1.0, xdrift=0.0):
         check(self.L.picsp_species_fill_synthetic(self.ctx, s, n, first_index, seed, vth, xdrift))
 
@@ -154,6 +175,7 @@ class Simulation:
         return n.value
 
     def set_sort_period(self, s, period): check(self.L.picsp_set_sort_period(self.ctx, s, period))
+    def set_cell_sort_period(self, s, period): check(self.L.picsp_set_cell_sort_period(self.ctx, s, period))
 
     # -- multi-GPU ------------------------------------------------------------------------------
     @staticmethod

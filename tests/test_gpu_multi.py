@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle.oracle import ELECTRON, ION, Oracle, normalise
-from tests.helpers import GRIDS, relerr
+from tests.helpers import GRIDS, assert_grid_close, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -43,7 +43,10 @@ def _worker(rank, world, port, numx, n, solver, out_dir):
     dist.broadcast_object_list(uid, src=0)
     sim.comm_attach(uid[0], rank, world)
     sim.bootstrap(); sim.step(3)
-    out = {g: sim.grid(g) for g in ("rho", "phi", "efx", "efy")}
+    out = {g: sim.grid(g) for g in ("rho", "phi", "efx", "efy", "den_i", "den_e")}   # den_*: collective, global sum on every rank
+    d = sim.dump(root=(rank == 0))           # collective: den.i / den.e reduced to rank 0, phi on rank 0, KE global
+    for k, v in d.items():
+        out["dump_" + k] = v
     for s, nm_ in ((ION, "i"), (ELECTRON, "e")):
         out["part_" + nm_] = np.stack(sim.get_species(s))
         out["ke_" + nm_] = np.array([sim.computeKE(s)])
@@ -67,6 +70,18 @@ def test_two_ranks_equal_oracle(tmp_path, solver):
     for g in ("rho", "phi", "efx", "efy"):
         assert np.array_equal(res[0][g], res[1][g]), f"{g} differs between ranks (redundant solve must be bit-identical)"
         assert relerr(res[0][g], o.grid(g)) < 1e-11, g
+    # what a sharded run dumps (writeSpecies, main.cpp:1166-1172) is the density of ALL particles: the download is a
+    # collective that sums the per-rank partial densities, the asynchronous dump reduces them to rank 0
+    nix = numx + 1
+    for g in ("den_i", "den_e"):
+        assert np.array_equal(res[0][g], res[1][g]), f"{g}: the two ranks disagree on the global density"
+        assert_grid_close(res[0][g], o.grid(g), nix, nix, 1e-12, g)
+        assert np.array_equal(res[0]["dump_" + g], res[0][g]), f"dump {g} on rank 0 is not the global density"
+        assert "dump_" + g not in res[1].files
+    assert np.array_equal(res[0]["dump_phi"], res[0]["phi"])
+    for r in range(world):
+        assert np.array_equal(res[r]["dump_rows_e"].T, res[r]["part_e"]) and np.array_equal(res[r]["dump_rows_i"].T, res[r]["part_i"])
+        assert res[r]["dump_ke"][1] == res[r]["ke_e"][0] or abs(res[r]["dump_ke"][1] - res[r]["ke_e"][0]) <= 1e-13 * abs(res[r]["ke_e"][0])
     for s, nm_ in ((ION, "i"), (ELECTRON, "e")):
         want = np.stack(o.get_species(s))
         got = np.concatenate([res[r]["part_" + nm_] for r in range(world)], axis=1)

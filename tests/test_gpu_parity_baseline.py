@@ -1,0 +1,96 @@
+"""GPU: FULL-STEP parity with the oracle on the BASELINE.json configurations themselves.
+
+bootstrap + 3 loop bodies of the reference's main() (main.cpp:453-504), all six grids and the phase space of both
+species against oracle/ (the C restatement, bit-identical to the unmodified reference TU), at the grid sizes
+BASELINE.json names and with particle counts the CPU oracle finishes in seconds:
+
+  config 4   1024^2 cells, spectral, the reference's OWN loadType-2 two-stream load (main.cpp:597-615) from the
+             product's host loader (picsp_host_loader_fill, driftE = 0.2222): every particle on the diagonal,
+             ~2000 particles per occupied cell through the tiled path (warp-aggregated deposit)
+  config 3   512^2 cells, periodic SOR (the reference's only SOR semantics), 1e6 particles per species
+  config 5   2048^2 cells, spectral (2049 = 3 * 683: Bluestein), 2e6 particles per species
+  config 2   256^2 cells, spectral, the config's FULL 6 553 600 particles per species
+
+Tolerance: the north_star's 1e-12 relative (max-norm; interior and edge nodes separately) after the bootstrap and
+1e-11 after three chained steps; the measured errors are printed on success.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle.oracle import ELECTRON, ION, Oracle, normalise
+from picsp_b200 import Params, Simulation, host
+from picsp_b200.lib import CRunConfig
+from tests.helpers import GRIDS, assert_grid_close, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def run_config(numx, n, solver, load_type, drift_e, steps=3):
+    nm = normalise()
+    Oracle.lib().oracle_set_fft_mode(3)          # cached double-precision Bluestein (checked against the long-double engine)
+    try:
+        o = Oracle(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, vth_i=nm["vth_i"], vth_e=nm["vth_e"], solver=solver)
+        o.seed(0)
+        o.init(ION, load_type, 0.0); o.init(ELECTRON, load_type, drift_e)
+        # the product's own host loader must produce the same initial state, bit for bit
+        cfg = CRunConfig()
+        cfg.numxCells = cfg.numyCells = numx
+        cfg.nParticlesI = cfg.nParticlesE = n
+        cfg.loadType, cfg.solverType = load_type, solver
+        cfg.stepSize, cfg.timeStep = nm["dx"], nm["dt"]
+        cfg.vthI, cfg.vthE, cfg.driftI, cfg.driftE = nm["vth_i"], nm["vth_e"], 0.0, drift_e
+        loaded = host.load_species(cfg, seed=0)
+        for s in (ION, ELECTRON):
+            for a, b in zip(loaded[s], o.get_species(s)):
+                assert np.array_equal(a, b), "host loader differs from the oracle's loader"
+        report = {}
+        with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, solverType=solver)) as sim:
+            for s in (ION, ELECTRON):
+                sim.set_species(s, *loaded[s])
+            o.bootstrap(); sim.bootstrap()
+            for st in range(steps + 1):
+                if st:
+                    o.step(1); sim.step(1)
+                tol = 1e-12 if st == 0 else 1e-11
+                worst = 0.0
+                for name in GRIDS:
+                    worst = max(worst, assert_grid_close(sim.grid(name), o.grid(name), sim.nix, sim.niy, tol, f"step{st}/{name}"))
+                for s in (ION, ELECTRON):
+                    got, want = sim.get_species(s), o.get_species(s)
+                    for k, nmk in enumerate("x y vx vy".split()):
+                        e = relerr(got[k], want[k])
+                        assert e <= tol, f"step{st} species {s} {nmk}: rel err {e:.3e}"
+                        worst = max(worst, e)
+                    ke, want_ke = sim.computeKE(s), o.computeKE(s)
+                    assert abs(ke - want_ke) <= tol * abs(want_ke)
+                report["bootstrap" if st == 0 else f"step{st}"] = worst
+            report["extra_pushes_e"] = sim.repush_count(ELECTRON)
+            report["stragglers_e"] = sim.straggler_count(ELECTRON)
+        return report
+    finally:
+        Oracle.lib().oracle_set_fft_mode(0)
+
+
+def test_config4_grid_reference_two_stream_load():
+    """1024^2 spectral, loadType 2 (main.cpp:597-615): all particles on the diagonal, two counter-streaming beams."""
+    nm = normalise()
+    r = run_config(1024, 2_000_000, 1, 2, nm["drift_e"])
+    print("config 4 grid (1024^2, spectral, reference loadType-2 two-stream, 2e6/species): max rel err vs oracle", r)
+
+
+def test_config3_grid_sor():
+    r = run_config(512, 1_000_000, 2, 1, 0.0)
+    print("config 3 grid (512^2, periodic SOR, 1e6/species): max rel err vs oracle", r)
+
+
+def test_config5_grid_spectral():
+    r = run_config(2048, 2_000_000, 1, 1, 0.0)
+    print("config 5 grid (2048^2, spectral, 2e6/species): max rel err vs oracle", r)
+
+
+def test_config2_full_size():
+    """BASELINE config 2 at its full size: 256^2 cells, 100 particles per cell per species."""
+    r = run_config(256, 6_553_600, 1, 1, 0.0)
+    print("config 2 FULL SIZE (256^2, spectral, 6 553 600/species): max rel err vs oracle", r)

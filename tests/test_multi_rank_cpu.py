@@ -53,12 +53,20 @@ def _worker(rank, world, port, numx, n, out_dir):
         full.scatterSpecies(ION); full.scatterSpecies(ELECTRON)
     full.computeRho()
     err = np.abs(rho.numpy() - full.rho).max() / np.abs(full.rho).max()
+    # dump semantics (picsp_dump_begin): the per-rank partial densities reduced to rank 0 are the density
+    # the single-rank run dumps, edge nodes (folded twice) included
+    den_err = 0.0
+    for s in (ION, ELECTRON):
+        d = torch.from_numpy(part.den[s].copy())
+        dist.reduce(d, dst=0)
+        if rank == 0:
+            den_err = max(den_err, float(np.abs(d.numpy() - full.den[s]).max() / np.abs(full.den[s]).max()))
     # every rank then solves redundantly on identical input
     part.rho[...] = rho.numpy(); part.solve(); part.computeEF()
     phi = torch.from_numpy(part.phi.copy())
     ref = phi.clone(); dist.broadcast(ref, src=0)
     same_phi = bool(torch.equal(phi, ref))
-    np.save(os.path.join(out_dir, f"r{rank}.npy"), np.array([err, float(same_phi)]))
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), np.array([err, float(same_phi), den_err]))
     dist.destroy_process_group()
 
 
@@ -66,6 +74,7 @@ def test_partial_rho_allreduce_equals_single_rank(tmp_path):
     world, port = 2, _free_port()
     mp.spawn(_worker, args=(world, port, 24, 4001, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
-        err, same = np.load(tmp_path / f"r{r}.npy")
+        err, same, den_err = np.load(tmp_path / f"r{r}.npy")
         assert err < 1e-13, err
         assert same == 1.0
+        assert den_err < 1e-13, den_err
