@@ -255,40 +255,46 @@ def main_ours(args, rank, world, local_rank):
     n_species = int(args.particles) // 2
     lo, hi = shard_range(n_species, rank, world)
     n_local = hi - lo
-    sim = Simulation(Params(args.cells, args.cells, nm["dx"], nm["dt"], nm["mass_i"], n_species, n_species,
-                            solverType=1, device=local_rank, capacity=(n_local, n_local), flags=args.flags))
-    if args.load == "synthetic":
-        sim.fill_synthetic(ION, n_local, first_index=lo, seed=1, vth=nm["vth_i"], xdrift=0.0)
-        sim.fill_synthetic(ELECTRON, n_local, first_index=lo, seed=2, vth=nm["vth_e"], xdrift=nm["drift_e"])
-    else:
-        # the reference's loadType 2 through the product's host loader: a sequential recurrence over ALL particles
-        # (ions first, the stale x carried into the electrons); every rank generates it and keeps its range
-        from picsp_b200 import host
-        from picsp_b200.lib import CRunConfig
-        cfg = CRunConfig()
-        cfg.numxCells = cfg.numyCells = args.cells
-        cfg.nParticlesI = cfg.nParticlesE = n_species
-        cfg.loadType, cfg.solverType = 2, 1
-        cfg.stepSize, cfg.timeStep = nm["dx"], nm["dt"]
-        cfg.vthI, cfg.vthE, cfg.driftI, cfg.driftE = nm["vth_i"], nm["vth_e"], 0.0, nm["drift_e"]
-        t_load = time.perf_counter()
-        loaded = host.load_species(cfg, seed=0)
-        for s_ in (ION, ELECTRON):
-            sim.set_species(s_, *(a[lo:hi] for a in loaded[s_]))
-        del loaded
-        print(f"[bench] reference loadType-2 load generated and uploaded in {time.perf_counter() - t_load:.1f} s", file=sys.stderr)
-    if world > 1:
-        uid = [Simulation.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        sim.comm_attach(uid[0], rank, world)
-    if args.sort_period_e > 0:
-        sim.set_sort_period(ELECTRON, args.sort_period_e)
-    if args.sort_period_i > 0:
-        sim.set_sort_period(ION, args.sort_period_i)
-    if args.cell_period_e >= 0:
-        sim.set_cell_sort_period(ELECTRON, args.cell_period_e)
-    if args.cell_period_i >= 0:
-        sim.set_cell_sort_period(ION, args.cell_period_i)
+    def make_sim():
+        sim = Simulation(Params(args.cells, args.cells, nm["dx"], nm["dt"], nm["mass_i"], n_species, n_species,
+                                solverType=1, device=local_rank, capacity=(n_local, n_local), flags=args.flags))
+        if args.load == "synthetic":
+            sim.fill_synthetic(ION, n_local, first_index=lo, seed=1, vth=nm["vth_i"], xdrift=0.0)
+            sim.fill_synthetic(ELECTRON, n_local, first_index=lo, seed=2, vth=nm["vth_e"], xdrift=nm["drift_e"])
+        else:
+            # the reference's loadType 2 through the product's host loader: a sequential recurrence over ALL particles
+            # (ions first, the stale x carried into the electrons); every rank generates it and keeps its range
+            from picsp_b200 import host
+            from picsp_b200.lib import CRunConfig
+            cfg = CRunConfig()
+            cfg.numxCells = cfg.numyCells = args.cells
+            cfg.nParticlesI = cfg.nParticlesE = n_species
+            cfg.loadType, cfg.solverType = 2, 1
+            cfg.stepSize, cfg.timeStep = nm["dx"], nm["dt"]
+            cfg.vthI, cfg.vthE, cfg.driftI, cfg.driftE = nm["vth_i"], nm["vth_e"], 0.0, nm["drift_e"]
+            t_load = time.perf_counter()
+            loaded = host.load_species(cfg, seed=0)
+            for s_ in (ION, ELECTRON):
+                sim.set_species(s_, *(a[lo:hi] for a in loaded[s_]))
+            del loaded
+            print(f"[bench] reference loadType-2 load generated and uploaded in {time.perf_counter() - t_load:.1f} s", file=sys.stderr)
+        if world > 1:
+            u = [Simulation.comm_unique_id() if rank == 0 else None]     # one NCCL communicator per context
+            dist.broadcast_object_list(u, src=0)
+            sim.comm_attach(u[0], rank, world)
+        if args.sort_period_e > 0:
+            sim.set_sort_period(ELECTRON, args.sort_period_e)
+        if args.sort_period_i > 0:
+            sim.set_sort_period(ION, args.sort_period_i)
+        if args.cell_period_e >= 0:
+            sim.set_cell_sort_period(ELECTRON, args.cell_period_e)
+        if args.cell_period_i >= 0:
+            sim.set_cell_sort_period(ION, args.cell_period_i)
+        if args.agg is not None:
+            sim.set_deposit_aggregation(ION, args.agg); sim.set_deposit_aggregation(ELECTRON, args.agg)
+        return sim
+
+    sim = make_sim()
     sim.bootstrap()
     sim.profile_enable(True)
     sim.step(args.warmup)
@@ -340,8 +346,15 @@ def main_ours(args, rank, world, local_rank):
                                  "and of the KE partial sums only)"}
 
     # ---- end to end through the C ABI with host buffers ---------------------------------
+    # The e2e run starts from a FRESH context: in the reference's semantics the density is never cleared,
+    # which makes boxes of many Debye lengths unstable; at this noise level velocities run away after ~510 steps in
+    # total (profiles/r02_long_run_instability.md), so the e2e periods must not be stacked on top of the steps above.
     e2e = None
     if not args.no_e2e:
+        sim.close()
+        sim = make_sim()
+        sim.bootstrap()
+        sim.step(2); sim.sync()
         e2e = run_e2e(sim, args, n_local, barrier, max_over_ranks, torch, rank)
 
     cpu_baseline = None
@@ -395,6 +408,15 @@ def run_e2e(sim, args, n_local, barrier, max_over_ranks, torch, rank=0):
     steps, periods = args.e2e_steps, args.e2e_periods
     root = rank == 0
     null = dp()
+    # untimed: one dump with nothing else running (allocates the device snapshot; measures the copies alone)
+    sim.sync(); barrier()
+    ta = time.perf_counter()
+    check(sim.L.picsp_dump_begin(sim.ctx, ptr(blocks[0]), ptr(blocks[1]), ptr(grids[0]) if root else null,
+                                 ptr(grids[1]) if root else null, ptr(grids[2]) if root else null, ptr(ke)))
+    check(sim.L.picsp_dump_wait(sim.ctx))
+    dump_alone = max_over_ranks(time.perf_counter() - ta)
+    for s in range(2):   # the dump overwrote the blocks with rows: seed them again
+        check(sim.L.picsp_species_download(sim.ctx, s, *(ptr(t) for t in quarters[s])))
     barrier()
     t0 = time.perf_counter()
     for s in range(2):
@@ -422,7 +444,7 @@ def run_e2e(sim, args, n_local, barrier, max_over_ranks, torch, rank=0):
     return {"value": float(args.particles) * total_steps / dt, "unit": UNIT,
             "h2d_bytes_per_step": h2d / total_steps, "d2h_bytes_per_step": d2h / total_steps,
             "steps_per_dump": steps, "dump_periods": periods, "seconds": dt, "pinned_host_memory": pinned,
-            "upload_seconds": upload, "steady_state_seconds": steady,
+            "upload_seconds": upload, "steady_state_seconds": steady, "one_dump_alone_seconds": dump_alone,
             "steady_state_value": float(args.particles) * total_steps / steady,
             "seconds_rank0": {"upload": t1 - t0, "periods_enqueue_and_dump_waits": t2 - t1, "waiting_for_dumps": wait_s,
                               "last_dump_drain": t3 - t2},
@@ -460,9 +482,10 @@ def main():
     ap.add_argument("--cells", type=int, default=1024)
     ap.add_argument("--particles", type=float, default=1e9, help="total particles (both species, all ranks)")
     ap.add_argument("--e2e-steps", type=int, default=50, help="steps per dump period (the reference dumps every 50 steps, main.cpp:507)")
-    ap.add_argument("--e2e-periods", type=int, default=10, help="dump periods of the end-to-end measurement")
+    ap.add_argument("--e2e-periods", type=int, default=8, help="dump periods of the end-to-end measurement")
     ap.add_argument("--load", choices=["synthetic", "ref2"], default="synthetic",
                     help="particle load: bench-only device loader (uniform two-stream) or the reference's loadType 2 (diagonal) from the host loader")
+    ap.add_argument("--agg", type=int, default=None, choices=[-1, 0, 1], help="warp-aggregated deposit: -1 automatic (library default), 0 off, 1 on")
     ap.add_argument("--cell-period-e", type=int, default=-1, help="steps between electron cell orderings (-1: library default, 0: never)")
     ap.add_argument("--cell-period-i", type=int, default=-1, help="steps between ion cell orderings (-1: library default, 0: never)")
     ap.add_argument("--sort-period-e", type=int, default=0, help="steps between electron tile sorts (0: library default)")

@@ -69,7 +69,16 @@ enum {
     PICSP_FLAG_NO_FUSE       = 1 << 2,  /* push does not pre-accumulate the next step's deposit */
     PICSP_FLAG_SOR_SINGLE_CTA = 1 << 3, /* SOR: use the single-CTA anti-diagonal kernel for every sweep (cross-check path) */
     PICSP_FLAG_SEPARATE_SORT  = 1 << 4, /* periodic re-binning as a stand-alone pass instead of inside the mover (cross-check path) */
-    PICSP_FLAG_NO_GRAPH       = 1 << 5  /* picsp_step never replays captured CUDA graphs (cross-check path) */
+    PICSP_FLAG_NO_GRAPH       = 1 << 5, /* picsp_step never replays captured CUDA graphs (cross-check path) */
+    /* EXTENSION WITHOUT REFERENCE SEMANTICS (BASELINE.json config 3 "bounded domain with wall boundaries"): the reference
+     * is periodic-only; its README says "bounded" and main.cpp:826-843 / :1064-1108 are commented-out sketches of
+     * absorbing walls and a Dirichlet solver.  With this flag: no periodic fold of the densities; phi = 0 on the four
+     * walls and a red-black Gauss-Seidel/SOR iteration on the interior, run to an L2 residual of 1e-12 (solverType is
+     * ignored); E from central differences inside and full one-sided differences on the walls; a particle that leaves
+     * the box is absorbed (position NaN, velocity 0 from then on: skip NaN rows in a download).  Checked against the
+     * repo's own CPU restatement oracle/walls_check.c, which is NOT the reference.  Needs the tiled store
+     * (not combinable with PICSP_FLAG_NO_SORT); usually combined with PICSP_FLAG_CLEAR_DENSITY. */
+    PICSP_FLAG_WALLS          = 1 << 6
 };
 
 /* Normalised quantities, i.e. the reference's globals after parse_ini_file
@@ -145,14 +154,19 @@ int picsp_step(picsp_ctx *ctx, int nsteps);         /* nsteps bodies of the loop
 /* ---- diagnostics ------------------------------------------------------------- */
 int picsp_compute_ke(picsp_ctx *ctx, int species, double *ke);        /* computeKE  src/main.cpp:1190-1203 (summed over ranks when a communicator is attached) */
 int picsp_delta_phi(picsp_ctx *ctx, double *max_phi, double *phi0);   /* max(phi), phi[0]  src/main.cpp:509-516 */
-int picsp_repush_count(picsp_ctx *ctx, int species, int64_t *n);      /* extra pushes done by the last picsp_push (main.cpp:807-845) */
+int picsp_repush_count(picsp_ctx *ctx, int species, int64_t *n);      /* extra pushes done by the last picsp_push (main.cpp:807-845); with PICSP_FLAG_WALLS: particles it absorbed */
 int picsp_straggler_count(picsp_ctx *ctx, int species, int64_t *n);   /* particles of the last push/deposit that fell outside their tile window */
 /* Steps between two tile sorts of a species (default: electrons 8, ions 96; <= 0 restores the default). */
 int picsp_set_sort_period(picsp_ctx *ctx, int species, int period);
 /* Steps between two orderings of the particles by CELL inside their tile (makes the mover's field gathers broadcast and
- * its deposits warp-aggregated; storage order only, results are bit-identical).  0 = never; default: ions 64,
- * electrons 0 (thermal electrons lose the order within 2-3 steps); < 0 restores the default. */
+ * its deposits warp-aggregated; storage order only, results are bit-identical).  0 = never (the default: measured
+ * on B200 the ordered store halves the shared-memory traffic of the mover but the aggregation costs as many issue slots
+ * as it saves, profiles/r02_mover_aggregation.md). */
 int picsp_set_cell_sort_period(picsp_ctx *ctx, int species, int period);
+/* Warp-aggregated deposit (lanes of a warp whose particles share a cell combine their weights with REDUX before touching
+ * shared memory): -1 automatic (default: on for a cell-ordered store and for loads concentrated on few bins, such as the
+ * reference's diagonal loadType 2), 0 off, 1 on.  Speed only: integer accumulation makes the result bit-identical. */
+int picsp_set_deposit_aggregation(picsp_ctx *ctx, int species, int mode);
 
 /* ---- multi-GPU: particles sharded by index range, grid replicated ------------ */
 /* One communicator per rank; id is an NCCL unique id (128 bytes) created by rank 0
@@ -177,7 +191,9 @@ enum {
     PICSP_PHASE_PUSH = 5,      /* the mover (fused with the next deposit unless NO_FUSE) */
     PICSP_PHASE_SORT = 6,
     PICSP_PHASE_STEP = 7,      /* one whole picsp_step() call, first launch to last */
-    PICSP_PHASE_COUNT = 8
+    PICSP_PHASE_PUSH_IONS = 8, /* the mover launches of species 0 alone (also counted in PICSP_PHASE_PUSH) */
+    PICSP_PHASE_PUSH_ELECTRONS = 9,
+    PICSP_PHASE_COUNT = 10
 };
 int picsp_profile_enable(picsp_ctx *ctx, int on);                       /* CUDA events around every phase on the library's stream */
 int picsp_profile_get(picsp_ctx *ctx, int phase, double *ms, int64_t *calls); /* synchronises; accumulates since last reset */

@@ -44,6 +44,7 @@ PushConst push_const(const picsp_ctx *c, int s) {
     pc.xl = g.xl; pc.yl = g.yl;
     pc.nix = g.nix; pc.niy = g.niy; pc.ntx = g.ntx; pc.nty = g.nty;
     pc.nn = g.nn; pc.guard = g.guard;
+    pc.walls = (c->prm.flags & PICSP_FLAG_WALLS) ? 1 : 0; pc.pad_ = 0;
     return pc;
 }
 
@@ -110,7 +111,8 @@ void compute_frac(picsp_ctx *c, int s) {
     // the shared-memory limbs of the tiled path carry at most MAX_FRAC_TILED fraction bits
     const int nt = c->g.ntx * c->g.nty;
     PICSP_LAUNCH(c, k_frac_from_hist, (nt + 255) / 256, 256, 0, sp.hist, c->g.ntx, c->g.nty, sp.frac,
-                 tiled(c) ? MAX_FRAC_TILED : 60, sp.frac_scratch);
+                 tiled(c) ? MAX_FRAC_TILED : 60, sp.frac_scratch, (long long)sp.n,
+                 sp.aggregate == 0 ? -1 : ((sp.aggregate > 0 || sp.cell_period > 0) ? 1 : 0));
 }
 
 // -- tile binning -------------------------------------------------------------------------
@@ -404,6 +406,7 @@ void op_push(picsp_ctx *c, int s) {
     if (fuse || tile) ensure_hist(c, s);   // histogram of the positions about to be pushed -> bound for acc
     if (fuse) compute_frac(c, s);
     PhaseScope ph(c, PICSP_PHASE_PUSH);
+    PhaseScope phs(c, s == 0 ? PICSP_PHASE_PUSH_IONS : PICSP_PHASE_PUSH_ELECTRONS);
     PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
     const int nt = c->g.ntx * c->g.nty;
     if (fuse || tile) PICSP_CUDA(cudaMemsetAsync(sp.hist_next, 0, sizeof(unsigned int) * nt, c->stream));
@@ -549,11 +552,11 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
             Species &sp = c->sp[s];
             sp.cap = p->capacity[s]; sp.q = p->charge[s]; sp.m = p->mass[s]; sp.spwt = p->spwt[s];
             alloc_particle_set(&sp.x, &sp.y, &sp.vx, &sp.vy, sp.cap);
-            dalloc(&sp.den, g.nn); dalloc(&sp.acc, g.nn); dalloc(&sp.frac, 1); dalloc(&sp.frac_scratch, 2);
+            dalloc(&sp.den, g.nn); dalloc(&sp.acc, g.nn); dalloc(&sp.frac, 2); dalloc(&sp.frac_scratch, 3);
             dalloc(&sp.hist, (size_t)g.ntx * g.nty); dalloc(&sp.hist_next, (size_t)g.ntx * g.nty);
             dalloc(&sp.counters, 2);
             sp.sort_period = (s == 0) ? 96 : 8;     // steps between re-binnings (ions barely move; electrons: profiles/r01_sweeps.md)
-            sp.cell_period = (s == 0) ? 64 : 0;     // steps between cell orderings inside the bins (thermal electrons lose the order in 2-3 steps)
+            sp.cell_period = 0;                     // steps between cell orderings inside the bins: off (profiles/r02_mover_aggregation.md)
             sp.steps_since_cellsort = sp.cell_period;   // the first push after a load orders it
             sp.ntiles = g.ntx * g.nty;
             sp.max_chunks = sp.cap / 512 + (long long)g.ntx * g.nty + 1;   // 512 = smallest chunk pick_chunk() returns
@@ -564,8 +567,8 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
             PICSP_CUDA(cudaMemsetAsync(sp.nchunks, 0, sizeof(int), c->stream));
             PICSP_CUDA(cudaMemsetAsync(sp.den, 0, sizeof(double) * g.nn, c->stream));      // src/main.cpp:427,431
             PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * g.nn, c->stream));
-            PICSP_CUDA(cudaMemsetAsync(sp.frac, 0, sizeof(int), c->stream));
-            PICSP_CUDA(cudaMemsetAsync(sp.frac_scratch, 0, 2 * sizeof(unsigned long long), c->stream));
+            PICSP_CUDA(cudaMemsetAsync(sp.frac, 0, 2 * sizeof(int), c->stream));
+            PICSP_CUDA(cudaMemsetAsync(sp.frac_scratch, 0, 3 * sizeof(unsigned long long), c->stream));
             PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
         }
         dalloc(&c->rho, g.nn); dalloc(&c->phi, g.nn);
@@ -627,6 +630,8 @@ void picsp_destroy(picsp_ctx *c) {
     cudaFree(c->snap_rows[0]); cudaFree(c->snap_rows[1]); cudaFree(c->snap_grids); cudaFree(c->snap_ke);
     if (c->ev_snap) cudaEventDestroy(c->ev_snap);
     if (c->ev_dump_done) cudaEventDestroy(c->ev_dump_done);
+    if (c->ev_dump_done2) cudaEventDestroy(c->ev_dump_done2);
+    if (c->copy_stream2) { cudaStreamSynchronize(c->copy_stream2); cudaStreamDestroy(c->copy_stream2); }
     for (auto &t : c->timers) for (auto e : t.pool) cudaEventDestroy(e);
     for (int g = 0; g < c->step_graph_count; g++) cudaGraphExecDestroy(c->step_graphs[g].exec);
     for (cudaGraphExec_t g : c->retired_graphs) cudaGraphExecDestroy(g);
@@ -997,6 +1002,8 @@ static bool ensure_snapshot(picsp_ctx *c) {
     if (!c->ev_snap) {
         PICSP_CUDA(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
         PICSP_CUDA(cudaEventCreateWithFlags(&c->ev_dump_done, cudaEventDisableTiming));
+        PICSP_CUDA(cudaEventCreateWithFlags(&c->ev_dump_done2, cudaEventDisableTiming));
+        PICSP_CUDA(cudaStreamCreateWithFlags(&c->copy_stream2, cudaStreamNonBlocking));
     }
     return true;
 }
@@ -1007,6 +1014,7 @@ int picsp_dump_wait(picsp_ctx *c) {
     if (!c->dump_in_flight) return PICSP_OK;
     PICSP_CUDA(cudaSetDevice(c->prm.device));
     PICSP_CUDA(cudaEventSynchronize(c->ev_dump_done));
+    PICSP_CUDA(cudaEventSynchronize(c->ev_dump_done2));
     c->dump_in_flight = false;
     if (c->dump_ke_host)
         for (int s = 0; s < 2; s++)      // src/main.cpp:1198: 0.5*spwt*mass is ADDED (Q10); chargeE == 1 (:1201)
@@ -1069,10 +1077,15 @@ int picsp_dump_begin(picsp_ctx *c, double *rows_i, double *rows_e, double *den_i
             if (den[s]) PICSP_CUDA(cudaMemcpyAsync(den[s], c->snap_grids + (size_t)s * g.nn, gbytes, cudaMemcpyDeviceToHost, c->copy_stream));
         if (phi) PICSP_CUDA(cudaMemcpyAsync(phi, c->snap_grids + 2 * (size_t)g.nn, gbytes, cudaMemcpyDeviceToHost, c->copy_stream));
     }
+    // the two species' rows go out on two streams (two copy engines): under a memory-bound mover one engine alone
+    // does not fill the PCIe link
+    PICSP_CUDA(cudaStreamWaitEvent(c->copy_stream2, c->ev_snap, 0));
     for (int s = 0; s < 2; s++)
         if (rows[s] && c->sp[s].n > 0)
-            PICSP_CUDA(cudaMemcpyAsync(rows[s], c->snap_rows[s], sizeof(double) * 4 * (size_t)c->sp[s].n, cudaMemcpyDeviceToHost, c->copy_stream));
+            PICSP_CUDA(cudaMemcpyAsync(rows[s], c->snap_rows[s], sizeof(double) * 4 * (size_t)c->sp[s].n, cudaMemcpyDeviceToHost,
+                                       s == 0 ? c->copy_stream : c->copy_stream2));
     PICSP_CUDA(cudaEventRecord(c->ev_dump_done, c->copy_stream));
+    PICSP_CUDA(cudaEventRecord(c->ev_dump_done2, c->copy_stream2));
     c->dump_in_flight = true;
     c->dump_ke_host = ke2;
     PICSP_API_END
@@ -1159,8 +1172,16 @@ int picsp_set_sort_period(picsp_ctx *c, int s, int period) {
 int picsp_set_cell_sort_period(picsp_ctx *c, int s, int period) {
     PICSP_API_BEGIN
     check_ctx(c); check_species(s);
-    c->sp[s].cell_period = period >= 0 ? period : (s == 0 ? 64 : 0);
+    c->sp[s].cell_period = period > 0 ? period : 0;
     c->sp[s].steps_since_cellsort = c->sp[s].cell_period;       // due at the next push
+    PICSP_API_END
+}
+
+int picsp_set_deposit_aggregation(picsp_ctx *c, int s, int mode) {
+    PICSP_API_BEGIN
+    check_ctx(c); check_species(s);
+    PICSP_REQUIRE(mode >= -1 && mode <= 1, PICSP_ERR_INVALID, "aggregation mode must be -1 (automatic), 0 (off) or 1 (on)");
+    c->sp[s].aggregate = mode;
     PICSP_API_END
 }
 

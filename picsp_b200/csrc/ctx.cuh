@@ -69,8 +69,8 @@ struct Species {
     double q = 0, m = 0, spwt = 0;
     double *den = nullptr;         // nn, accumulating
     long long *acc = nullptr;      // nn, fixed-point deposit accumulator (order-independent => deterministic)
-    int *frac = nullptr;           // device scalar: fixed-point fraction bits acc was filled with
-    unsigned long long *frac_scratch = nullptr;   // [0] running max population, [1] CTA ticket (k_frac_from_hist)
+    int *frac = nullptr;           // device [2]: fixed-point fraction bits acc was filled with; warp-aggregated deposit on/off
+    unsigned long long *frac_scratch = nullptr;   // [0] running max neighbourhood population, [1] CTA ticket, [2] running max bin population (k_frac_from_hist)
     unsigned int *hist = nullptr;      // particles per tile at the positions currently stored
     unsigned int *hist_next = nullptr; // filled by the mover for the positions it writes
     bool hist_valid = false;
@@ -99,6 +99,7 @@ struct Species {
     bool staged_v_valid = false;   // vx2/vy2 hold the current velocities in upload order (left there by a download)
     // cell order inside a bin (k_cell_count / k_cell_scan / k_cell_permute)
     int cell_period = 0;           // steps between two cell orderings (0: never)
+    int aggregate = -1;            // warp-aggregated deposit: -1 automatic (cell-ordered store or concentrated load), 0 off, 1 on
     int steps_since_cellsort = 0;
     unsigned int *cell_cnt = nullptr;    // [chunks][CELLKEYS] populations, then first slots
     long long cell_cnt_chunks = 0;
@@ -173,7 +174,8 @@ struct picsp_ctx {
     int64_t snap_rows_cap[2] = {0, 0};
     double *snap_grids = nullptr;                // den_i | den_e | phi, nn each
     double *snap_ke = nullptr;                   // [2] sum(vx^2+vy^2) per species (summed over ranks)
-    cudaEvent_t ev_snap = nullptr, ev_dump_done = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_dump_done = nullptr, ev_dump_done2 = nullptr;
+    cudaStream_t copy_stream2 = nullptr;         // second copy engine for the electrons' rows
     bool dump_in_flight = false;
     double *dump_ke_host = nullptr;              // caller's [2]: the Q10 constant is added in picsp_dump_wait
     bool snapshot_unavailable = false;           // not enough memory for a snapshot: dumps are synchronous

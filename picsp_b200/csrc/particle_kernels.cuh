@@ -21,6 +21,8 @@ struct PushConst {
     int nix, niy;
     int ntx, nty;
     long long nn, guard;
+    int walls;        // PICSP_FLAG_WALLS (extension, no reference semantics): a particle that leaves the box is absorbed
+    int pad_;
 };
 
 // XtoL / YtoL, src/main.cpp:643-652: true division, x0 = y0 = 0.
@@ -151,33 +153,45 @@ __global__ void k_tile_hist(const double *__restrict__ x, const double *__restri
 // the fraction-bit count and resets the scratch for the next call.
 __global__ void __launch_bounds__(256)
 k_frac_from_hist(const unsigned int *__restrict__ hist, int ntx, int nty, int *__restrict__ frac, int cap,
-                 unsigned long long *__restrict__ scratch) {
-    __shared__ unsigned long long s_max[8];
-    unsigned long long m = 0;
+                 unsigned long long *__restrict__ scratch, long long n, int force_agg) {
+    __shared__ unsigned long long s_max[8], s_tmax[8];
+    unsigned long long m = 0, tm = 0;          // largest 5x5 neighbourhood, largest single tile
     const int wx = ntx < 5 ? ntx : 5, wy = nty < 5 ? nty : 5;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < ntx * nty) {
         const int tx = t / nty, ty = t % nty;
+        tm = hist[t];
         for (int a = 0; a < wx; a++)
             for (int b = 0; b < wy; b++) {
                 int ux = (tx - wx / 2 + a + 2 * ntx) % ntx, uy = (ty - wy / 2 + b + 2 * nty) % nty;
                 m += hist[ux * nty + uy];
             }
     }
-    for (int o = 16; o > 0; o >>= 1) { unsigned long long v = __shfl_xor_sync(0xffffffffu, m, o); m = v > m ? v : m; }
-    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long v = __shfl_xor_sync(0xffffffffu, m, o); m = v > m ? v : m;
+        v = __shfl_xor_sync(0xffffffffu, tm, o); tm = v > tm ? v : tm;
+    }
+    if ((threadIdx.x & 31) == 0) { s_max[threadIdx.x >> 5] = m; s_tmax[threadIdx.x >> 5] = tm; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 0; w < (blockDim.x + 31) / 32; w++) m = s_max[w] > m ? s_max[w] : m;
+        for (int w = 0; w < (blockDim.x + 31) / 32; w++) { m = s_max[w] > m ? s_max[w] : m; tm = s_tmax[w] > tm ? s_tmax[w] : tm; }
         atomicMax(&scratch[0], m);
+        atomicMax(&scratch[2], tm);
         __threadfence();
         if (atomicAdd(&scratch[1], 1ull) == (unsigned long long)gridDim.x - 1) {   // last CTA
             __threadfence();
             const unsigned long long mx = atomicExch(&scratch[0], 0ull);
+            const unsigned long long tmx = atomicExch(&scratch[2], 0ull);
             scratch[1] = 0ull;
             const int bits = 64 - __clzll((long long)(mx | 1ull));
             const int f = 62 - bits;
-            *frac = f > cap ? cap : (f < 0 ? 0 : f);
+            frac[0] = f > cap ? cap : (f < 0 ? 0 : f);
+            // frac[1]: the mover combines the deposits of the lanes of a warp that share a cell before they touch shared
+            // memory (deposit_commit).  Worth its instructions only when whole warps share cells: a cell-ordered store
+            // (force_agg), or a load concentrated on few bins — the busiest bin holds more than 8x its fair share,
+            // e.g. the reference's diagonal two-stream load (src/main.cpp:597-615): 64 of 4096 bins occupied.
+            const long long fair = n / ((long long)ntx * nty) + 1;
+            frac[1] = (force_agg > 0 || (force_agg == 0 && (long long)tmx > 8 * fair + 4096)) ? 1 : 0;      // force_agg: 1 on, 0 automatic, -1 off
         }
     }
 }

@@ -614,6 +614,7 @@ __device__ __forceinline__ int push_one(double &px, double &py, double &pvx, dou
             }
         }
         if (!done_fast) { // straggler, wrapped or out-of-box position
+            if (c.walls && px != px) break;      // walls extension: an absorbed particle (position NaN) stays where it is
             const Straggler r = gather_straggler(E, px, py, c.dx, inv_dx, c.xl, c.yl, c.nix, c.niy, c.nn, c.guard);
             e.x = r.ex; e.y = r.ey;
             if (iter == 0) { oi = r.i; oj = r.j; }
@@ -625,6 +626,13 @@ __device__ __forceinline__ int push_one(double &px, double &py, double &pvx, dou
         // src/main.cpp:807-845: exactly one wrap per push, then push again.  Common case first:
         // both coordinates inside the box means none of the four tests fires.
         if (in_range_bits(px, tc.xl_bits) && in_range_bits(py, tc.yl_bits)) break;
+        if (c.walls) {
+            // Extension (PICSP_FLAG_WALLS; the reference is periodic-only, its absorbing wall is a commented-out sketch at
+            // src/main.cpp:826-843): a particle that leaves the box is absorbed — position NaN, velocity 0: it never
+            // deposits, never gathers, never moves again and adds nothing to the kinetic energy.
+            if (!in_box(px, py, c)) { px = py = __longlong_as_double(0x7FF8000000000000ll); pvx = pvy = 0.0; extra++; }
+            break;
+        }
         if (px < 0.0) px += c.xl;
         else if (px >= c.xl) px -= c.xl;
         else if (py < 0.0) py += c.yl;
@@ -717,11 +725,11 @@ __device__ __forceinline__ unsigned long long warp_sum52(unsigned m, unsigned lo
 // ~5e5 particles per occupied cell): one MATCH finds the lanes per cell, the fixed-point weights of a
 // group are summed exactly with REDUX and its first lane alone touches the accumulators.  Integer sums: the
 // result is bit-identical to the lane-by-lane deposit.  Returns true when the deposit stayed inside the window.
-__device__ __forceinline__ bool deposit_commit(const Deposit &dp, unsigned act, const PushConst &c, unsigned *sLo, unsigned *sHi,
-                                               long long *__restrict__ acc) {
+__device__ __forceinline__ bool deposit_commit(const Deposit &dp, unsigned act, bool aggregate, const PushConst &c, unsigned *sLo,
+                                               unsigned *sHi, long long *__restrict__ acc) {
     unsigned long long v00 = dp.w00, v10 = dp.w10, v01 = dp.w01, v11 = dp.w11;
     bool own = dp.mode == 1;
-    if (PICSP_AGG_ROUNDS > 0 && act == 0xffffffffu) {       // full warps only; the tail slice of a chunk takes the plain path
+    if (PICSP_AGG_ROUNDS > 0 && aggregate && act == 0xffffffffu) {       // full warps only; the tail slice of a chunk takes the plain path
         const unsigned lane = threadIdx.x & 31u;
         const int key = dp.mode == 1 ? dp.k : -1 - (int)lane;                 // lanes without a window deposit match nobody
         const unsigned peers = __match_any_sync(0xffffffffu, key);
@@ -863,7 +871,8 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
     const int count = ck.count;
     const bool nbr_ok = (c.ntx >= 3 && c.nty >= 3);
     const double inv_dx = 1.0 / c.dx;
-    const double scale = (MODE != 2) ? exp2((double)*frac) : 0.0;
+    const double scale = (MODE != 2) ? exp2((double)frac[0]) : 0.0;
+    const bool aggregate = (MODE != 2) && frac[1] != 0;      // CTA-uniform: decided by k_frac_from_hist
     unsigned extra = 0, outside = 0, same = 0;
 
     // everything that happens to particle k of the chunk
@@ -878,7 +887,7 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
         if (MODE != 2) {
             Deposit dp;
             deposit_prepare(px, py, c, inv_dx, tc, scale, dp, ci, cj);
-            if (!deposit_commit(dp, act, c, sLo, sHi, acc)) outside++;
+            if (!deposit_commit(dp, act, aggregate, c, sLo, sHi, acc)) outside++;
         } else if (in_box(px, py, c)) {
             double fi, fj;
             ci = floor_nonneg(to_logical_fast(px, c.dx, inv_dx), fi);
@@ -910,7 +919,7 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
                 // the fixed-point scale assumes no particle moves more than one tile in ONE step
                 const int ox = oi >= 0 ? min((int)((unsigned)oi / TILE), tc.ntx1) : 0;
                 const int oy = oi >= 0 ? min((int)((unsigned)oj / TILE), tc.nty1) : 0;
-                if (ox != ux || oy != uy) {
+                if ((ox != ux || oy != uy) && !(c.walls && ci < 0)) {        // an absorbed particle is filed under bin 0: not a displacement
                     int ax = abs(ux - ox), ay = abs(uy - oy);
                     ax = min(ax, c.ntx - ax); ay = min(ay, c.nty - ay);
                     if (ax > 1 || ay > 1) atomicOr(err, ERR_BIT_DISPLACEMENT);

@@ -88,6 +88,7 @@ def load_library():
         "picsp_straggler_count": ([ctx, C.c_int, _i64p], C.c_int),
         "picsp_set_sort_period": ([ctx, C.c_int, C.c_int], C.c_int),
         "picsp_set_cell_sort_period": ([ctx, C.c_int, C.c_int], C.c_int),
+        "picsp_set_deposit_aggregation": ([ctx, C.c_int, C.c_int], C.c_int),
         "picsp_comm_unique_id": ([C.c_void_p], C.c_int),
         "picsp_comm_attach": ([ctx, C.c_void_p, C.c_int, C.c_int], C.c_int),
         "picsp_species_fill_synthetic": ([ctx, C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_double], C.c_int),

