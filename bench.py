@@ -210,12 +210,17 @@ def workload_config(args, n_local):
     load = ("synthetic two-stream electrons + cold ions uniform in the box (bench-only device loader)" if args.load == "synthetic" else
             "the reference's own loadType-2 two-stream load (main.cpp:597-615, host loader picsp_host_loader_fill): every particle "
             "on the domain diagonal")
+    bounded = bool(getattr(args, "walls", False))
     cfg = {
-        "workload": (f"{load}, {args.cells}x{args.cells} cells periodic "
-                     f"({args.cells + 1}^2 nodes), spectral solver, {args.particles:.3g} particles total "
-                     f"({args.particles // 2} per species), BASELINE.json configs[3]"),
+        "workload": ((f"{load}, {args.cells}x{args.cells} cells periodic "
+                      f"({args.cells + 1}^2 nodes), spectral solver, {args.particles:.3g} particles total "
+                      f"({args.particles // 2} per species), BASELINE.json configs[3]") if not bounded else
+                     (f"{load}, {args.cells}x{args.cells} cells BOUNDED ({args.cells + 1}^2 nodes): absorbing walls, phi = 0 on the walls, "
+                      f"red-black Gauss-Seidel/SOR to an L2 residual of 1e-12, density cleared every step, {args.particles:.3g} particles "
+                      f"total; BASELINE.json configs[2] as an EXTENSION WITHOUT REFERENCE SEMANTICS (the reference is periodic-only)")),
         "load": args.load,
-        "cells": args.cells, "particles_total": int(args.particles), "solver": "spectral (cuFFT D2Z/Z2D)",
+        "cells": args.cells, "particles_total": int(args.particles),
+        "solver": "red-black SOR, Dirichlet walls (k_rb_sor, one cooperative launch)" if bounded else "spectral (cuFFT D2Z/Z2D)",
         "sharding": f"particles by index range over {args.gpus} rank(s), grid replicated, 1 NCCL all-reduce of rho per step",
         "l2_policy": "inputs exceed L2 (particle state per rank >> 126 MB); no explicit flush",
     }
@@ -485,6 +490,8 @@ def main():
     ap.add_argument("--e2e-periods", type=int, default=8, help="dump periods of the end-to-end measurement")
     ap.add_argument("--load", choices=["synthetic", "ref2"], default="synthetic",
                     help="particle load: bench-only device loader (uniform two-stream) or the reference's loadType 2 (diagonal) from the host loader")
+    ap.add_argument("--walls", action="store_true", help="BASELINE.json configs[2]: bounded domain (PICSP_FLAG_WALLS | PICSP_FLAG_CLEAR_DENSITY): "
+                    "absorbing walls, Dirichlet red-black SOR; extension WITHOUT reference semantics")
     ap.add_argument("--agg", type=int, default=None, choices=[-1, 0, 1], help="warp-aggregated deposit: -1 automatic (library default), 0 off, 1 on")
     ap.add_argument("--cell-period-e", type=int, default=-1, help="steps between electron cell orderings (-1: library default, 0: never)")
     ap.add_argument("--cell-period-i", type=int, default=-1, help="steps between ion cell orderings (-1: library default, 0: never)")
@@ -498,6 +505,8 @@ def main():
                     help="dram bytes per launch of the dominant kernel from the committed ncu --set full capture")
     args = ap.parse_args()
     args.particles = int(args.particles)
+    if args.walls:
+        args.flags |= 64 | 1
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

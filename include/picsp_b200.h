@@ -145,6 +145,9 @@ int picsp_compute_rho(picsp_ctx *ctx);              /* computeRho               
 int picsp_solve(picsp_ctx *ctx);                    /* the solverType switch     src/main.cpp:492-497 */
 int picsp_solve_spectral(picsp_ctx *ctx);           /* spectralPotentialSolver   src/main.cpp:960-1058 */
 int picsp_solve_sor(picsp_ctx *ctx, int64_t *sweeps, double *l2); /* solvePotential src/main.cpp:904-957 (outputs may be NULL) */
+/* Sweeps and residual of the last iterative solve (periodic SOR or the PICSP_FLAG_WALLS red-black SOR; negative sweeps:
+ * the cap was hit).  Host-synchronous. */
+int picsp_solve_status(picsp_ctx *ctx, int64_t *sweeps, double *l2);
 int picsp_compute_ef(picsp_ctx *ctx);               /* computeEF                 src/main.cpp:1111-1139 */
 int picsp_push(picsp_ctx *ctx, int species);        /* pushSpecies (+gather)     src/main.cpp:772-847, :671-681 */
 int picsp_rewind(picsp_ctx *ctx, int species);      /* rewindSpecies             src/main.cpp:850-866 */

@@ -375,3 +375,89 @@ class Reference(_Base):
             out[("@" if is_attr else "") + name] = a
         out["#groups"] = [L.picsp_ref_h5_group_name(i).decode() for i in range(L.picsp_ref_h5_group_count())]
         return out
+
+
+class WallsChecker:
+    """oracle/libpicsp_walls_check.so — the repository's OWN CPU restatement of the PICSP_FLAG_WALLS extension
+    (Dirichlet red-black SOR, absorbing walls).  NOT the reference: the reference has no bounded-domain semantics
+    (see oracle/walls_check.c).  Same call names as ``Oracle`` where they apply."""
+
+    WALLS_SO = os.path.join(HERE, "libpicsp_walls_check.so")
+    TOL, BATCH, MAX_SWEEPS = 1e-12, 16, 100000
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            if not os.path.isfile(cls.WALLS_SO):
+                build(ref=False)
+            L = C.CDLL(cls.WALLS_SO)
+            L.walls_deposit.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, C.c_long, C.c_double, C.c_int]
+            L.walls_rho.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double]
+            L.walls_omega.argtypes = [C.c_int, C.c_int]; L.walls_omega.restype = C.c_double
+            L.walls_rb_sor.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, C.c_double, C.c_double, C.c_long, C.c_int, C.c_long, _dp]
+            L.walls_rb_sor.restype = C.c_long
+            L.walls_ef.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp]
+            L.walls_push.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _dp, _dp, C.c_long,
+                                     C.c_double, C.c_double, C.c_int]
+            L.walls_push.restype = C.c_long
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, numx, numy, dx, dt, mass_i, n_i, n_e, clear=True):
+        self.L = self.lib()
+        self.numx, self.numy, self.nix, self.niy = int(numx), int(numy), int(numx) + 1, int(numy) + 1
+        self.dx, self.dt, self.clear = float(dx), float(dt), bool(clear)
+        self.mass, self.charge = [float(mass_i), 1.0], [1.0, -1.0]
+        self.spwt = [(1.0 * self.numx * self.numy * self.dx * self.dx) / n for n in (n_i, n_e)]
+        nn = self.nix * self.niy
+        self.den = [np.zeros(nn), np.zeros(nn)]
+        self.rho, self.phi, self.efx, self.efy = (np.zeros(nn) for _ in range(4))
+        self.part = [None, None]
+        self.omega = self.L.walls_omega(self.numx, self.numy)
+        self.last_sweeps, self.last_l2, self.absorbed = 0, 0.0, [0, 0]
+
+    def set_species(self, s, x, y, vx, vy):
+        self.part[s] = [np.ascontiguousarray(a, dtype=np.float64).copy() for a in (x, y, vx, vy)]
+
+    def get_species(self, s):
+        return tuple(a.copy() for a in self.part[s])
+
+    def grid(self, name):
+        return {"den_i": self.den[0], "den_e": self.den[1]}.get(name, getattr(self, name, None))
+
+    def scatterSpecies(self, s):
+        x, y = self.part[s][:2]
+        self.L.walls_deposit(self.nix, self.niy, self.dx, _ptr(self.den[s]), _ptr(x), _ptr(y), len(x), self.spwt[s], int(self.clear))
+
+    def computeRho(self):
+        self.L.walls_rho(self.nix, self.niy, _ptr(self.rho), _ptr(self.den[0]), _ptr(self.den[1]), self.charge[0], self.charge[1])
+
+    def solve(self, fixed_sweeps=0):
+        l2 = np.zeros(1)
+        self.last_sweeps = self.L.walls_rb_sor(self.nix, self.niy, self.dx, _ptr(self.phi), _ptr(self.rho), self.omega, self.TOL,
+                                               self.MAX_SWEEPS, self.BATCH, int(fixed_sweeps), _ptr(l2))
+        self.last_l2 = float(l2[0])
+
+    def computeEF(self):
+        self.L.walls_ef(self.nix, self.niy, self.dx, _ptr(self.phi), _ptr(self.efx), _ptr(self.efy))
+
+    def _push(self, s, half):
+        x, y, vx, vy = self.part[s]
+        return self.L.walls_push(self.nix, self.niy, self.dx, self.dt, _ptr(self.efx), _ptr(self.efy), _ptr(x), _ptr(y), _ptr(vx),
+                                 _ptr(vy), len(x), self.charge[s], self.mass[s], int(half))
+
+    def pushSpecies(self, s):
+        self.absorbed[s] = self._push(s, 0)
+        return self.absorbed[s]
+
+    def rewindSpecies(self, s):
+        self._push(s, 1)
+
+    def bootstrap(self, sweeps=0):
+        self.scatterSpecies(ION); self.scatterSpecies(ELECTRON); self.computeRho(); self.solve(sweeps); self.computeEF()
+        self.rewindSpecies(ION); self.rewindSpecies(ELECTRON)
+
+    def step(self, sweeps=0):
+        self.scatterSpecies(ION); self.scatterSpecies(ELECTRON); self.computeRho(); self.solve(sweeps); self.computeEF()
+        self.pushSpecies(ION); self.pushSpecies(ELECTRON)

@@ -105,6 +105,7 @@ void ensure_hist(picsp_ctx *c, int s) {
     sp.hist_valid = true;
 }
 bool tiled(const picsp_ctx *c) { return !(c->prm.flags & PICSP_FLAG_NO_SORT); }
+bool walls(const picsp_ctx *c) { return (c->prm.flags & PICSP_FLAG_WALLS) != 0; }
 
 void compute_frac(picsp_ctx *c, int s) {
     Species &sp = c->sp[s];
@@ -309,7 +310,7 @@ void op_deposit(picsp_ctx *c, int s) {
     const double weight = sp.spwt / (g.dx * g.dx);   // value/dxdy, src/main.cpp:657,664
     const int clear = (c->prm.flags & PICSP_FLAG_CLEAR_DENSITY) ? 1 : 0;
     PICSP_LAUNCH(c, k_deposit_finalize, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, sp.den, sp.acc, sp.frac, weight, g.nn, clear);
-    PICSP_LAUNCH(c, k_fold_periodic, 1, 1024, 0, sp.den, g.nix, g.niy);
+    if (!walls(c)) PICSP_LAUNCH(c, k_fold_periodic, 1, 1024, 0, sp.den, g.nix, g.niy);
     sp.acc_valid = false;
 }
 
@@ -330,6 +331,10 @@ void op_grid_phase(picsp_ctx *c) {
             sp.acc_valid = false;
         }
         const int clear = (c->prm.flags & PICSP_FLAG_CLEAR_DENSITY) ? 1 : 0;
+        if (walls(c))
+            PICSP_LAUNCH(c, k_grid_phase_walls, blocks_for(g.nn, 256, c->num_sms * 32), 256, 0, gs[0], gs[1], c->rho, g.nix, g.niy, clear,
+                         c->d_error, c->h_error_mapped);
+        else
         PICSP_LAUNCH(c, k_grid_phase, blocks_for(g.nn, 256, c->num_sms * 32), 256, 0, gs[0], gs[1], c->rho, g.nix, g.niy, clear,
                      c->d_error, c->h_error_mapped);   // one node per thread up to 1.2M nodes: latency-bound otherwise
     }
@@ -347,7 +352,8 @@ void op_compute_rho(picsp_ctx *c) {
     if (c->comm) op_allreduce_rho(c);
     {
         PhaseScope ph(c, PICSP_PHASE_RHO);
-        PICSP_LAUNCH(c, k_fold_periodic, 1, 1024, 0, c->rho, g.nix, g.niy);
+        if (walls(c)) PICSP_LAUNCH(c, k_zero_walls, 8, 256, 0, c->rho, g.nix, g.niy);
+        else PICSP_LAUNCH(c, k_fold_periodic, 1, 1024, 0, c->rho, g.nix, g.niy);
     }
 }
 
@@ -379,15 +385,41 @@ void op_solve_sor(picsp_ctx *c) {
     }
 }
 
+// PICSP_FLAG_WALLS: Dirichlet red-black SOR to a residual of WALLS_TOL, one cooperative launch (extension, no reference)
+constexpr double WALLS_TOL = 1e-12;
+constexpr int WALLS_BATCH = 16, WALLS_MAX_SWEEPS = 100000;
+void op_solve_walls(picsp_ctx *c) {
+    PhaseScope ph(c, PICSP_PHASE_SOLVE);
+    const Geom &g = c->g;
+    if (c->walls_grid == 0) {
+        int per_sm = 0;
+        PICSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rb_sor, 256, 0));
+        PICSP_REQUIRE(per_sm > 0, PICSP_ERR_CUDA, "k_rb_sor cannot be made resident");
+        const long long want = ((long long)(g.nix - 2) * ((g.niy - 1) / 2) + 255) / 256;      // one node of a colour per thread
+        c->walls_grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)std::min(per_sm, 4) * c->num_sms));
+        dalloc(&c->d_walls_partial, (size_t)c->walls_grid);
+    }
+    double *phi = c->phi; const double *rho = c->rho;
+    int nix = g.nix, niy = g.niy, max_sweeps = WALLS_MAX_SWEEPS, batch = WALLS_BATCH;
+    double dx = g.dx, omega = c->walls_omega, tol = WALLS_TOL;
+    long long *status = c->d_sor_status; double *l2 = c->d_scalars + 3, *partial = c->d_walls_partial;
+    void *args[] = {&phi, &rho, &nix, &niy, &dx, &omega, &tol, &max_sweeps, &batch, &status, &l2, &partial};
+    PICSP_CUDA(cudaLaunchCooperativeKernel((const void *)k_rb_sor, dim3(c->walls_grid), dim3(256), args, 0, c->stream));
+    c->launches++;
+    c->busy[0] = c->busy[1] = true;
+}
+
 void op_solve(picsp_ctx *c) {
-    if (c->prm.solverType == PICSP_SOLVER_SPECTRAL) op_solve_spectral(c);
+    if (walls(c)) op_solve_walls(c);
+    else if (c->prm.solverType == PICSP_SOLVER_SPECTRAL) op_solve_spectral(c);
     else op_solve_sor(c);
 }
 
 void op_compute_ef(picsp_ctx *c) {
     PhaseScope ph(c, PICSP_PHASE_EF);
     const Geom &g = c->g;
-    PICSP_LAUNCH(c, k_compute_ef, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, c->phi, c->E, g.nix, g.niy, g.dx, g.dx);
+    if (walls(c)) PICSP_LAUNCH(c, k_compute_ef_walls, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, c->phi, c->E, g.nix, g.niy, g.dx);
+    else PICSP_LAUNCH(c, k_compute_ef, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, c->phi, c->E, g.nix, g.niy, g.dx, g.dx);
 }
 
 void op_push(picsp_ctx *c, int s) {
@@ -521,6 +553,8 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
         PICSP_REQUIRE(p->solverType == PICSP_SOLVER_SPECTRAL || p->solverType == PICSP_SOLVER_SOR, PICSP_ERR_INVALID,
                       "solverType must be 1 (spectral) or 2 (SOR)");   // src/main.cpp:310
         PICSP_REQUIRE(p->capacity[0] >= 0 && p->capacity[1] >= 0, PICSP_ERR_INVALID, "negative capacity");
+        PICSP_REQUIRE(!((p->flags & PICSP_FLAG_WALLS) && (p->flags & PICSP_FLAG_NO_SORT)), PICSP_ERR_INVALID,
+                      "PICSP_FLAG_WALLS needs the tiled store (not combinable with PICSP_FLAG_NO_SORT)");
         PICSP_REQUIRE(p->capacity[0] <= 0xFFFFFFFFll && p->capacity[1] <= 0xFFFFFFFFll, PICSP_ERR_INVALID,
                       "per-rank species capacity is limited to 2^32-1 particles");
         int ndev = 0;
@@ -542,6 +576,8 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
         g.nn = (long long)g.nix * g.niy;
         g.guard = 4ll * g.niy + 8;
         g.ntx = (g.ncx + TILE - 1) / TILE; g.nty = (g.ncy + TILE - 1) / TILE;
+        // optimal over-relaxation of the 5-point Dirichlet problem on the larger grid extent
+        c->walls_omega = 2.0 / (1.0 + std::sin(3.14159265358979323846 / (double)std::max(g.ncx, g.ncy)));
 
         cudaDeviceProp prop;
         PICSP_CUDA(cudaGetDeviceProperties(&prop, p->device));
@@ -624,6 +660,7 @@ void picsp_destroy(picsp_ctx *c) {
         cudaFree(sp.cell_cnt); cudaFree(sp.tile_chunk0);
     }
     cudaFree(c->rho); cudaFree(c->phi); cudaFree(c->E_alloc); cudaFree(c->rhok); cudaFree(c->phik);
+    cudaFree(c->d_walls_partial);
     cudaFree(c->d_red); cudaFree(c->d_scalars); cudaFree(c->d_sor_status); cudaFree(c->d_sor_progress); cudaFree(c->d_error); cudaFree(c->stage);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_error_mapped) cudaFreeHost(c->h_error_mapped);
@@ -854,6 +891,17 @@ int picsp_solve_sor(picsp_ctx *c, int64_t *sweeps, double *l2) {
     }
     PICSP_API_END
 }
+int picsp_solve_status(picsp_ctx *c, int64_t *sweeps, double *l2) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    long long *h = reinterpret_cast<long long *>(c->h_pinned + 16);
+    PICSP_CUDA(cudaMemcpyAsync(h, c->d_sor_status, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    const double v = read_scalar(c, c->d_scalars + 3);
+    if (sweeps) *sweeps = *h;
+    if (l2) *l2 = v;
+    PICSP_API_END
+}
 int picsp_compute_ef(picsp_ctx *c) { PICSP_OP(op_compute_ef(c)) }
 int picsp_push(picsp_ctx *c, int s) { PICSP_OP(check_species(s); op_push(c, s)) }
 int picsp_rewind(picsp_ctx *c, int s) { PICSP_OP(check_species(s); op_rewind(c, s)) }
@@ -874,7 +922,7 @@ static void one_step(picsp_ctx *c) {
 constexpr long long STEP_GRAPH_MAX_PARTICLES = 1ll << 26;   // above this a step is >= 1 ms of kernels and the launches hide behind them
 
 static bool step_graph_eligible(const picsp_ctx *c) {
-    if (c->profiling || c->comm || c->graphs_disabled || (c->prm.flags & (PICSP_FLAG_NO_GRAPH | PICSP_FLAG_NO_FUSE | PICSP_FLAG_NO_SORT))) return false;
+    if (c->profiling || c->comm || c->graphs_disabled || (c->prm.flags & (PICSP_FLAG_NO_GRAPH | PICSP_FLAG_NO_FUSE | PICSP_FLAG_NO_SORT | PICSP_FLAG_WALLS))) return false;
     if (c->sp[0].n + c->sp[1].n > STEP_GRAPH_MAX_PARTICLES) return false;
     for (int s = 0; s < 2; s++) {
         const Species &sp = c->sp[s];

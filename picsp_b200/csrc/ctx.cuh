@@ -133,6 +133,9 @@ struct picsp_ctx {
     double *d_scalars = nullptr;    // [0..7] results (ke, maxphi, phi0, sor l2, ...)
     long long *d_sor_status = nullptr;
     int *d_sor_progress = nullptr;  // per-band column progress of the pipelined SOR sweep
+    double *d_walls_partial = nullptr;   // PICSP_FLAG_WALLS: per-CTA residual partials of k_rb_sor
+    int walls_grid = 0;             // its cooperative grid (co-resident CTAs)
+    double walls_omega = 1.0;
     int *d_error = nullptr;         // sticky device-side error flag
     double *h_pinned = nullptr;     // small pinned staging for scalar read-backs
 

@@ -2,6 +2,8 @@
 //
 // Each kernel names the reference statements it replaces (/root/reference/src/main.cpp).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "ctx.cuh"
 
 namespace picsp {
@@ -410,6 +412,125 @@ __global__ void k_sor_residual_final(const double *__restrict__ partial, int n, 
         double L2 = sqrt(t) / (nix * niy);
         *d_l2 = L2;
         status[0] = (L2 < 1e-2) ? 1 : 0;
+    }
+}
+
+// ===========================================================================
+// PICSP_FLAG_WALLS — EXTENSION WITHOUT REFERENCE SEMANTICS (BASELINE.json config 3, "bounded domain with wall
+// boundaries").  The reference is periodic-only; these kernels are checked against the repo's own CPU restatement
+// (test infrastructure outside the product tree), not against the reference.
+// ===========================================================================
+// grid phase without periodic folds: den += w * acc * 2^-frac on every node; rho = q_i*den_i + q_e*den_e on interior
+// nodes, 0 on the walls (Dirichlet nodes carry no equation)
+__global__ void k_grid_phase_walls(GridPhaseSpecies s0, GridPhaseSpecies s1, double *__restrict__ rho, int nix, int niy, int clear,
+                                   const int *__restrict__ err, int *__restrict__ err_host) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && *err) *err_host = *err;
+    const double sc0 = s0.weight * exp2((double)(-*s0.frac)), sc1 = s1.weight * exp2((double)(-*s1.frac));
+    const unsigned nn = (unsigned)nix * (unsigned)niy;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < nn; k += gridDim.x * blockDim.x) {
+        const int i = (int)(k / (unsigned)niy), j = (int)(k - (unsigned)i * (unsigned)niy);
+        const long long a0 = s0.acc[k], a1 = s1.acc[k];
+        const double di = (clear ? 0.0 : s0.den[k]) + (double)a0 * sc0, de = (clear ? 0.0 : s1.den[k]) + (double)a1 * sc1;
+        s0.acc[k] = 0; s1.acc[k] = 0;
+        s0.den[k] = di; s1.den[k] = de;
+        rho[k] = (i > 0 && i < nix - 1 && j > 0 && j < niy - 1) ? __dadd_rn(__dmul_rn(s0.q, di), __dmul_rn(s1.q, de)) : 0.0;
+    }
+}
+__global__ void k_zero_walls(double *__restrict__ f, int nix, int niy) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 2 * (nix + niy); k += gridDim.x * blockDim.x) {
+        if (k < niy) f[k] = 0.0;
+        else if (k < 2 * niy) f[(long long)(nix - 1) * niy + (k - niy)] = 0.0;
+        else if (k < 2 * niy + nix) f[(long long)(k - 2 * niy) * niy] = 0.0;
+        else f[(long long)(k - 2 * niy - nix) * niy + niy - 1] = 0.0;
+    }
+}
+
+// Red-black Gauss-Seidel / SOR for  lap(phi) = -rho  with phi = 0 on the four walls (5-point stencil, dx == dy):
+//     g = 0.25 * ((phi[i-1][j] + phi[i+1][j]) + (phi[i][j-1] + phi[i][j+1]) + dx^2 * rho[i][j]);   phi += omega * (g - phi)
+// first on the nodes with (i + j) even, then on the odd ones; warm-started from the previous phi.  After every `batch`
+// sweeps the residual  L2 = sqrt(sum_interior R^2) / (nix * niy),  R = g - phi,  is evaluated (fixed reduction tree) and
+// the iteration stops when L2 < tol (or after max_sweeps).  ONE cooperative launch: colours and the residual test
+// are separated by grid-wide barriers, no host round trip.  Every operation is explicitly rounded (no contraction), so
+// the iterate after a given number of sweeps is bit-identical to the CPU restatement used by the tests.
+// status[0] = sweeps done (negative: the cap was hit), *d_l2 = last residual.
+__global__ void __launch_bounds__(256)
+k_rb_sor(double *phi, const double *__restrict__ rho, int nix, int niy, double dx, double omega, double tol, int max_sweeps,
+         int batch, long long *status, double *d_l2, double *partial) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double s_red[32];
+    __shared__ double s_l2;
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    const double dx2 = __dmul_rn(dx, dx);
+    const int ni = nix - 2, nj = niy - 2;
+    const int half = (nj + 1) / 2;
+    for (long long k = tid; k < 2ll * (nix + niy); k += nth) {      // the walls
+        if (k < niy) phi[k] = 0.0;
+        else if (k < 2 * niy) phi[(long long)(nix - 1) * niy + (k - niy)] = 0.0;
+        else if (k < 2 * niy + nix) phi[(k - 2 * niy) * niy] = 0.0;
+        else phi[(k - 2 * niy - nix) * niy + niy - 1] = 0.0;
+    }
+    grid.sync();
+    int sweep = 0;
+    double L2 = 1e300;
+    while (sweep < max_sweeps) {
+        for (int colour = 0; colour < 2; colour++) {
+            for (long long k = tid; k < (long long)ni * half; k += nth) {
+                const int i = 1 + (int)(k / half), jj = (int)(k % half);
+                const int j = 1 + 2 * jj + ((i + 1 + colour) & 1);          // (i + j) & 1 == colour
+                if (j <= niy - 2) {
+                    const long long c = (long long)i * niy + j;
+                    const double a = __dadd_rn(__ldcg(&phi[c - niy]), __ldcg(&phi[c + niy]));
+                    const double b = __dadd_rn(__ldcg(&phi[c - 1]), __ldcg(&phi[c + 1]));
+                    const double g = __dmul_rn(0.25, __dadd_rn(__dadd_rn(a, b), __dmul_rn(dx2, rho[c])));
+                    const double old = __ldcg(&phi[c]);
+                    __stcg(&phi[c], __dadd_rn(old, __dmul_rn(omega, __dadd_rn(g, -old))));
+                }
+            }
+            grid.sync();
+        }
+        sweep++;
+        if (sweep % batch == 0 || sweep == max_sweeps) {
+            double sum = 0.0;
+            for (long long k = tid; k < (long long)ni * nj; k += nth) {
+                const int i = 1 + (int)(k / nj), j = 1 + (int)(k % nj);
+                const long long c = (long long)i * niy + j;
+                const double a = __dadd_rn(__ldcg(&phi[c - niy]), __ldcg(&phi[c + niy]));
+                const double b = __dadd_rn(__ldcg(&phi[c - 1]), __ldcg(&phi[c + 1]));
+                const double R = __dadd_rn(__dmul_rn(0.25, __dadd_rn(__dadd_rn(a, b), __dmul_rn(dx2, rho[c]))), -__ldcg(&phi[c]));
+                sum = __dadd_rn(sum, __dmul_rn(R, R));
+            }
+            const double t = block_sum(sum, s_red);
+            if (threadIdx.x == 0) __stcg(&partial[blockIdx.x], t);
+            grid.sync();
+            if (threadIdx.x == 0) {               // every CTA adds the same partials in the same order: one verdict for the grid
+                double tot = 0.0;
+                for (unsigned b = 0; b < gridDim.x; b++) tot += __ldcg(&partial[b]);
+                s_l2 = sqrt(tot) / ((double)nix * (double)niy);
+            }
+            __syncthreads();
+            L2 = s_l2;
+            if (L2 < tol) break;
+            grid.sync();                           // nobody rewrites `partial` or phi before everyone has read the verdict's inputs
+        }
+    }
+    if (tid == 0) { status[0] = L2 < tol ? sweep : -(long long)sweep; *d_l2 = L2; }
+}
+
+// E = -grad(phi): central differences inside, full one-sided differences on the walls
+__global__ void k_compute_ef_walls(const double *__restrict__ phi, double2 *__restrict__ E, int nix, int niy, double dx) {
+    const long long nn = (long long)nix * niy;
+    const double two_dx = __dmul_rn(2.0, dx);
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nn; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k / niy), j = (int)(k % niy);
+        double2 e;
+        if (i == 0) e.x = __ddiv_rn(__dadd_rn(phi[k], -phi[k + niy]), dx);
+        else if (i == nix - 1) e.x = __ddiv_rn(__dadd_rn(phi[k - niy], -phi[k]), dx);
+        else e.x = __ddiv_rn(__dadd_rn(phi[k - niy], -phi[k + niy]), two_dx);
+        if (j == 0) e.y = __ddiv_rn(__dadd_rn(phi[k], -phi[k + 1]), dx);
+        else if (j == niy - 1) e.y = __ddiv_rn(__dadd_rn(phi[k - 1], -phi[k]), dx);
+        else e.y = __ddiv_rn(__dadd_rn(phi[k - 1], -phi[k + 1]), two_dx);
+        E[k] = e;
     }
 }
 

@@ -77,6 +77,7 @@ def load_library():
         "picsp_solve": ([ctx], C.c_int),
         "picsp_solve_spectral": ([ctx], C.c_int),
         "picsp_solve_sor": ([ctx, _i64p, _dp], C.c_int),
+        "picsp_solve_status": ([ctx, _i64p, _dp], C.c_int),
         "picsp_compute_ef": ([ctx], C.c_int),
         "picsp_push": ([ctx, C.c_int], C.c_int),
         "picsp_rewind": ([ctx, C.c_int], C.c_int),

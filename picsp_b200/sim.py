@@ -18,7 +18,7 @@ from .lib import CParams, check, load_library
 ION, ELECTRON = 0, 1
 GRID_IDS = {"den_i": 0, "den_e": 1, "rho": 2, "phi": 3, "efx": 4, "efy": 5}
 PHASES = ("deposit", "rho", "allreduce", "solve", "ef", "push", "sort", "step", "push_ions", "push_electrons")
-FLAG_CLEAR_DENSITY, FLAG_NO_SORT, FLAG_NO_FUSE, FLAG_SOR_SINGLE_CTA, FLAG_SEPARATE_SORT, FLAG_NO_GRAPH = 1, 2, 4, 8, 16, 32
+FLAG_CLEAR_DENSITY, FLAG_NO_SORT, FLAG_NO_FUSE, FLAG_SOR_SINGLE_CTA, FLAG_SEPARATE_SORT, FLAG_NO_GRAPH, FLAG_WALLS = 1, 2, 4, 8, 16, 32, 64
 
 _dp = C.POINTER(C.c_double)
 
@@ -147,6 +147,11 @@ class Simulation:
         return True
 
     def solve(self): check(self.L.picsp_solve(self.ctx))
+
+    def solve_status(self):
+        sw, l2 = C.c_int64(), C.c_double()
+        check(self.L.picsp_solve_status(self.ctx, C.byref(sw), C.byref(l2)))
+        return sw.value, l2.value
     def computeEF(self): check(self.L.picsp_compute_ef(self.ctx))
     def pushSpecies(self, s): check(self.L.picsp_push(self.ctx, s))
     def rewindSpecies(self, s): check(self.L.picsp_rewind(self.ctx, s))

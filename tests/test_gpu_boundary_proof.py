@@ -81,12 +81,12 @@ def test_reference_main_with_the_integration_patch_runs_on_the_gpu(tmp_path, fus
         "particle_e_0": (relerr(c["/particle.e/0"], g["particle_e_0"]), 1e-12),
         "particle_i_0": (relerr(c["/particle.i/0"], g["particle_i_0"]), 1e-12),
         "den_e_0": (relerr(c["/den.e/0"][1:-1, 1:-1], g["den_e_0"][1:-1, 1:-1]), 1e-12),
-        "den_i_50": (relerr(c["/den.i/50"][1:-1, 1:-1], g["den_i_50"][1:-1, 1:-1]), 1e-11),
-        # rho is a ~1e-9 cancellation residue of two O(1) densities for this load (ions and electrons start on the
-        # same positions), so phi inherits the densities' last-bit differences amplified by that ratio
-        "phi_0": (relerr(c["/phi/0"], g["phi_0"]), 1e-5),
-        "phi_50": (relerr(c["/phi/50"], g["phi_50"]), 1e-5),
-        "energy[:3]": (np.abs(c["/timedata/energy"][:3] / g["energy"][:3] - 1).max(), 1e-8),
+        "den_i_50": (relerr(c["/den.i/50"][1:-1, 1:-1], g["den_i_50"][1:-1, 1:-1]), 1e-12),
+        # at ts = 0 rho is a cancellation residue of two O(1) densities for this load (ions and electrons start on the
+        # same positions), so phi_0 inherits the densities' last-bit differences amplified by that ratio (measured 5e-11)
+        "phi_0": (relerr(c["/phi/0"], g["phi_0"]), 1e-9),
+        "phi_50": (relerr(c["/phi/50"], g["phi_50"]), 1e-11),
+        "energy[:3]": (np.abs(c["/timedata/energy"][:3] / g["energy"][:3] - 1).max(), 1e-11),
     }
     print("boundary proof, measured relative errors vs the unmodified reference:", {k: f"{v[0]:.2e}" for k, v in errs.items()})
     bad = {k: v for k, v in errs.items() if not v[0] <= v[1]}

@@ -31,21 +31,23 @@ def test_whole_program_first_100_steps(tmp_path):
     assert f.datasets("phi") == sorted(["0", "50", "100"])
     assert f.read("/particle.e/0").shape == (10000, 4) and f.read("/den.i/50").shape == (65, 65)
     assert f.read("/timedata/energy").shape == g["energy"].shape
-    # numbers.  The shipped load puts ions and electrons on (almost) the same positions, so rho — and phi,
-    # its solve — start as a ~1e-9 cancellation residue of two O(1) densities: phi inherits the densities'
-    # last-bit summation-order differences amplified by that ratio, hence the looser bound on phi only.
+    # numbers.  The shipped load puts ions and electrons on (almost) the same positions, so at ts = 0 rho — and phi,
+    # its solve — is a cancellation residue of two O(1) densities: phi_0 inherits the densities' last-bit
+    # summation-order differences (1e-15) amplified by that ratio (measured 5.0e-11 on B200, hence 1e-9 for phi_0 only);
+    # everything else is held to the north_star's 1e-12 / 1e-11 (measured: den 2e-15 .. 8e-15, phi_50 1.5e-14).
     errs = {
         "particle_e_0": (relerr(f.read("/particle.e/0"), g["particle_e_0"]), 1e-12),
         "particle_i_0": (relerr(f.read("/particle.i/0"), g["particle_i_0"]), 1e-12),
         "den_e_0": (relerr(f.read("/den.e/0")[1:-1, 1:-1], g["den_e_0"][1:-1, 1:-1]), 1e-12),
-        "den_i_50": (relerr(f.read("/den.i/50")[1:-1, 1:-1], g["den_i_50"][1:-1, 1:-1]), 1e-9),
-        "phi_0": (relerr(f.read("/phi/0"), g["phi_0"]), 1e-5),
-        "phi_50": (relerr(f.read("/phi/50"), g["phi_50"]), 1e-5),
+        "den_i_50": (relerr(f.read("/den.i/50")[1:-1, 1:-1], g["den_i_50"][1:-1, 1:-1]), 1e-12),
+        "phi_0": (relerr(f.read("/phi/0"), g["phi_0"]), 1e-9),
+        "phi_50": (relerr(f.read("/phi/50"), g["phi_50"]), 1e-11),
     }
+    print("whole program, measured relative errors vs the reference's main():", {k: f"{v[0]:.2e}" for k, v in errs.items()})
     bad = {k: v for k, v in errs.items() if not v[0] <= v[1]}
     assert not bad, f"{bad} (all: {errs})"
     e = f.read("/timedata/energy")
-    assert np.allclose(e[:3], g["energy"][:3], rtol=1e-8, atol=0)
+    assert np.allclose(e[:3], g["energy"][:3], rtol=1e-11, atol=0)
 
 
 def trace_stats(e, m, g, gm):

@@ -28,7 +28,7 @@ from tests.helpers import GRIDS, assert_grid_close, relerr
 pytestmark = pytest.mark.gpu
 
 
-def run_config(numx, n, solver, load_type, drift_e, steps=3):
+def run_config(numx, n, solver, load_type, drift_e, steps=3, field_tol=1e-11):
     nm = normalise()
     Oracle.lib().oracle_set_fft_mode(3)          # cached double-precision Bluestein (checked against the long-double engine)
     try:
@@ -57,7 +57,8 @@ def run_config(numx, n, solver, load_type, drift_e, steps=3):
                 tol = 1e-12 if st == 0 else 1e-11
                 worst = 0.0
                 for name in GRIDS:
-                    worst = max(worst, assert_grid_close(sim.grid(name), o.grid(name), sim.nix, sim.niy, tol, f"step{st}/{name}"))
+                    gtol = tol if (st == 0 or name.startswith("den")) else field_tol
+                    worst = max(worst, assert_grid_close(sim.grid(name), o.grid(name), sim.nix, sim.niy, gtol, f"step{st}/{name}"))
                 for s in (ION, ELECTRON):
                     got, want = sim.get_species(s), o.get_species(s)
                     for k, nmk in enumerate("x y vx vy".split()):
@@ -79,7 +80,11 @@ def run_config(numx, n, solver, load_type, drift_e, steps=3):
 def test_config4_grid_reference_two_stream_load():
     """1024^2 spectral, loadType 2 (main.cpp:597-615): all particles on the diagonal, two counter-streaming beams."""
     nm = normalise()
-    r = run_config(1024, 2_000_000, 1, 2, nm["drift_e"])
+    # Ions and electrons are loaded on the SAME positions (main.cpp:599-604 for both species), so rho = den_i - den_e is a
+    # cancellation residue (max|rho| ~ 1e-3 of max|den| after three steps) and inherits the densities' last-bit
+    # summation-order differences (4e-15 of den, reference's serial sum vs exact integer accumulation) amplified by that
+    # ratio: the chained fields are held to 1e-10 here (measured 1.6e-11), densities and phase space to 1e-11.
+    r = run_config(1024, 2_000_000, 1, 2, nm["drift_e"], field_tol=1e-10)
     print("config 4 grid (1024^2, spectral, reference loadType-2 two-stream, 2e6/species): max rel err vs oracle", r)
 
 
