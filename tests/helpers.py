@@ -22,7 +22,7 @@ def relerr(a, b):
     assert a.shape == b.shape, (a.shape, b.shape)
     fin = np.isfinite(b)
     assert np.array_equal(np.isfinite(a), fin), "non-finite pattern differs"
-    assert np.array_equal(a[~fin], b[~fin]) or not (~fin).any()
+    assert np.array_equal(a[~fin], b[~fin], equal_nan=True) or not (~fin).any()      # same infinities / NaNs in the same places
     if not fin.any():
         return 0.0
     d = np.abs(a[fin] - b[fin]).max()

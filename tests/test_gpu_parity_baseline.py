@@ -63,7 +63,8 @@ def run_config(numx, n, solver, load_type, drift_e, steps=3, field_tol=1e-11):
                     got, want = sim.get_species(s), o.get_species(s)
                     for k, nmk in enumerate("x y vx vy".split()):
                         e = relerr(got[k], want[k])
-                        assert e <= tol, f"step{st} species {s} {nmk}: rel err {e:.3e}"
+                        ptol = tol if (st == 0 or k < 2) else field_tol      # velocities are sums of kicks dt*q/m*E: they carry E's error
+                        assert e <= ptol, f"step{st} species {s} {nmk}: rel err {e:.3e}"
                         worst = max(worst, e)
                     # KE: the reference adds up to 6.5e6 terms one after the other (main.cpp:1193-1197), the CUDA reduction
                     # is a tree: the difference is the serial sum's own rounding (~n * 2^-53 for equal terms), not the state
@@ -83,7 +84,8 @@ def test_config4_grid_reference_two_stream_load():
     # Ions and electrons are loaded on the SAME positions (main.cpp:599-604 for both species), so rho = den_i - den_e is a
     # cancellation residue (max|rho| ~ 1e-3 of max|den| after three steps) and inherits the densities' last-bit
     # summation-order differences (4e-15 of den, reference's serial sum vs exact integer accumulation) amplified by that
-    # ratio: the chained fields are held to 1e-10 here (measured 1.6e-11), densities and phase space to 1e-11.
+    # ratio: the chained fields — and the velocities of the cold species, which are nothing but accumulated kicks of that
+    # field — are held to 1e-10 here (measured 1.6e-11), densities and positions to 1e-11.
     r = run_config(1024, 2_000_000, 1, 2, nm["drift_e"], field_tol=1e-10)
     print("config 4 grid (1024^2, spectral, reference loadType-2 two-stream, 2e6/species): max rel err vs oracle", r)
 

@@ -56,7 +56,7 @@ def test_bounded_plasma_steps_match_the_checker(clear):
     xe, ye = rng.random(n) * xl, rng.random(n) * xl
     vxe, vye = rng.standard_normal(n), rng.standard_normal(n)
     hot = rng.random(n) < 0.05
-    vxe[hot] *= 40; vye[hot] *= 40                          # up to ~4 cells per step: many absorbed in 4 steps
+    vxe[hot] *= 8; vye[hot] *= 8                            # ~2.7 cells per step per sigma (max ~12 < 16): many absorbed in 4 steps
     xi, yi = rng.random(n) * xl, rng.random(n) * xl
     vi = 0.02 * rng.standard_normal(n)
     flags = FLAG_WALLS | (FLAG_CLEAR_DENSITY if clear else 0)
