@@ -176,6 +176,9 @@ int picsp_set_deposit_aggregation(picsp_ctx *ctx, int species, int mode);
  * with picsp_comm_unique_id and distributed by the caller (e.g. torch.distributed). */
 int picsp_comm_unique_id(void *id128);
 int picsp_comm_attach(picsp_ctx *ctx, const void *id128, int rank, int nranks);
+/* Collective: returns when every rank's library stream has reached this point (a plain stream synchronise without a
+ * communicator). */
+int picsp_comm_barrier(picsp_ctx *ctx);
 
 /* ---- bench-only synthetic loader (NOT reference behaviour) ------------------- */
 /* Fills n particles of a species on the device: positions uniform in the box,

@@ -44,6 +44,12 @@ int picsp_host_loader_fill(picsp_loader *ld, const picsp_run_config *cfg, int sp
  * quiet != 0 suppresses stdout. */
 int picsp_host_run(const char *ini_path, const char *out_path, int max_steps, int quiet, int device);
 
+/* The same program as one process per GPU: rank r of nranks owns the particles [N*r/nranks, N*(r+1)/nranks) of
+ * each species in loader order, the grid is replicated, rank 0 owns the output file (den.i / den.e reduced over the ranks,
+ * phi, energies, metadata) and every rank writes its own rows of the /particle.i and /particle.e datasets into it.  The NCCL unique id is passed
+ * from rank 0 to the others through the file <out_path>.ncclid; all ranks must see the same out_path (one node). */
+int picsp_host_run_ranked(const char *ini_path, const char *out_path, int max_steps, int quiet, int device, int rank, int nranks);
+
 /* The HDF5 writer the driver uses, exposed for tests and tools: the subset of the format that
  * picsp's output needs (root attributes, first-level groups, contiguous f64 rank-2 datasets). */
 typedef struct picsp_h5 picsp_h5;

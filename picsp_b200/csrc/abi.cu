@@ -1257,6 +1257,15 @@ int picsp_comm_attach(picsp_ctx *c, const void *id128, int rank, int nranks) {
     PICSP_API_END
 }
 
+int picsp_comm_barrier(picsp_ctx *c) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    PICSP_CUDA(cudaSetDevice(c->prm.device));
+    if (c->comm) PICSP_NCCL(nccl().AllReduce(c->d_scalars + 4, c->d_scalars + 4, 1, ncclFloat64, ncclSum, c->comm, c->stream));
+    PICSP_CUDA(cudaStreamSynchronize(c->stream));
+    PICSP_API_END
+}
+
 // ---- bench-only loader ---------------------------------------------------------------------
 int picsp_species_fill_synthetic(picsp_ctx *c, int s, int64_t n, int64_t first_index, uint64_t seed, double vth, double xdrift) {
     PICSP_API_BEGIN

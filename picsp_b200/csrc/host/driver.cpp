@@ -1,8 +1,11 @@
 // The reference's `main` around the hot path (src/main.cpp:336-561), on top of the kernel ABI.
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <iostream>
 #include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
 
 #include "host.hpp"
 
@@ -28,8 +31,42 @@ struct Pinned {
     } while (0)
 }  // namespace
 
-int run(const std::string &ini_path, const std::string &out_path, int max_steps, bool quiet, int device, std::string *err) {
+// The NCCL unique id of a sharded run travels through a small file next to the output (rank 0 writes it atomically,
+// the others poll): the host program has no launcher of its own, any launcher that sets RANK / WORLD_SIZE /
+// LOCAL_RANK (torchrun --no-python, srun, a shell loop) will do.
+static int exchange_unique_id(const std::string &id_path, int rank, char id[128], std::string *err) {
+    if (rank == 0) {
+        int rc = picsp_comm_unique_id(id);
+        if (rc != PICSP_OK) { if (err) *err = picsp_last_error(); return rc; }
+        const std::string tmp = id_path + ".tmp";
+        FILE *f = std::fopen(tmp.c_str(), "wb");
+        if (!f || std::fwrite(id, 1, 128, f) != 128) { if (f) std::fclose(f); if (err) *err = "cannot write " + tmp; return PICSP_ERR_INVALID; }
+        std::fclose(f);
+        if (std::rename(tmp.c_str(), id_path.c_str()) != 0) { if (err) *err = "cannot publish " + id_path; return PICSP_ERR_INVALID; }
+        return PICSP_OK;
+    }
+    for (int tries = 0; tries < 6000; tries++) {          // up to 60 s
+        FILE *f = std::fopen(id_path.c_str(), "rb");
+        if (f) {
+            const size_t n = std::fread(id, 1, 128, f);
+            std::fclose(f);
+            if (n == 128) return PICSP_OK;
+        }
+        std::this_thread::sleep_for(std::chrono::milliseconds(10));
+    }
+    if (err) *err = "timed out waiting for rank 0's communicator id at " + id_path;
+    return PICSP_ERR_NCCL;
+}
+
+// One process per GPU.  rank r of nranks owns the particles [N*r/nranks, N*(r+1)/nranks) of each species in loader
+// order; every rank runs the loader over ALL particles (the RNG stream and the loadType-2 recurrence are
+// sequential) and keeps its range.  Rank 0 owns the file: it writes the grids (den.i / den.e arrive reduced over the
+// ranks), the energies and the metadata; every rank writes its own rows of the /particle.i and /particle.e datasets into the block rank 0
+// reserved (all ranks track the same offsets).
+int run(const std::string &ini_path, const std::string &out_path, int max_steps, bool quiet, int device, std::string *err,
+        int rank, int nranks) {
     auto start = std::chrono::steady_clock::now();
+    if (rank != 0) quiet = true;
     picsp_run_config cfg;
     int rc = parse_run_config(ini_path, cfg, !quiet, err);
     if (rc != PICSP_OK) return rc;
@@ -38,7 +75,9 @@ int run(const std::string &ini_path, const std::string &out_path, int max_steps,
     std::string path = out_path.empty() ? "output/data.h5" : out_path;
     if (out_path.empty()) mkdir("output", 0777);
     H5Writer h5;
-    if (!h5.open(path, err)) return PICSP_ERR_INVALID;
+    if (rank == 0) {
+        if (!h5.open(path, err)) return PICSP_ERR_INVALID;
+    }
     for (const char *g : {"/particle.e", "/particle.i", "/timedata", "/phi", "/den.e", "/den.i"}) h5.create_group(g);
     // root attributes, main.cpp:348-353
     h5.write_attr_f64("Lx", cfg.numxCells * cfg.stepSize);
@@ -49,6 +88,8 @@ int run(const std::string &ini_path, const std::string &out_path, int max_steps,
     h5.write_attr_i32("Ny", cfg.numyCells + 1);
 
     const int64_t nI = cfg.nParticlesI, nE = cfg.nParticlesE;
+    const int64_t loI = nI * rank / nranks, hiI = nI * (rank + 1) / nranks, loE = nE * rank / nranks, hiE = nE * (rank + 1) / nranks;
+    const int64_t mI = hiI - loI, mE = hiE - loE;                   // this rank's particles
     const int nix = cfg.numxCells + 1, niy = cfg.numyCells + 1;
     picsp_params prm = {};
     prm.numxCells = cfg.numxCells; prm.numyCells = cfg.numyCells;
@@ -57,7 +98,7 @@ int run(const std::string &ini_path, const std::string &out_path, int max_steps,
     prm.charge[0] = cfg.chargeE; prm.charge[1] = -cfg.chargeE;      // main.cpp:407-408
     prm.mass[0] = cfg.massI; prm.mass[1] = cfg.massE;
     prm.spwt[0] = cfg.ion_spwt; prm.spwt[1] = cfg.electron_spwt;
-    prm.capacity[0] = nI; prm.capacity[1] = nE;
+    prm.capacity[0] = mI; prm.capacity[1] = mE;
     prm.device = device;
     Guard g;
     HOST_CHECK(picsp_create(&prm, &g.c));
@@ -68,8 +109,19 @@ int run(const std::string &ini_path, const std::string &out_path, int max_steps,
             const int64_t n = s == 0 ? nI : nE;
             std::vector<double> x(n), y(n), vx(n), vy(n);
             ld.fill(cfg, s, x.data(), y.data(), vx.data(), vy.data());
-            HOST_CHECK(picsp_species_upload(g.c, s, x.data(), y.data(), vx.data(), vy.data(), n));
+            const int64_t lo = s == 0 ? loI : loE, m = s == 0 ? mI : mE;
+            HOST_CHECK(picsp_species_upload(g.c, s, x.data() + lo, y.data() + lo, vx.data() + lo, vy.data() + lo, m));
         }
+    }
+    const std::string id_path = path + ".ncclid";
+    if (nranks > 1) {
+        char id[128];
+        rc = exchange_unique_id(id_path, rank, id, err);
+        if (rc != PICSP_OK) return rc;
+        HOST_CHECK(picsp_comm_attach(g.c, id, rank, nranks));
+        HOST_CHECK(picsp_comm_barrier(g.c));                        // rank 0 has created the file
+        if (rank == 0) std::remove(id_path.c_str());
+        else if (!h5.open(path, err, true)) return PICSP_ERR_INVALID;
     }
     if (!quiet) {   // main.cpp:440-450
         std::cout << "*********** Normalized Parameters ***********" << std::endl;
@@ -98,7 +150,7 @@ int run(const std::string &ini_path, const std::string &out_path, int max_steps,
     // One set of page-locked dump buffers: a dump is snapshot on the device and copied out while the steps of the next
     // period run (picsp_dump_begin / picsp_dump_wait); it is written to the file when the next dump is due.
     const size_t nn = (size_t)nix * niy;
-    Pinned rows_i(4 * (size_t)nI), rows_e(4 * (size_t)nE), den_i(nn), den_e(nn), phi(nn), ke(2);
+    Pinned rows_i(4 * (size_t)mI), rows_e(4 * (size_t)mE), den_i(nn), den_e(nn), phi(nn), ke(2);
     if (!rows_i.p || !rows_e.p || !den_i.p || !den_e.p || !phi.p || !ke.p) {
         if (err) *err = "cannot allocate page-locked dump buffers";
         return PICSP_ERR_CUDA;
@@ -109,9 +161,11 @@ int run(const std::string &ini_path, const std::string &out_path, int max_steps,
         int rc = picsp_dump_wait(g.c);
         if (rc != PICSP_OK) return rc;
         const std::string t = std::to_string(pending_ts);
-        h5.write_dataset_f64("/particle.i/" + t, rows_i.p, nI, 4);
-        h5.write_dataset_f64("/den.i/" + t, den_i.p, nix, niy);
-        h5.write_dataset_f64("/particle.e/" + t, rows_e.p, nE, 4);
+        uint64_t at = h5.reserve_dataset_f64("/particle.i/" + t, nI, 4);          // same offset on every rank
+        if (!h5.write_rows(at, loI, mI, 4, rows_i.p)) return PICSP_ERR_INVALID;
+        h5.write_dataset_f64("/den.i/" + t, den_i.p, nix, niy);                    // rank 0 (others only advance the offset)
+        at = h5.reserve_dataset_f64("/particle.e/" + t, nE, 4);
+        if (!h5.write_rows(at, loE, mE, 4, rows_e.p)) return PICSP_ERR_INVALID;
         h5.write_dataset_f64("/den.e/" + t, den_e.p, nix, niy);
         h5.write_dataset_f64("/phi/" + t, phi.p, nix, niy);
         if ((size_t)ti < nT) { energy[2 * ti] = ke.p[0]; energy[2 * ti + 1] = ke.p[1]; }
@@ -131,11 +185,17 @@ int run(const std::string &ini_path, const std::string &out_path, int max_steps,
             HOST_CHECK(picsp_delta_phi(g.c, &max_phi, &phi0));
             if (!quiet) std::printf("TS: %i \t delta_phi: %.3g\n", upto, max_phi - phi0);
             HOST_CHECK(flush_pending());
-            HOST_CHECK(picsp_dump_begin(g.c, rows_i.p, rows_e.p, den_i.p, den_e.p, phi.p, ke.p));
+            HOST_CHECK(picsp_dump_begin(g.c, rows_i.p, rows_e.p, rank == 0 ? den_i.p : nullptr, rank == 0 ? den_e.p : nullptr,
+                                        rank == 0 ? phi.p : nullptr, ke.p));
             pending_ts = upto;
         }
     }
     HOST_CHECK(flush_pending());
+    if (nranks > 1) {
+        if (rank != 0 && !h5.close(err)) return PICSP_ERR_INVALID;    // this rank's rows are on disk
+        HOST_CHECK(picsp_comm_barrier(g.c));
+        if (rank != 0) return PICSP_OK;
+    }
     h5.write_dataset_f64("/timedata/energy", energy.data(), nT, 2);     // writeKE, main.cpp:1179-1188
     if (!h5.close(err)) return PICSP_ERR_INVALID;
     if (!quiet) {

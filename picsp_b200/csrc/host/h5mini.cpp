@@ -81,16 +81,46 @@ Buf dataspace(int rank, uint64_t d0, uint64_t d1) {
 
 }  // namespace
 
-bool H5Writer::open(const std::string &path, std::string *err) {
-    fp_ = std::fopen(path.c_str(), "wb");
-    if (!fp_) { if (err) *err = "cannot create " + path; return false; }
+bool H5Writer::open(const std::string &path, std::string *err, bool shadow) {
+    shadow_ = shadow;
+    fp_ = std::fopen(path.c_str(), shadow ? "r+b" : "wb");
+    if (!fp_) { if (err) *err = (shadow ? "cannot open " : "cannot create ") + path; return false; }
     objs_.clear(); attrs_.clear();
     Obj root; root.name = "/"; root.is_group = true;
     objs_.push_back(root);
     std::vector<uint8_t> sb(96, 0);    // superblock placeholder (96 bytes), rewritten by close()
     eof_ = 0;
-    append(sb);
+    if (shadow) eof_ = sb.size(); else append(sb);
     return true;
+}
+
+uint64_t H5Writer::reserve_dataset_f64(const std::string &abs_name, uint64_t d0, uint64_t d1) {
+    while (eof_ % 8) { if (!shadow_) std::fputc(0, fp_); eof_++; }
+    const uint64_t at = eof_;
+    eof_ += sizeof(double) * d0 * d1;
+    if (!shadow_) {
+        size_t slash = abs_name.rfind('/');
+        size_t parent = find_or_make_group(abs_name.substr(0, slash));
+        Obj o; o.name = abs_name.substr(slash + 1); o.d0 = d0; o.d1 = d1; o.data_addr = at;
+        objs_.push_back(o);
+        objs_[parent].children.push_back(objs_.size() - 1);
+        std::fflush(fp_);
+        std::fseek(fp_, (long)eof_, SEEK_SET);        // the block is filled by write_rows() of all ranks
+    }
+    return at;
+}
+
+bool H5Writer::write_rows(uint64_t data_addr, uint64_t row_lo, uint64_t nrows, uint64_t d1, const double *data) {
+    if (!fp_) return false;
+    if (nrows == 0) return true;
+    std::fflush(fp_);
+    const long keep = std::ftell(fp_);
+    if (std::fseek(fp_, (long)(data_addr + sizeof(double) * row_lo * d1), SEEK_SET) != 0) return false;
+    const size_t n = (size_t)(nrows * d1);
+    const bool ok = std::fwrite(data, sizeof(double), n, fp_) == n;
+    std::fflush(fp_);
+    std::fseek(fp_, keep, SEEK_SET);
+    return ok;
 }
 
 uint64_t H5Writer::append(const std::vector<uint8_t> &bytes) {
@@ -117,6 +147,7 @@ void H5Writer::create_group(const std::string &abs_name) { find_or_make_group(ab
 void H5Writer::write_dataset_f64(const std::string &abs_name, const double *data, uint64_t d0, uint64_t d1) {
     // "/group/name" (picsp only ever writes one level below a first-level group)
     size_t slash = abs_name.rfind('/');
+    if (shadow_) { reserve_dataset_f64(abs_name, d0, d1); return; }      // rank 0 writes this one; keep the offsets in step
     size_t parent = find_or_make_group(abs_name.substr(0, slash));
     Obj o; o.name = abs_name.substr(slash + 1); o.d0 = d0; o.d1 = d1;
     while (eof_ % 8) { std::fputc(0, fp_); eof_++; }
@@ -203,6 +234,7 @@ uint64_t H5Writer::write_group(size_t idx, uint16_t leaf_k) {
 
 bool H5Writer::close(std::string *err) {
     if (!fp_) { if (err) *err = "file not open"; return false; }
+    if (shadow_) { bool ok = std::fclose(fp_) == 0; fp_ = nullptr; return ok; }      // the metadata belongs to rank 0
     // dataset object headers
     for (Obj &o : objs_) {
         if (o.is_group) continue;

@@ -38,9 +38,15 @@ struct Loader {
 // ---- minimal HDF5 writer: exactly the subset picsp's output uses (src/main.cpp:21-36, 1142-1247)
 class H5Writer {
 public:
-    bool open(const std::string &path, std::string *err);
+    // shadow = true: another process (rank 0 of a sharded run) owns the file's metadata; this writer only tracks the
+    // same sequence of dataset offsets and writes row slices into the existing file
+    bool open(const std::string &path, std::string *err, bool shadow = false);
     void create_group(const std::string &abs_name);                                      // "/particle.e"
     void write_dataset_f64(const std::string &abs_name, const double *data, uint64_t d0, uint64_t d1);
+    // sharded runs: reserve the raw-data block of a dataset (every rank calls it in the same order and gets the same
+    // address), then every rank writes its own rows of it
+    uint64_t reserve_dataset_f64(const std::string &abs_name, uint64_t d0, uint64_t d1);
+    bool write_rows(uint64_t data_addr, uint64_t row_lo, uint64_t nrows, uint64_t d1, const double *data);
     void write_attr_f64(const std::string &name, double v);                               // root attributes
     void write_attr_i32(const std::string &name, int32_t v);
     bool close(std::string *err);
@@ -52,11 +58,13 @@ private:
     std::vector<Attr> attrs_;
     FILE *fp_ = nullptr;
     uint64_t eof_ = 0;
+    bool shadow_ = false;
     size_t find_or_make_group(const std::string &abs_name);
     uint64_t append(const std::vector<uint8_t> &bytes);
     uint64_t write_group(size_t idx, uint16_t leaf_k);
 };
 
-int run(const std::string &ini_path, const std::string &out_path, int max_steps, bool quiet, int device, std::string *err);
+int run(const std::string &ini_path, const std::string &out_path, int max_steps, bool quiet, int device, std::string *err,
+        int rank = 0, int nranks = 1);
 
 }  // namespace picsp_host

@@ -36,6 +36,16 @@ int picsp_host_run(const char *ini_path, const char *out_path, int max_steps, in
     return rc;
 }
 
+int picsp_host_run_ranked(const char *ini_path, const char *out_path, int max_steps, int quiet, int device, int rank, int nranks) {
+    if (!ini_path || nranks < 1 || rank < 0 || rank >= nranks) return PICSP_ERR_INVALID;
+    std::string err;
+    int rc;
+    try { rc = picsp_host::run(ini_path, out_path ? out_path : "", max_steps, quiet != 0, device, &err, rank, nranks); }
+    catch (const std::exception &e) { err = e.what(); rc = PICSP_ERR_INVALID; }
+    if (rc != PICSP_OK && !err.empty()) std::cerr << "picsp_b200 (rank " << rank << "): " << err << std::endl;
+    return rc;
+}
+
 picsp_h5 *picsp_host_h5_open(const char *path) {
     if (!path) return nullptr;
     auto *w = new picsp_host::H5Writer();

@@ -92,6 +92,7 @@ def load_library():
         "picsp_set_deposit_aggregation": ([ctx, C.c_int, C.c_int], C.c_int),
         "picsp_comm_unique_id": ([C.c_void_p], C.c_int),
         "picsp_comm_attach": ([ctx, C.c_void_p, C.c_int, C.c_int], C.c_int),
+        "picsp_comm_barrier": ([ctx], C.c_int),
         "picsp_species_fill_synthetic": ([ctx, C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_double], C.c_int),
         "picsp_profile_enable": ([ctx, C.c_int], C.c_int),
         "picsp_profile_get": ([ctx, C.c_int, _dp, _i64p], C.c_int),
@@ -102,6 +103,7 @@ def load_library():
         "picsp_host_loader_destroy": ([C.c_void_p], None),
         "picsp_host_loader_fill": ([C.c_void_p, C.POINTER(CRunConfig), C.c_int, _dp, _dp, _dp, _dp], C.c_int),
         "picsp_host_run": ([C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int], C.c_int),
+        "picsp_host_run_ranked": ([C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
         "picsp_host_h5_open": ([C.c_char_p], C.c_void_p),
         "picsp_host_h5_group": ([C.c_void_p, C.c_char_p], C.c_int),
         "picsp_host_h5_dataset_f64": ([C.c_void_p, C.c_char_p, _dp, C.c_uint64, C.c_uint64], C.c_int),

@@ -89,3 +89,42 @@ def test_two_ranks_equal_oracle(tmp_path, solver):
             assert relerr(got[k], want[k]) < 1e-11
         assert abs(res[0]["ke_" + nm_][0] - o.computeKE(s)) <= 1e-11 * abs(o.computeKE(s))
         assert res[0]["ke_" + nm_][0] == res[1]["ke_" + nm_][0]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_host_program_sharded_over_two_gpus_writes_the_single_rank_file(tmp_path):
+    """`picsp_b200_run input.ini` launched once per GPU (RANK / WORLD_SIZE / LOCAL_RANK) on BASELINE config 1: ONE HDF5
+    file, rows of both ranks in list order, den.i / den.e reduced over the ranks.  Equal to the single-GPU
+    file (den to 1e-13) and to the reference's own main() (golden)."""
+    import subprocess
+    from picsp_b200 import host
+    from picsp_b200.lib import PKG
+    from tests import h5mini
+    from tests.helpers import GOLDEN, load_golden
+    ini = os.path.join(GOLDEN, "input_ini_shipped.ini")
+    exe = os.path.join(PKG, "picsp_b200_run")
+    out2, out1 = str(tmp_path / "two.h5"), str(tmp_path / "one.h5")
+    procs = [subprocess.Popen([exe, ini, "--out", out2, "--steps", "100"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                              env=dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r))) for r in range(2)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1][-1500:] for o in outs]
+    assert "TS: 100 \t delta_phi:" in outs[0][0] and outs[1][0] == "", "rank 0 alone prints the reference's lines"
+    assert not os.path.exists(out2 + ".ncclid")
+    host.run(ini, out1, max_steps=100, quiet=True)
+    a, b, g = h5mini.File(out2), h5mini.File(out1), load_golden("whole_run_input_ini")
+    assert a.attrs().keys() == b.attrs().keys() and sorted(a.groups()) == sorted(b.groups())
+    worst = 0.0
+    for grp in ("particle.i", "particle.e", "den.i", "den.e", "phi"):
+        assert a.datasets(grp) == b.datasets(grp) == sorted(["0", "50", "100"])
+        for ts in ("0", "50", "100"):
+            x, y = a.read(f"/{grp}/{ts}"), b.read(f"/{grp}/{ts}")
+            assert x.shape == y.shape
+            if grp.startswith("den"):
+                x, y = x[1:-1, 1:-1], y[1:-1, 1:-1]
+            e = relerr(x, y)
+            tol = 1e-13 if grp.startswith("den") else (1e-9 if (grp, ts) == ("phi", "0") else 1e-11)
+            assert e <= tol, (grp, ts, e)
+            worst = max(worst, e)
+    assert np.allclose(a.read("/timedata/energy"), b.read("/timedata/energy"), rtol=1e-12, atol=0)
+    assert relerr(a.read("/particle.e/0"), g["particle_e_0"]) <= 1e-12 and relerr(a.read("/den.i/50")[1:-1, 1:-1], g["den_i_50"][1:-1, 1:-1]) <= 1e-12
+    print(f"2-rank host run vs 1-rank: worst rel err {worst:.2e}")
