@@ -221,7 +221,8 @@ def workload_config(args, n_local):
         "load": args.load,
         "cells": args.cells, "particles_total": int(args.particles),
         "solver": "red-black SOR, Dirichlet walls (k_rb_sor, one cooperative launch)" if bounded else "spectral (cuFFT D2Z/Z2D)",
-        "sharding": f"particles by index range over {args.gpus} rank(s), grid replicated, 1 NCCL all-reduce of rho per step",
+        "sharding": f"particles by index range over {args.gpus} rank(s), grid replicated, the partial rho summed once per step "
+                    f"({getattr(args, 'rho_reduction', 'n/a')})",
         "l2_policy": "inputs exceed L2 (particle state per rank >> 126 MB); no explicit flush",
     }
     if n_local is not None:
@@ -300,6 +301,8 @@ def main_ours(args, rank, world, local_rank):
         return sim
 
     sim = make_sim()
+    args.rho_reduction = ("single rank: none" if world == 1 else
+                          ("own reduce-scatter + all-gather kernel over NVLink peer memory (CUDA IPC)" if sim.comm_peer_reduction() else "ncclAllReduce"))
     sim.bootstrap()
     sim.profile_enable(True)
     sim.step(args.warmup)

@@ -78,7 +78,8 @@ enum {
      * the box is absorbed (position NaN, velocity 0 from then on: skip NaN rows in a download).  Checked against the
      * repo's own CPU restatement oracle/walls_check.c, which is NOT the reference.  Needs the tiled store
      * (not combinable with PICSP_FLAG_NO_SORT); usually combined with PICSP_FLAG_CLEAR_DENSITY. */
-    PICSP_FLAG_WALLS          = 1 << 6
+    PICSP_FLAG_WALLS          = 1 << 6,
+    PICSP_FLAG_NCCL_ONLY      = 1 << 7  /* sharded runs: sum the partial rho with ncclAllReduce instead of the library's own peer-memory kernels (cross-check path) */
 };
 
 /* Normalised quantities, i.e. the reference's globals after parse_ini_file
@@ -173,12 +174,17 @@ int picsp_set_deposit_aggregation(picsp_ctx *ctx, int species, int mode);
 
 /* ---- multi-GPU: particles sharded by index range, grid replicated ------------ */
 /* One communicator per rank; id is an NCCL unique id (128 bytes) created by rank 0
- * with picsp_comm_unique_id and distributed by the caller (e.g. torch.distributed). */
+ * with picsp_comm_unique_id and distributed by the caller (e.g. torch.distributed).
+ * When all ranks sit on one NVLink node, picsp_comm_attach also maps the ranks' rho buffers into each other (CUDA IPC) and
+ * picsp_step sums the partial densities with the library's own reduce-scatter + all-gather kernel over peer memory;
+ * otherwise, and for the per-function calls, NCCL does it. */
 int picsp_comm_unique_id(void *id128);
 int picsp_comm_attach(picsp_ctx *ctx, const void *id128, int rank, int nranks);
 /* Collective: returns when every rank's library stream has reached this point (a plain stream synchronise without a
  * communicator). */
 int picsp_comm_barrier(picsp_ctx *ctx);
+/* 1 when picsp_step sums the partial rho with the library's own peer-memory kernels, 0 when NCCL does it. */
+int picsp_comm_peer_reduction(picsp_ctx *ctx);
 
 /* ---- bench-only synthetic loader (NOT reference behaviour) ------------------- */
 /* Fills n particles of a species on the device: positions uniform in the box,

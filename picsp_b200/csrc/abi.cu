@@ -12,6 +12,7 @@
 #include "ctx.cuh"
 #include "grid_kernels.cuh"
 #include "particle_kernels.cuh"
+#include "peer_kernels.cuh"
 #include "tile_kernels.cuh"
 
 using namespace picsp;
@@ -76,6 +77,8 @@ void check_device_error(picsp_ctx *c) {
         int v = *h;
         PICSP_CUDA(cudaMemsetAsync(c->d_error, 0, sizeof(int), c->stream));
         *c->h_error_mapped = 0;
+        if (v & ERR_BIT_PEER)
+            throw Error(PICSP_ERR_NCCL, "a rank did not reach the peer-memory barrier of the rho reduction within 2 s");
         if (v & ERR_BIT_REBIN)
             throw Error(PICSP_ERR_STATE, "internal: a re-binning mover overflowed a bin (histogram and bin function disagree)");
         if (v & ERR_BIT_RUNAWAY)
@@ -283,6 +286,7 @@ void make_tensor_map(picsp_ctx *c) {
 
 // -- operations ---------------------------------------------------------------------
 void op_allreduce_rho(picsp_ctx *c);   // comm section below
+void op_peer_reduce_rho(picsp_ctx *c);
 
 // makes sure acc_s holds the fixed-point deposit of the stored positions (scatter loop of scatterSpecies)
 void ensure_acc(picsp_ctx *c, int s) {
@@ -331,14 +335,16 @@ void op_grid_phase(picsp_ctx *c) {
             sp.acc_valid = false;
         }
         const int clear = (c->prm.flags & PICSP_FLAG_CLEAR_DENSITY) ? 1 : 0;
+        double *rho_out = c->peer_ok ? c->peer_part[c->rank] : c->rho;      // sharded: the partial goes where the peers can read it
         if (walls(c))
-            PICSP_LAUNCH(c, k_grid_phase_walls, blocks_for(g.nn, 256, c->num_sms * 32), 256, 0, gs[0], gs[1], c->rho, g.nix, g.niy, clear,
+            PICSP_LAUNCH(c, k_grid_phase_walls, blocks_for(g.nn, 256, c->num_sms * 32), 256, 0, gs[0], gs[1], rho_out, g.nix, g.niy, clear,
                          c->d_error, c->h_error_mapped);
         else
-        PICSP_LAUNCH(c, k_grid_phase, blocks_for(g.nn, 256, c->num_sms * 32), 256, 0, gs[0], gs[1], c->rho, g.nix, g.niy, clear,
-                     c->d_error, c->h_error_mapped);   // one node per thread up to 1.2M nodes: latency-bound otherwise
+            PICSP_LAUNCH(c, k_grid_phase, blocks_for(g.nn, 256, c->num_sms * 32), 256, 0, gs[0], gs[1], rho_out, g.nix, g.niy, clear,
+                         c->d_error, c->h_error_mapped);   // one node per thread up to 1.2M nodes: latency-bound otherwise
     }
-    if (c->comm) op_allreduce_rho(c);    // the folds are linear: folding the partial rho first commutes with the sum
+    if (c->peer_ok) op_peer_reduce_rho(c);
+    else if (c->comm) op_allreduce_rho(c);    // the folds are linear: folding the partial rho first commutes with the sum
 }
 
 
@@ -498,6 +504,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
@@ -512,6 +519,7 @@ NcclApi &nccl() {
         api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
         api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
         api.Reduce = (decltype(api.Reduce))dlsym(api.handle, "ncclReduce");
+        api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
         api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
         api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
     });
@@ -531,6 +539,71 @@ void op_allreduce_rho(picsp_ctx *c) {
     // every rank holds the partial interior rho of its own particles; boundary nodes are 0 (Q3)
     PhaseScope ph(c, PICSP_PHASE_ALLREDUCE);
     PICSP_NCCL(nccl().AllReduce(c->rho, c->rho, (size_t)c->g.nn, ncclFloat64, ncclSum, c->comm, c->stream));
+}
+
+// reduce-scatter + all-gather of the partial rho over peer memory (peer_kernels.cuh): barrier, one kernel, barrier
+void op_peer_reduce_rho(picsp_ctx *c) {
+    PhaseScope ph(c, PICSP_PHASE_ALLREDUCE);
+    PeerPtrs pp;
+    for (int k = 0; k < PEER_MAX_RANKS; k++) { pp.part[k] = c->peer_part[k]; pp.full[k] = c->peer_full[k]; pp.flags[k] = c->peer_flags[k]; }
+    const long long slice = (c->g.nn + c->nranks - 1) / c->nranks;
+    c->peer_epoch++;
+    PICSP_LAUNCH(c, k_peer_barrier, 1, 32, 0, pp, c->rank, c->nranks, c->peer_epoch, 0, c->d_error);       // every partial is complete
+    PICSP_LAUNCH(c, k_peer_reduce, blocks_for(slice, 256, c->num_sms * 8), 256, 0, pp, c->rank, c->nranks, c->g.nn);
+    PICSP_LAUNCH(c, k_peer_barrier, 1, 32, 0, pp, c->rank, c->nranks, c->peer_epoch, 1, c->d_error);       // every slice has landed everywhere
+}
+
+// Maps the ranks' blocks into each other (CUDA IPC handles exchanged with one ncclAllGather).  Any failure on any rank
+// (ranks on different nodes, no peer access, IPC refused) leaves ALL ranks on the NCCL all-reduce.
+void peer_setup(picsp_ctx *c) {
+    const Geom &g = c->g;
+    if (c->nranks < 2 || c->nranks > PEER_MAX_RANKS || (c->prm.flags & PICSP_FLAG_NCCL_ONLY) || !nccl().AllGather) return;
+    const size_t words = 2 * (size_t)g.nn + 2 * PEER_MAX_RANKS + 16;
+    int ok = 1;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (cudaMalloc((void **)&c->peer_block, words * sizeof(double)) != cudaSuccess) { cudaGetLastError(); c->peer_block = nullptr; ok = 0; }
+    if (ok && cudaMemsetAsync(c->peer_block, 0, words * sizeof(double), c->stream) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine, c->peer_block) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    // exchange {ok, handle}: 128 bytes per rank
+    struct Slot { int ok; int pad[15]; cudaIpcMemHandle_t h; };
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64 && sizeof(Slot) == 128, "IPC handle layout");
+    Slot my; memset(&my, 0, sizeof(my)); my.ok = ok; my.h = mine;
+    Slot *d_all = nullptr;
+    PICSP_CUDA(cudaMalloc((void **)&d_all, sizeof(Slot) * c->nranks));
+    PICSP_CUDA(cudaMemcpyAsync(d_all + c->rank, &my, sizeof(Slot), cudaMemcpyHostToDevice, c->stream));
+    PICSP_NCCL(nccl().AllGather(d_all + c->rank, d_all, sizeof(Slot), ncclInt8, c->comm, c->stream));
+    std::vector<Slot> all(c->nranks);
+    PICSP_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(Slot) * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+    PICSP_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_all);
+    for (int k = 0; k < c->nranks; k++) ok = ok && all[k].ok;
+    for (int k = 0; ok && k < c->nranks; k++) {
+        if (k == c->rank) continue;
+        if (cudaIpcOpenMemHandle(&c->peer_mapped[k], all[k].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); c->peer_mapped[k] = nullptr; ok = 0; }
+    }
+    // second round: did every rank manage to map every block?
+    double *d_flag = c->d_scalars + 5;
+    const double mine_ok = ok ? 0.0 : 1.0;
+    PICSP_CUDA(cudaMemcpyAsync(d_flag, &mine_ok, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PICSP_NCCL(nccl().AllReduce(d_flag, d_flag, 1, ncclFloat64, ncclSum, c->comm, c->stream));
+    const double failures = read_scalar(c, d_flag);
+    if (failures != 0.0) {
+        for (int k = 0; k < c->nranks; k++) if (c->peer_mapped[k]) { cudaIpcCloseMemHandle(c->peer_mapped[k]); c->peer_mapped[k] = nullptr; }
+        cudaFree(c->peer_block); c->peer_block = nullptr;
+        return;
+    }
+    for (int k = 0; k < c->nranks; k++) {
+        double *base = k == c->rank ? c->peer_block : (double *)c->peer_mapped[k];
+        c->peer_part[k] = base; c->peer_full[k] = base + g.nn;
+        c->peer_flags[k] = reinterpret_cast<unsigned long long *>(base + 2 * g.nn);
+    }
+    // the summed rho now lives in this rank's block: every consumer of c->rho (solve, downloads, per-function calls) follows
+    PICSP_CUDA(cudaMemcpyAsync(c->peer_full[c->rank], c->rho, sizeof(double) * g.nn, cudaMemcpyDeviceToDevice, c->stream));
+    PICSP_CUDA(cudaStreamSynchronize(c->stream));
+    c->rho_owned = c->rho;
+    c->rho = c->peer_full[c->rank];
+    c->peer_ok = true;
 }
 
 }  // namespace
@@ -648,6 +721,13 @@ void picsp_destroy(picsp_ctx *c) {
     cudaSetDevice(c->prm.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->peer_ok) {
+        // nobody may unmap or free a block a peer kernel could still touch: meet once more, then tear down
+        try { if (c->comm) { nccl().AllReduce(c->d_scalars + 4, c->d_scalars + 4, 1, ncclFloat64, ncclSum, c->comm, c->stream); cudaStreamSynchronize(c->stream); } } catch (...) {}
+        for (int k = 0; k < c->nranks; k++) if (c->peer_mapped[k]) cudaIpcCloseMemHandle(c->peer_mapped[k]);
+        c->rho = c->rho_owned;
+        cudaFree(c->peer_block);
+    }
     if (c->comm) { try { nccl().CommDestroy(c->comm); } catch (...) {} }
     if (c->have_plans) { cufftDestroy(c->plan_fwd); cufftDestroy(c->plan_inv); }
     for (int s = 0; s < 2; s++) {
@@ -1254,8 +1334,11 @@ int picsp_comm_attach(picsp_ctx *c, const void *id128, int rank, int nranks) {
     memcpy(&id, id128, sizeof(id));
     PICSP_NCCL(nccl().CommInitRank(&c->comm, nranks, id, rank));
     c->rank = rank; c->nranks = nranks;
+    peer_setup(c);
     PICSP_API_END
 }
+
+int picsp_comm_peer_reduction(picsp_ctx *c) { return (c && c->peer_ok) ? 1 : 0; }
 
 int picsp_comm_barrier(picsp_ctx *c) {
     PICSP_API_BEGIN

@@ -170,6 +170,15 @@ struct picsp_ctx {
 
     // multi-GPU
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+    // peer-memory reduction of the partial rho (peer_kernels.cuh): one cudaMalloc block per rank, mapped by every
+    // other rank of the node through CUDA IPC:  [ partial rho (nn) | summed rho (nn) | arrival flags ]
+    bool peer_ok = false;
+    double *peer_block = nullptr;                // this rank's block
+    void *peer_mapped[8] = {};                   // the others' blocks as mapped here (nullptr for this rank)
+    double *peer_part[8] = {}, *peer_full[8] = {};
+    unsigned long long *peer_flags[8] = {};
+    unsigned long long peer_epoch = 0;
+    double *rho_owned = nullptr;                 // the context's own rho allocation (c->rho points into peer_block while peer_ok)
 
     // asynchronous dumps (picsp_dump_begin / picsp_dump_wait): device-side snapshot of what the reference dumps
     // (writeSpecies / writePot, src/main.cpp:1142-1216), copied out on the copy stream while the time loop goes on

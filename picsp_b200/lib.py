@@ -93,6 +93,7 @@ def load_library():
         "picsp_comm_unique_id": ([C.c_void_p], C.c_int),
         "picsp_comm_attach": ([ctx, C.c_void_p, C.c_int, C.c_int], C.c_int),
         "picsp_comm_barrier": ([ctx], C.c_int),
+        "picsp_comm_peer_reduction": ([ctx], C.c_int),
         "picsp_species_fill_synthetic": ([ctx, C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_double], C.c_int),
         "picsp_profile_enable": ([ctx, C.c_int], C.c_int),
         "picsp_profile_get": ([ctx, C.c_int, _dp, _i64p], C.c_int),

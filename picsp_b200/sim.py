@@ -18,7 +18,7 @@ from .lib import CParams, check, load_library
 ION, ELECTRON = 0, 1
 GRID_IDS = {"den_i": 0, "den_e": 1, "rho": 2, "phi": 3, "efx": 4, "efy": 5}
 PHASES = ("deposit", "rho", "allreduce", "solve", "ef", "push", "sort", "step", "push_ions", "push_electrons")
-FLAG_CLEAR_DENSITY, FLAG_NO_SORT, FLAG_NO_FUSE, FLAG_SOR_SINGLE_CTA, FLAG_SEPARATE_SORT, FLAG_NO_GRAPH, FLAG_WALLS = 1, 2, 4, 8, 16, 32, 64
+FLAG_CLEAR_DENSITY, FLAG_NO_SORT, FLAG_NO_FUSE, FLAG_SOR_SINGLE_CTA, FLAG_SEPARATE_SORT, FLAG_NO_GRAPH, FLAG_WALLS, FLAG_NCCL_ONLY = 1, 2, 4, 8, 16, 32, 64, 128
 
 _dp = C.POINTER(C.c_double)
 
@@ -193,6 +193,9 @@ class Simulation:
     def comm_attach(self, unique_id: bytes, rank: int, nranks: int):
         buf = C.create_string_buffer(unique_id, 128)
         check(self.L.picsp_comm_attach(self.ctx, buf, rank, nranks))
+
+    def comm_peer_reduction(self):
+        return bool(self.L.picsp_comm_peer_reduction(self.ctx))
 
     # -- instrumentation ------------------------------------------------------------------------
     def profile_enable(self, on=True): check(self.L.picsp_profile_enable(self.ctx, 1 if on else 0))

@@ -23,7 +23,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, numx, n, solver, out_dir):
+def _worker(rank, world, port, numx, n, solver, out_dir, flags=0):
     import torch
     import torch.distributed as dist
     from picsp_b200 import Params, Simulation
@@ -36,14 +36,15 @@ def _worker(rank, world, port, numx, n, solver, out_dir):
     o.seed(8); o.init(ION, 1); o.init(ELECTRON, 1)
     lo, hi = shard_range(n, rank, world)
     sim = Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, solverType=solver, device=rank,
-                            capacity=(hi - lo, hi - lo)))
+                            capacity=(hi - lo, hi - lo), flags=flags))
     for s in (ION, ELECTRON):
         sim.set_species(s, *(a[lo:hi] for a in o.get_species(s)))
     uid = [Simulation.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     sim.comm_attach(uid[0], rank, world)
     sim.bootstrap(); sim.step(3)
-    out = {g: sim.grid(g) for g in ("rho", "phi", "efx", "efy", "den_i", "den_e")}   # den_*: collective, global sum on every rank
+    out = {g: sim.grid(g) for g in ("rho", "phi", "efx", "efy", "den_i", "den_e")}
+    out["peer"] = np.array([int(sim.comm_peer_reduction())])   # den_*: collective, global sum on every rank
     d = sim.dump(root=(rank == 0))           # collective: den.i / den.e reduced to rank 0, phi on rank 0, KE global
     for k, v in d.items():
         out["dump_" + k] = v
@@ -56,17 +57,21 @@ def _worker(rank, world, port, numx, n, solver, out_dir):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("solver", [1, 2])
-def test_two_ranks_equal_oracle(tmp_path, solver):
+@pytest.mark.parametrize("solver,flags", [(1, 0), (2, 0), (1, 128)], ids=["spectral-peer", "sor-peer", "spectral-nccl-only"])
+def test_two_ranks_equal_oracle(tmp_path, solver, flags):
+    """flags 0: the partial rho is summed by the library's own peer-memory kernels (when the two GPUs can map each other);
+    128 = PICSP_FLAG_NCCL_ONLY: by ncclAllReduce.  Both against the single-rank oracle."""
     import torch.multiprocessing as mp
     from picsp_b200.sim import shard_range
     numx, n, world = 64, 40_000, 2
-    mp.spawn(_worker, args=(world, _free_port(), numx, n, solver, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), numx, n, solver, str(tmp_path), flags), nprocs=world, join=True)
     nm = normalise()
     o = Oracle(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, vth_i=nm["vth_i"], solver=solver)
     o.seed(8); o.init(ION, 1); o.init(ELECTRON, 1)
     o.bootstrap(); o.step(3)
     res = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
+    assert res[0]["peer"][0] == res[1]["peer"][0] and (flags == 0 or res[0]["peer"][0] == 0)
+    print("rho reduction:", "own peer-memory kernels" if res[0]["peer"][0] else "ncclAllReduce")
     for g in ("rho", "phi", "efx", "efy"):
         assert np.array_equal(res[0][g], res[1][g]), f"{g} differs between ranks (redundant solve must be bit-identical)"
         assert relerr(res[0][g], o.grid(g)) < 1e-11, g
