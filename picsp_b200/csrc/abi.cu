@@ -558,7 +558,8 @@ void op_peer_reduce_rho(picsp_ctx *c) {
 void peer_setup(picsp_ctx *c) {
     const Geom &g = c->g;
     if (c->nranks < 2 || c->nranks > PEER_MAX_RANKS || (c->prm.flags & PICSP_FLAG_NCCL_ONLY) || !nccl().AllGather) return;
-    const size_t words = 2 * (size_t)g.nn + 2 * PEER_MAX_RANKS + 16;
+    const size_t nnp = ((size_t)g.nn + 31) & ~(size_t)31;          // every sub-buffer 256-byte aligned (cuFFT reads rho from here)
+    const size_t words = 2 * nnp + 2 * PEER_MAX_RANKS + 16;
     int ok = 1;
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof(mine));
@@ -595,8 +596,8 @@ void peer_setup(picsp_ctx *c) {
     }
     for (int k = 0; k < c->nranks; k++) {
         double *base = k == c->rank ? c->peer_block : (double *)c->peer_mapped[k];
-        c->peer_part[k] = base; c->peer_full[k] = base + g.nn;
-        c->peer_flags[k] = reinterpret_cast<unsigned long long *>(base + 2 * g.nn);
+        c->peer_part[k] = base; c->peer_full[k] = base + nnp;
+        c->peer_flags[k] = reinterpret_cast<unsigned long long *>(base + 2 * nnp);
     }
     // the summed rho now lives in this rank's block: every consumer of c->rho (solve, downloads, per-function calls) follows
     PICSP_CUDA(cudaMemcpyAsync(c->peer_full[c->rank], c->rho, sizeof(double) * g.nn, cudaMemcpyDeviceToDevice, c->stream));

@@ -75,17 +75,17 @@ int run(const std::string &ini_path, const std::string &out_path, int max_steps,
     std::string path = out_path.empty() ? "output/data.h5" : out_path;
     if (out_path.empty()) mkdir("output", 0777);
     H5Writer h5;
-    if (rank == 0) {
+    if (rank == 0) {          // the other ranks open it (for their row slices only) once rank 0 has created it
         if (!h5.open(path, err)) return PICSP_ERR_INVALID;
+        for (const char *g : {"/particle.e", "/particle.i", "/timedata", "/phi", "/den.e", "/den.i"}) h5.create_group(g);
+        // root attributes, main.cpp:348-353
+        h5.write_attr_f64("Lx", cfg.numxCells * cfg.stepSize);
+        h5.write_attr_f64("Ly", cfg.numyCells * cfg.stepSize);
+        h5.write_attr_i32("dp", cfg.dumpPeriod);
+        h5.write_attr_i32("Nt", cfg.nTimeSteps);
+        h5.write_attr_i32("Nx", cfg.numxCells + 1);
+        h5.write_attr_i32("Ny", cfg.numyCells + 1);
     }
-    for (const char *g : {"/particle.e", "/particle.i", "/timedata", "/phi", "/den.e", "/den.i"}) h5.create_group(g);
-    // root attributes, main.cpp:348-353
-    h5.write_attr_f64("Lx", cfg.numxCells * cfg.stepSize);
-    h5.write_attr_f64("Ly", cfg.numyCells * cfg.stepSize);
-    h5.write_attr_i32("dp", cfg.dumpPeriod);
-    h5.write_attr_i32("Nt", cfg.nTimeSteps);
-    h5.write_attr_i32("Nx", cfg.numxCells + 1);
-    h5.write_attr_i32("Ny", cfg.numyCells + 1);
 
     const int64_t nI = cfg.nParticlesI, nE = cfg.nParticlesE;
     const int64_t loI = nI * rank / nranks, hiI = nI * (rank + 1) / nranks, loE = nE * rank / nranks, hiE = nE * (rank + 1) / nranks;

@@ -111,7 +111,12 @@ def test_host_program_sharded_over_two_gpus_writes_the_single_rank_file(tmp_path
     out2, out1 = str(tmp_path / "two.h5"), str(tmp_path / "one.h5")
     procs = [subprocess.Popen([exe, ini, "--out", out2, "--steps", "100"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
                               env=dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r))) for r in range(2)]
-    outs = [p.communicate(timeout=600) for p in procs]
+    try:
+        outs = [p.communicate(timeout=240) for p in procs]
+    finally:
+        for p in procs:                 # a rank that died must not leave the other one waiting in a collective
+            if p.poll() is None:
+                p.kill()
     assert all(p.returncode == 0 for p in procs), [o[1][-1500:] for o in outs]
     assert "TS: 100 \t delta_phi:" in outs[0][0] and outs[1][0] == "", "rank 0 alone prints the reference's lines"
     assert not os.path.exists(out2 + ".ncclid")
