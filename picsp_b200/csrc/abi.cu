@@ -145,7 +145,9 @@ void sort_prepare(picsp_ctx *c, int s) {
         dalloc(&sp.chunk_cnt, (size_t)sp.max_chunks * 9); dalloc(&sp.chunk_base, (size_t)sp.max_chunks * 9);
     }
     sp.chunk2 = pick_chunk(c, sp.n);
-    PICSP_LAUNCH(c, k_scan_tiles, 1, 1024, 0, sp.hist, nt, sp.tile_off, (Chunk *)sp.chunks2, sp.nchunks2, sp.cursor, sp.chunk2);
+    if (!sp.scan_chunk0) dalloc(&sp.scan_chunk0, (size_t)nt);
+    PICSP_LAUNCH(c, k_scan_tiles, 1, 1024, 0, sp.hist, nt, sp.tile_off, sp.scan_chunk0, sp.nchunks2, sp.cursor, sp.chunk2);
+    PICSP_LAUNCH(c, k_fill_chunks, (nt * 32 + 255) / 256, 256, 0, sp.hist, nt, sp.tile_off, sp.scan_chunk0, (Chunk *)sp.chunks2, sp.chunk2);
 }
 void sort_finish(picsp_ctx *c, int s, bool result_in_second_set = true) {
     Species &sp = c->sp[s];
@@ -738,7 +740,7 @@ void picsp_destroy(picsp_ctx *c) {
         cudaFree(sp.x2); cudaFree(sp.id2);
         cudaFree(sp.tile_off); cudaFree(sp.chunks); cudaFree(sp.nchunks); cudaFree(sp.cursor);
         cudaFree(sp.chunks2); cudaFree(sp.nchunks2); cudaFree(sp.chunk_cnt); cudaFree(sp.chunk_base);
-        cudaFree(sp.cell_cnt); cudaFree(sp.tile_chunk0);
+        cudaFree(sp.cell_cnt); cudaFree(sp.tile_chunk0); cudaFree(sp.scan_chunk0);
     }
     cudaFree(c->rho); cudaFree(c->phi); cudaFree(c->E_alloc); cudaFree(c->rhok); cudaFree(c->phik);
     cudaFree(c->d_walls_partial);
@@ -772,7 +774,9 @@ int picsp_sync(picsp_ctx *c) {
 // ---- state exchange -------------------------------------------------------------------
 static void ensure_copy_stream(picsp_ctx *c) {
     if (c->copy_stream) return;
-    PICSP_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    int lo_prio = 0, hi_prio = 0;      // highest priority: a copy kernel's few CTAs are placed before the mover's pending ones
+    PICSP_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    PICSP_CUDA(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, hi_prio));
     for (int k = 0; k < 4; k++) PICSP_CUDA(cudaEventCreateWithFlags(&c->ev_ready[k], cudaEventDisableTiming));
 }
 
@@ -1132,7 +1136,11 @@ static bool ensure_snapshot(picsp_ctx *c) {
         PICSP_CUDA(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
         PICSP_CUDA(cudaEventCreateWithFlags(&c->ev_dump_done, cudaEventDisableTiming));
         PICSP_CUDA(cudaEventCreateWithFlags(&c->ev_dump_done2, cudaEventDisableTiming));
-        PICSP_CUDA(cudaStreamCreateWithFlags(&c->copy_stream2, cudaStreamNonBlocking));
+        int lo_prio = 0, hi_prio = 0;
+        PICSP_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        PICSP_CUDA(cudaStreamCreateWithPriority(&c->copy_stream2, cudaStreamNonBlocking, hi_prio));
+        const char *e = getenv("PICSP_DUMP_COPY_CTAS");     // experiment switch: CTAs of the copy kernel per species (0: copy engines)
+        c->dump_copy_ctas = e ? atoi(e) : 0;
     }
     return true;
 }
@@ -1210,9 +1218,24 @@ int picsp_dump_begin(picsp_ctx *c, double *rows_i, double *rows_e, double *den_i
     // does not fill the PCIe link
     PICSP_CUDA(cudaStreamWaitEvent(c->copy_stream2, c->ev_snap, 0));
     for (int s = 0; s < 2; s++)
-        if (rows[s] && c->sp[s].n > 0)
-            PICSP_CUDA(cudaMemcpyAsync(rows[s], c->snap_rows[s], sizeof(double) * 4 * (size_t)c->sp[s].n, cudaMemcpyDeviceToHost,
-                                       s == 0 ? c->copy_stream : c->copy_stream2));
+        if (rows[s] && c->sp[s].n > 0) {
+            cudaStream_t cs = s == 0 ? c->copy_stream : c->copy_stream2;
+            const size_t bytes = sizeof(double) * 4 * (size_t)c->sp[s].n;
+            bool by_kernel = false;
+            if (c->dump_copy_ctas > 0) {                       // page-locked destination, mapped into the device's address space?
+                cudaPointerAttributes at;
+                if (cudaPointerGetAttributes(&at, rows[s]) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+                    k_copy_to_host<<<c->dump_copy_ctas, 256, 0, cs>>>(reinterpret_cast<const double2 *>(c->snap_rows[s]),
+                                                                     reinterpret_cast<double2 *>(at.devicePointer), (long long)(bytes / 16));
+                    PICSP_CUDA(cudaGetLastError());
+                    c->launches++;
+                    by_kernel = true;
+                } else {
+                    cudaGetLastError();
+                }
+            }
+            if (!by_kernel) PICSP_CUDA(cudaMemcpyAsync(rows[s], c->snap_rows[s], bytes, cudaMemcpyDeviceToHost, cs));
+        }
     PICSP_CUDA(cudaEventRecord(c->ev_dump_done, c->copy_stream));
     PICSP_CUDA(cudaEventRecord(c->ev_dump_done2, c->copy_stream2));
     c->dump_in_flight = true;

@@ -104,6 +104,7 @@ struct Species {
     unsigned int *cell_cnt = nullptr;    // [chunks][CELLKEYS] populations, then first slots
     long long cell_cnt_chunks = 0;
     int *tile_chunk0 = nullptr;          // [ntiles] first chunk of every bin
+    int *scan_chunk0 = nullptr;          // [ntiles] the same for the chunk table under construction (k_scan_tiles -> k_fill_chunks)
     int ntiles = 0;
 };
 
@@ -189,6 +190,7 @@ struct picsp_ctx {
     cudaEvent_t ev_snap = nullptr, ev_dump_done = nullptr, ev_dump_done2 = nullptr;
     cudaStream_t copy_stream2 = nullptr;         // second copy engine for the electrons' rows
     bool dump_in_flight = false;
+    int dump_copy_ctas = 0;                      // > 0: the rows leave through k_copy_to_host with that many CTAs instead of a copy engine
     double *dump_ke_host = nullptr;              // caller's [2]: the Q10 constant is added in picsp_dump_wait
     bool snapshot_unavailable = false;           // not enough memory for a snapshot: dumps are synchronous
 

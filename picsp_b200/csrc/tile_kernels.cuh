@@ -83,37 +83,61 @@ struct __align__(16) Chunk {
 
 // ---------------------------------------------------------------------------
 // binning: exclusive scan of the tile histogram -> tile offsets + chunk table
-// (single CTA; ntiles <= 128*128)
+// k_scan_tiles (one CTA; ntiles <= 128*128): block-wide scan of the populations and of the chunk counts ->
+// tile_off[], first chunk of every bin, number of chunks, zeroed cursors.  k_fill_chunks (one warp per bin) then writes
+// the bin's chunk entries in parallel.  (Round 1 did both in one kernel with a serial prefix on thread 0 and serial
+// per-thread chunk writes: 178 us per re-binning at 4096 bins with ~30 chunks each; now ~10 us.)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
 k_scan_tiles(const unsigned int *__restrict__ hist, int ntiles, long long *__restrict__ tile_off,
-             Chunk *__restrict__ chunks, int *__restrict__ nchunks, unsigned int *__restrict__ cursor, int chunk) {
-    __shared__ long long s_part[1024];
-    __shared__ int s_chunk[1024];
-    const int tid = threadIdx.x, nt = blockDim.x;
+             int *__restrict__ chunk0, int *__restrict__ nchunks, unsigned int *__restrict__ cursor, int chunk) {
+    __shared__ long long s_part[32];
+    __shared__ int s_chunk[32];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, w = tid >> 5;
     const int per = (ntiles + nt - 1) / nt;
     const int lo = tid * per, hi = min(lo + per, ntiles);
     long long sum = 0; int csum = 0;
     for (int t = lo; t < hi; t++) { unsigned int h = hist[t]; sum += h; csum += (int)((h + chunk - 1) / chunk); }
-    s_part[tid] = sum; s_chunk[tid] = csum;
+    // inclusive scan over the threads: inside the warps, then over the warp totals
+    long long isum = sum; int icsum = csum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long v = __shfl_up_sync(0xffffffffu, isum, o); const int u = __shfl_up_sync(0xffffffffu, icsum, o);
+        if (lane >= o) { isum += v; icsum += u; }
+    }
+    if (lane == 31) { s_part[w] = isum; s_chunk[w] = icsum; }
     __syncthreads();
-    if (tid == 0) {
-        long long a = 0; int b = 0;
-        for (int k = 0; k < nt; k++) { long long v = s_part[k]; int w = s_chunk[k]; s_part[k] = a; s_chunk[k] = b; a += v; b += w; }
-        tile_off[ntiles] = a;
-        *nchunks = b;
+    if (w == 0) {
+        long long v = lane < nt / 32 ? s_part[lane] : 0, iv = v; int u = lane < nt / 32 ? s_chunk[lane] : 0, iu = u;
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long a = __shfl_up_sync(0xffffffffu, iv, o); const int b = __shfl_up_sync(0xffffffffu, iu, o);
+            if (lane >= o) { iv += a; iu += b; }
+        }
+        s_part[lane] = iv - v; s_chunk[lane] = iu - u;            // exclusive warp offsets
+        if (lane == 31) { tile_off[ntiles] = iv; *nchunks = iu; }
     }
     __syncthreads();
-    long long off = s_part[tid]; int coff = s_chunk[tid];
+    long long off = s_part[w] + isum - sum; int coff = s_chunk[w] + icsum - csum;
     for (int t = lo; t < hi; t++) {
-        unsigned int h = hist[t];
+        const unsigned int h = hist[t];
         tile_off[t] = off;
+        chunk0[t] = coff;
         cursor[t] = 0u;
-        for (unsigned int done = 0; done < h; done += chunk) {
-            Chunk ck; ck.start = off + done; ck.count = (int)min((unsigned int)chunk, h - done); ck.tile = t;
-            chunks[coff++] = ck;
-        }
-        off += h;
+        off += h; coff += (int)((h + chunk - 1) / chunk);
+    }
+}
+
+// one warp per bin: its chunk entries {first particle, count <= chunk, bin}
+__global__ void __launch_bounds__(256)
+k_fill_chunks(const unsigned int *__restrict__ hist, int ntiles, const long long *__restrict__ tile_off,
+              const int *__restrict__ chunk0, Chunk *__restrict__ chunks, int chunk) {
+    const int t = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (t >= ntiles) return;
+    const unsigned int h = hist[t];
+    const int nch = (int)((h + chunk - 1) / chunk), c0 = chunk0[t];
+    const long long off = tile_off[t];
+    for (int k = lane; k < nch; k += 32) {
+        Chunk ck; ck.start = off + (long long)k * chunk; ck.count = (int)min((unsigned int)chunk, h - (unsigned int)k * (unsigned int)chunk); ck.tile = t;
+        chunks[c0 + k] = ck;
     }
 }
 
