@@ -1139,8 +1139,6 @@ static bool ensure_snapshot(picsp_ctx *c) {
         int lo_prio = 0, hi_prio = 0;
         PICSP_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
         PICSP_CUDA(cudaStreamCreateWithPriority(&c->copy_stream2, cudaStreamNonBlocking, hi_prio));
-        const char *e = getenv("PICSP_DUMP_COPY_CTAS");     // experiment switch: CTAs of the copy kernel per species (0: copy engines)
-        c->dump_copy_ctas = e ? atoi(e) : 0;
     }
     return true;
 }
@@ -1217,25 +1215,12 @@ int picsp_dump_begin(picsp_ctx *c, double *rows_i, double *rows_e, double *den_i
     // the two species' rows go out on two streams (two copy engines): under a memory-bound mover one engine alone
     // does not fill the PCIe link
     PICSP_CUDA(cudaStreamWaitEvent(c->copy_stream2, c->ev_snap, 0));
+    // (a copy KERNEL on a high-priority stream instead of the copy engines was tried: it takes SM slots from the mover and
+    // is no faster over PCIe — e2e 5.1e10 -> 4.9e10 / 4.3e10 / 3.5e10 with 8 / 32 / 128 CTAs, profiles/r02_e2e_dumps.md)
     for (int s = 0; s < 2; s++)
-        if (rows[s] && c->sp[s].n > 0) {
-            cudaStream_t cs = s == 0 ? c->copy_stream : c->copy_stream2;
-            const size_t bytes = sizeof(double) * 4 * (size_t)c->sp[s].n;
-            bool by_kernel = false;
-            if (c->dump_copy_ctas > 0) {                       // page-locked destination, mapped into the device's address space?
-                cudaPointerAttributes at;
-                if (cudaPointerGetAttributes(&at, rows[s]) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
-                    k_copy_to_host<<<c->dump_copy_ctas, 256, 0, cs>>>(reinterpret_cast<const double2 *>(c->snap_rows[s]),
-                                                                     reinterpret_cast<double2 *>(at.devicePointer), (long long)(bytes / 16));
-                    PICSP_CUDA(cudaGetLastError());
-                    c->launches++;
-                    by_kernel = true;
-                } else {
-                    cudaGetLastError();
-                }
-            }
-            if (!by_kernel) PICSP_CUDA(cudaMemcpyAsync(rows[s], c->snap_rows[s], bytes, cudaMemcpyDeviceToHost, cs));
-        }
+        if (rows[s] && c->sp[s].n > 0)
+            PICSP_CUDA(cudaMemcpyAsync(rows[s], c->snap_rows[s], sizeof(double) * 4 * (size_t)c->sp[s].n, cudaMemcpyDeviceToHost,
+                                       s == 0 ? c->copy_stream : c->copy_stream2));
     PICSP_CUDA(cudaEventRecord(c->ev_dump_done, c->copy_stream));
     PICSP_CUDA(cudaEventRecord(c->ev_dump_done2, c->copy_stream2));
     c->dump_in_flight = true;

@@ -190,7 +190,6 @@ struct picsp_ctx {
     cudaEvent_t ev_snap = nullptr, ev_dump_done = nullptr, ev_dump_done2 = nullptr;
     cudaStream_t copy_stream2 = nullptr;         // second copy engine for the electrons' rows
     bool dump_in_flight = false;
-    int dump_copy_ctas = 0;                      // > 0: the rows leave through k_copy_to_host with that many CTAs instead of a copy engine
     double *dump_ke_host = nullptr;              // caller's [2]: the Q10 constant is added in picsp_dump_wait
     bool snapshot_unavailable = false;           // not enough memory for a snapshot: dumps are synchronous
 

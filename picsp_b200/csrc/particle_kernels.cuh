@@ -316,15 +316,4 @@ __global__ void k_rows_unpermute(const double *__restrict__ x, const double *__r
     }
 }
 
-// Device -> pinned-host copy done by a few CTAs instead of a copy engine (dump snapshots, picsp_dump_begin): under a
-// memory-bound mover the copy engines' HBM reads are starved (38 GB/s instead of 47 GB/s alone); a kernel's loads
-// compete like everybody else's.  16-byte stores, one 512-byte contiguous run per warp instruction.
-__global__ void __launch_bounds__(256)
-k_copy_to_host(const double2 *__restrict__ src, double2 *__restrict__ dst, long long n2) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
-        const double2 v = __ldcs(src + i);
-        __stcs(dst + i, v);
-    }
-}
-
 }  // namespace picsp
