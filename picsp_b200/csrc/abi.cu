@@ -380,7 +380,7 @@ void op_solve_sor(picsp_ctx *c) {
     PhaseScope ph(c, PICSP_PHASE_SOLVE);
     const Geom &g = c->g;
     const int bands = (g.nix + SOR_ROWS - 1) / SOR_ROWS;
-    if (bands <= c->num_sms && g.nix > SOR_DEPTH + 8 && g.niy >= 4 && !(c->prm.flags & PICSP_FLAG_SOR_SINGLE_CTA)) {
+    if (bands <= c->num_sms && !(c->prm.flags & PICSP_FLAG_SOR_SINGLE_CTA)) {
         // sweep 0 pipelined over co-resident bands, then the reference's convergence test; further sweeps
         // (never needed in practice) fall through to the single-CTA kernel
         PICSP_CUDA(cudaMemsetAsync(c->d_sor_progress, 0, sizeof(int) * bands, c->stream));

@@ -296,17 +296,6 @@ __device__ __forceinline__ double sor_pick(const double2 &pair, const double *gm
     return (reinterpret_cast<unsigned long long>(gmem_elem) & 8ull) ? pair.y : pair.x;
 }
 
-// Arithmetic of the pipelined sweep (round 2).  The reference's update (src/main.cpp:920-924) is
-//     g = coef*((up + down)/dx2 + (left + right)/dy2 + rho/eps);   v = center + 1.4*(g - center)
-// Evaluated literally, every step of the wavefront waits for ~10 dependent FP64 operations behind the one value it
-// really depends on (the neighbour row's NEW `up`).  The same quantity, grouped so that everything that is already
-// known sits in a precomputed term T, is
-//     v = (a1*up + (a2*left + T)),   T = ((1-1.4)*center + a1*down) + (a2*right + a3*rho)
-//     a1 = 1.4*coef/dx2, a2 = 1.4*coef/dy2, a3 = 1.4*coef/eps
-// and puts ONE FMA behind the arriving `up`.  T of the NEXT column is computed while this column's `up` is still in
-// flight (all its inputs are old values streamed ahead through the cp.async ring).  The rounding sequence differs from
-// the reference's in the last bit per node; the errors are damped along the sweep (a1 + a2 = 0.7 < 1), measured
-// <= 2e-15 of max|phi| against the literal single-CTA kernel (tests: 1e-13 required, 1e-12 against the reference).
 __global__ void __launch_bounds__(SOR_ROWS, 1)
 k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int niy, double dx, double dy,
                       int *progress) {
@@ -320,16 +309,16 @@ k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int 
     const bool last_row_of_band = (t == rows_here - 1);
     const double dx2 = dx * dx, dy2 = dy * dy, eps = 1.0;
     const double coef = 0.5 * (1 / ((1 / dx2) + (1 / dy2)));
-    const double a1 = 1.4 * coef / dx2, a2 = 1.4 * coef / dy2, a3 = 1.4 * coef / eps, am = 1.0 - 1.4;
+    const double rdx2 = 1 / dx2, rdy2 = 1 / dy2;
     const int q_row = (i + 1 > nix - 1) ? 1 : i + 1;          // src/main.cpp:917
     const int p_row = (i - 1 < 0) ? nix - 2 : i - 1;          // src/main.cpp:916
     const double *row = phi + (long long)(active ? i : 0) * niy;
     const double *row_q = phi + (long long)(active ? q_row : 0) * niy;
     const double *row_p = phi + (long long)(active ? p_row : 0) * niy;
     const double *rrho = rho + (long long)(active ? i : 0) * niy;
-    // row nix-1 reads the NEW phi(1, j): fetched ahead, gated by the previous band's progress (the launcher only uses
-    // this kernel when nix > D + 8, so row 1 is always far enough in front)
+    // row nix-1 reads the NEW phi(1, j); it may be fetched ahead only if row 1 is far enough in front
     const bool q_is_new = (i == nix - 1);
+    const bool q_prefetch_ok = !q_is_new || (nix > D + 8);
     const bool up_from_global = (t == 0);   // previous band's last row (b > 0), or the i == 0 wrap (old values)
     int granted = (b == 0) ? niy : 0;       // columns of the previous band known to be complete (polling threads only)
 
@@ -337,7 +326,7 @@ k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int 
     auto fetch = [&](int k, int jj) {
         if (active && jj >= 0 && jj < niy) {
             // Threads that read values ANOTHER band produces this sweep — thread 0 (new phi(i-1,.)) and the row
-            // nix-1 (new phi(1,.), implied by the previous band's progress) — wait for the previous band first
+            // nix-1 (new phi(1,.), implied by the previous band's progress) — wait for the previous band first,
             // (progress is published 16 columns at a time; this also covers the fetches issued before the first barrier).
             if ((up_from_global || q_is_new) && b > 0 && jj >= granted) {
                 const int want = min(jj + 1, niy);
@@ -345,59 +334,46 @@ k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int 
                 __threadfence();
             }
             if (jj < niy - 1) sor_cp_async16(&s_ring[k][0][t], &row[jj + 1]);      // old phi(i,jj+1); jj == niy-1 uses saved_col1
-            sor_cp_async16(&s_ring[k][1][t], &row_q[jj]);                          // old phi(i+1,jj) | new phi(1,jj)
+            if (q_prefetch_ok) sor_cp_async16(&s_ring[k][1][t], &row_q[jj]);       // old phi(i+1,jj) | new phi(1,jj)
             sor_cp_async16(&s_ring[k][2][t], &rrho[jj]);
             if (up_from_global) sor_cp_async16(&s_ring[k][3][t], &row_p[jj]);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    double left = 0.0, saved_col1 = 0.0;
-    double Tcur = 0.0, right_cur = 0.0, up_cur = 0.0;          // inputs of the column this thread works on next
-    if (active) { left = __ldcg(&row[niy - 2]); right_cur = __ldcg(&row[0]); }   // r wrap for j == 0 (old); phi_old(i,0) is column 0's centre
+    double left = 0.0, center = 0.0, saved_col1 = 0.0;
+    if (active) { left = __ldcg(&row[niy - 2]); center = __ldcg(&row[0]); }   // r wrap for j == 0 (old), phi_old(i,0)
 #pragma unroll
-    for (int k = 0; k < D - 1; k++) fetch(k, k - t);           // groups of steps 0 .. D-2; step -1 below issues D-1
+    for (int k = 0; k < D; k++) fetch(k, k - t);
 
     const int nsteps = niy + rows_here - 1;
-    for (int s0 = -1; s0 < nsteps; s0 += D) {
+    for (int s0 = 0; s0 < nsteps; s0 += D) {
 #pragma unroll
-        for (int kk = 0; kk < D; kk++) {
-            const int s = s0 + kk;
-            constexpr int DM1 = D - 1;
-            const int k = (kk + DM1) % D;                       // slot of step s (s0 == -1 mod D)
-            const int k1 = kk % D;                              // slot of step s + 1
+        for (int k = 0; k < D; k++) {
+            const int s = s0 + k;
             if (s < nsteps) {               // uniform across the CTA
                 const int j = s - t;
                 const bool work = active && j >= 0 && j < niy;
-                const bool next = active && j + 1 >= 0 && j + 1 < niy;
-                // 1. the one value this step waits for: the neighbour row's result of the previous step
-                double up = up_cur;
-                if (work && !up_from_global) up = s_new[(s + 1) & 1][t - 1];
-                // 2. meanwhile: everything the NEXT column needs that is already known
-                asm volatile("cp.async.wait_group %0;" ::"n"(D - 2) : "memory");   // the group that filled slot k1 has landed
-                double Tn = 0.0, right_n = 0.0, up_n = 0.0;
-                if (next) {
-                    const int jn = j + 1;
-                    right_n = (jn == niy - 1) ? saved_col1 : sor_pick(s_ring[k1][0][t], &row[jn + 1]);
-                    const double down = sor_pick(s_ring[k1][1][t], &row_q[jn]);
-                    const double rh = sor_pick(s_ring[k1][2][t], &rrho[jn]);
-                    if (up_from_global) up_n = sor_pick(s_ring[k1][3][t], &row_p[jn]);
-                    Tn = fma(a1, down, am * right_cur) + fma(a3, rh, a2 * right_n);     // right_cur = phi_old(i, jn): the next centre
-                }
-                // 3. this column
+                asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");   // the group that filled slot k has landed
                 if (work) {
-                    const double v = fma(a1, up, fma(a2, left, Tcur));
+                    const double right = (j == niy - 1) ? saved_col1 : sor_pick(s_ring[k][0][t], &row[j + 1]);
+                    const double down = q_prefetch_ok ? sor_pick(s_ring[k][1][t], &row_q[j]) : __ldcg(&row_q[j]);
+                    const double rh = sor_pick(s_ring[k][2][t], &rrho[j]);
+                    const double up = up_from_global ? sor_pick(s_ring[k][3][t], &row_p[j])
+                                                     : s_new[(s + 1) & 1][t - 1];   // written at step s-1 by thread t-1
+                    const double g = coef * (sor_div(up + down, dx2, rdx2) + sor_div(left + right, dy2, rdy2) + (rh / eps));
+                    const double v = center + 1.4 * (g - center);
                     __stcg(&phi[(long long)i * niy + j], v);
                     s_new[s & 1][t] = v;
                     if (j == 1) saved_col1 = v;
                     left = v;
+                    center = right;         // phi_old(i, j+1) is the next centre
                     if (last_row_of_band && ((j & 15) == 15 || j == niy - 1)) {   // one gpu-scope fence (~770 cycles) per 16 columns
                         __threadfence();
                         *(volatile int *)&progress[b] = j + 1;
                     }
                 }
-                if (next) { Tcur = Tn; right_cur = right_n; up_cur = up_n; }
-                fetch(k, j + D);            // refill the slot this step used, for step s + D
+                fetch(k, j + D);            // refill this slot for step s + D
                 __syncthreads();
             }
         }
