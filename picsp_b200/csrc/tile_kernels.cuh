@@ -741,14 +741,18 @@ __device__ __forceinline__ unsigned long long warp_sum52(unsigned m, unsigned lo
 #define PICSP_AGG_MIN 4        // lanes of a warp in one cell from which their deposits are combined before touching shared memory
 #endif
 #ifndef PICSP_AGG_ROUNDS
-#define PICSP_AGG_ROUNDS 3     // cells per warp that get combined; lanes of further cells deposit individually
+#define PICSP_AGG_ROUNDS 2     // cells per warp that get combined (0: never); lanes of further cells deposit individually
 #endif
 
 // Warp-aggregated commit.  Lanes of a warp whose particles sit in the SAME cell would hit the same eight
 // shared-memory words and serialise (a cell-ordered store, or the reference's own diagonal two-stream load with
-// ~5e5 particles per occupied cell): one MATCH finds the lanes per cell, the fixed-point weights of a
-// group are summed exactly with REDUX and its first lane alone touches the accumulators.  Integer sums: the
-// result is bit-identical to the lane-by-lane deposit.  Returns true when the deposit stayed inside the window.
+// ~5e5 particles per occupied cell).  Up to two groups per warp are combined: the lanes that share the
+// cell of lane 0 (or, when lane 0 is a stray, of the first lane outside its group), then the largest-looking group
+// among the rest (the two interleaved beams of the diagonal load); the fixed-point weights of a group are summed
+// exactly with REDUX and its first lane alone touches the accumulators; every other lane deposits for itself.
+// One SHFL + one VOTE per group instead of a MATCH (round-2 ncu: MATCH + POPC + VOTE and its loop made the
+// ordered-store kernel issue-bound).  Integer sums: the result is bit-identical to the lane-by-lane deposit.
+// Returns true when the deposit stayed inside the window.
 __device__ __forceinline__ bool deposit_commit(const Deposit &dp, unsigned act, bool aggregate, const PushConst &c, unsigned *sLo,
                                                unsigned *sHi, long long *__restrict__ acc) {
     unsigned long long v00 = dp.w00, v10 = dp.w10, v01 = dp.w01, v11 = dp.w11;
@@ -756,18 +760,25 @@ __device__ __forceinline__ bool deposit_commit(const Deposit &dp, unsigned act, 
     if (PICSP_AGG_ROUNDS > 0 && aggregate && act == 0xffffffffu) {       // full warps only; the tail slice of a chunk takes the plain path
         const unsigned lane = threadIdx.x & 31u;
         const int key = dp.mode == 1 ? dp.k : -1 - (int)lane;                 // lanes without a window deposit match nobody
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
-        unsigned big = __ballot_sync(0xffffffffu, __popc(peers) >= PICSP_AGG_MIN);
-#pragma unroll 1
-        for (int r = 0; r < PICSP_AGG_ROUNDS && big; r++) {
-            const int ld = __ffs(big) - 1;
-            const unsigned m = __shfl_sync(0xffffffffu, peers, ld);
-            if ((m >> lane) & 1u) {
-                v00 = warp_sum52(m, dp.w00); v10 = warp_sum52(m, dp.w10);
-                v01 = warp_sum52(m, dp.w01); v11 = warp_sum52(m, dp.w11);
-                own = (int)lane == ld;
+        unsigned done = 0u;
+#pragma unroll
+        for (int r = 0; r < PICSP_AGG_ROUNDS; r++) {
+            int ld = __ffs(~done) - 1;                                         // first lane not yet in a group (r == 0: lane 0)
+            unsigned m = __ballot_sync(0xffffffffu, key == __shfl_sync(0xffffffffu, key, ld)) & ~done;
+            if (r == 0 && __popc(m) < 8 && m != 0xffffffffu) {                // lane 0 is a stray of an ordered warp: try its first non-member
+                const int l1 = __ffs(~m) - 1;
+                const unsigned m1 = __ballot_sync(0xffffffffu, key == __shfl_sync(0xffffffffu, key, l1));
+                if (__popc(m1) > __popc(m)) { m = m1; ld = l1; }
             }
-            big &= ~m;
+            if (__popc(m) >= PICSP_AGG_MIN) {                                  // warp-uniform
+                if ((m >> lane) & 1u) {
+                    v00 = warp_sum52(m, dp.w00); v10 = warp_sum52(m, dp.w10);
+                    v01 = warp_sum52(m, dp.w01); v11 = warp_sum52(m, dp.w11);
+                    own = (int)lane == ld;
+                }
+            }
+            done |= m;
+            if (done == 0xffffffffu) break;
         }
     }
     if (own) {
