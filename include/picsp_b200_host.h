@@ -29,6 +29,11 @@ typedef struct picsp_run_config {
  * Returns PICSP_ERR_INVALID where the reference would exit(EXIT_FAILURE) (main.cpp:323-326). */
 int picsp_host_parse_ini(const char *path, picsp_run_config *out, int print_banner);
 
+/* Every "section:key" <TAB> value <NEWLINE> pair the reader finds in a file (keys lower-cased, sorted), for checking the
+ * reader against iniparser's own fixtures.  Returns the number of bytes needed (including the terminating NUL) or a
+ * negative error code; writes at most buflen bytes. */
+int64_t picsp_host_ini_dump(const char *path, char *buf, int64_t buflen);
+
 /* The loader (main.cpp:567-617) with the reference's RNG (std::mt19937(seed) +
  * uniform_real_distribution<double>(0,1), main.cpp:49-54).  One loader carries the RNG state and the
  * loadType-2 recurrence across species; fill ions (species 0) first, then electrons, as main does. */

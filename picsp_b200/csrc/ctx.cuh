@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cufft.h>
 #include <nccl.h>      // types only; the library is dlopen'ed in comm.cuh
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges are no-ops unless a profiler injects itself
 
 #include <cstdint>
 #include <cstdio>
@@ -208,9 +209,16 @@ struct picsp_ctx {
 namespace picsp {
 
 // RAII phase scope: CUDA events on the library's stream when profiling is on.
+inline const char *phase_name(int ph) {
+    static const char *names[PICSP_PHASE_COUNT] = {"picsp:deposit", "picsp:rho", "picsp:allreduce", "picsp:solve", "picsp:ef", "picsp:push",
+                                                    "picsp:sort", "picsp:step", "picsp:push_ions", "picsp:push_electrons"};
+    return ph >= 0 && ph < PICSP_PHASE_COUNT ? names[ph] : "picsp";
+}
+
 struct PhaseScope {
     picsp_ctx *c; int phase; cudaEvent_t e0 = nullptr, e1 = nullptr;
     PhaseScope(picsp_ctx *ctx, int ph) : c(ctx), phase(ph) {
+        nvtxRangePushA(phase_name(ph));          // NVTX range per phase (nsys / ncu --nvtx timelines)
         if (!c->profiling) return;
         PhaseTimer &t = c->timers[phase];
         while (t.pool.size() < t.used + 2) {
@@ -222,6 +230,7 @@ struct PhaseScope {
     ~PhaseScope() {
         if (e1) cudaEventRecord(e1, c->stream);
         if (c->profiling) c->timers[phase].calls++;
+        nvtxRangePop();
     }
 };
 

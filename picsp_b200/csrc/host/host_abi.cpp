@@ -1,4 +1,6 @@
 // extern "C" face of the host driver (include/picsp_b200_host.h).
+#include <algorithm>
+#include <cstring>
 #include <iostream>
 
 #include "host.hpp"
@@ -12,6 +14,20 @@ int picsp_host_parse_ini(const char *path, picsp_run_config *out, int print_bann
     std::string err;
     try { return picsp_host::parse_run_config(path, *out, print_banner != 0, &err); }
     catch (...) { return PICSP_ERR_INVALID; }
+}
+
+int64_t picsp_host_ini_dump(const char *path, char *buf, int64_t buflen) {
+    if (!path) return PICSP_ERR_INVALID;
+    picsp_host::IniFile ini;
+    std::string err;
+    try { if (!ini.load(path, &err)) return PICSP_ERR_INVALID; } catch (...) { return PICSP_ERR_INVALID; }
+    std::string out;
+    for (const auto &kv : ini.entries()) { out += kv.first; out += '\t'; out += kv.second; out += '\n'; }
+    if (buf && buflen > 0) {
+        const size_t n = std::min<size_t>(out.size(), (size_t)buflen - 1);
+        std::memcpy(buf, out.data(), n); buf[n] = 0;
+    }
+    return (int64_t)out.size() + 1;
 }
 
 picsp_loader *picsp_host_loader_create(uint32_t seed) {

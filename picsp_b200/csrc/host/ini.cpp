@@ -47,13 +47,20 @@ bool IniFile::load(const std::string &path, std::string *err) {
         std::string key = lower(strip(t.substr(0, eq)));
         std::string rest = strip(t.substr(eq + 1));
         std::string val;
-        if (rest.size() >= 2 && rest[0] == '"' && rest.find('"', 1) != std::string::npos) {
-            val = rest.substr(1, rest.find('"', 1) - 1);
-        } else if (rest.size() >= 2 && rest[0] == '\'' && rest.find('\'', 1) != std::string::npos) {
-            val = rest.substr(1, rest.find('\'', 1) - 1);
+        // iniparser_line() tries a double-quoted form, then a single-quoted one, then "everything up to ; or #"
+        // (iniparser.c:583-585).  A quoted value needs at least one character that is not the quote, and sscanf does
+        // not insist on the closing quote; an empty pair of quotes falls through to the third form and is then mapped
+        // to the empty string (:594-596), while three or more quotes in a row stay as they are.
+        if (rest.size() >= 2 && rest[0] == '"' && rest[1] != '"') {
+            const size_t close = rest.find('"', 1);
+            val = strip(rest.substr(1, close == std::string::npos ? std::string::npos : close - 1));
+        } else if (rest.size() >= 2 && rest[0] == '\'' && rest[1] != '\'') {
+            const size_t close = rest.find('\'', 1);
+            val = strip(rest.substr(1, close == std::string::npos ? std::string::npos : close - 1));
         } else {
             size_t cut = rest.find_first_of(";#");
             val = strip(cut == std::string::npos ? rest : rest.substr(0, cut));
+            if (val == "\"\"" || val == "''") val.clear();
         }
         kv_[section.empty() ? key : section + ":" + key] = val;
     }

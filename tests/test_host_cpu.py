@@ -108,3 +108,44 @@ def test_h5_writer_roundtrip(tmp_path):
     for k, a in data.items():
         assert np.array_equal(f.read(k), a), k
     assert open(path, "rb").read(8) == b"\x89HDF\r\n\x1a\n"
+
+
+TWISTED = "/root/reference/lib/iniparser/test/twisted.ini"
+
+
+@pytest.mark.skipif(not os.path.isfile(TWISTED), reason="iniparser's own fixture lives in the reference tree (build container only)")
+def test_ini_reader_agrees_with_iniparser_on_its_own_twisted_fixture():
+    """The reference's vendored iniparser 3.1 ships `twisted.ini`, 131 lines of blank / comment / quote / trailing-';'
+    edge cases.  Every `section:key` that the reference's parser (compiled from the reference tree into
+    oracle/_ref/libpicsp_ref.so) reports must come out of the product's own reader with the same value."""
+    from oracle.oracle import REF_SO
+    if not os.path.isfile(REF_SO):
+        pytest.skip("oracle/_ref not built")
+    R = C.CDLL(REF_SO)
+    R.iniparser_load.argtypes = [C.c_char_p]; R.iniparser_load.restype = C.c_void_p
+    R.iniparser_getstring.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]; R.iniparser_getstring.restype = C.c_char_p
+    R.iniparser_freedict.argtypes = [C.c_void_p]
+    R.iniparser_getnsec.argtypes = [C.c_void_p]; R.iniparser_getnsec.restype = C.c_int
+    R.iniparser_getsecname.argtypes = [C.c_void_p, C.c_int]; R.iniparser_getsecname.restype = C.c_char_p
+    R.iniparser_getsecnkeys.argtypes = [C.c_void_p, C.c_char_p]; R.iniparser_getsecnkeys.restype = C.c_int
+    R.iniparser_getseckeys.argtypes = [C.c_void_p, C.c_char_p]; R.iniparser_getseckeys.restype = C.POINTER(C.c_char_p)
+    d = R.iniparser_load(TWISTED.encode())
+    assert d
+    want = {}
+    for s in range(R.iniparser_getnsec(d)):
+        sec = R.iniparser_getsecname(d, s)
+        n = R.iniparser_getsecnkeys(d, sec)
+        keys = R.iniparser_getseckeys(d, sec)
+        for k in range(n):
+            key = keys[k]
+            want[key.decode()] = R.iniparser_getstring(d, key, b"<missing>").decode()
+    R.iniparser_freedict(d)
+    assert len(want) >= 30
+    L = picsp_b200.load_library()
+    need = L.picsp_host_ini_dump(TWISTED.encode(), None, 0)
+    assert need > 0
+    buf = C.create_string_buffer(need)
+    assert L.picsp_host_ini_dump(TWISTED.encode(), buf, need) == need
+    got = dict(line.split("\t", 1) for line in buf.value.decode().split("\n") if "\t" in line)
+    bad = {k: (got.get(k), v) for k, v in want.items() if got.get(k) != v}
+    assert not bad, f"reader differs from iniparser on {len(bad)} of {len(want)} keys: {dict(list(bad.items())[:8])}"
