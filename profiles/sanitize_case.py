@@ -24,3 +24,19 @@ for numx, numy, n, period, flags in ((40, 72, 20003, 1, 0), (32, 20, 9001, 3, 0)
         sim.bootstrap(); sim.step(7)
         x, y, vx, vy = sim.get_species(ELECTRON)
         print(numx, numy, period, flags, sim.computeKE(ELECTRON), float(x.max()), sim.straggler_count(ELECTRON), sim.repush_count(ELECTRON))
+# round 2: cell order inside a bin + warp-aggregated deposit (forced on), a clustered load (REDUX groups, two
+# interleaved groups), the asynchronous dump, the walls extension (cooperative red-black SOR, absorption)
+for numx, numy, n, cell, agg in ((48, 40, 30001, 2, -1), (64, 64, 40000, 0, 1)):
+    with Simulation(Params(numx, numy, nm["dx"], nm["dt"], nm["mass_i"], n, n, solverType=1)) as sim:
+        sim.set_sort_period(ELECTRON, 3); sim.set_cell_sort_period(ION, cell); sim.set_cell_sort_period(ELECTRON, cell)
+        sim.set_deposit_aggregation(ION, agg); sim.set_deposit_aggregation(ELECTRON, agg)
+        x = rng.random(n) * numx * nm["dx"]; y = rng.random(n) * numy * nm["dx"]
+        x[: n // 2] = (7 + (np.arange(n // 2) & 1) + rng.random(n // 2)) * nm["dx"]; y[: n // 2] = (9 + rng.random(n // 2)) * nm["dx"]
+        sim.set_species(ION, x, y, 0 * x, 0 * x); sim.set_species(ELECTRON, x, y, rng.standard_normal(n), rng.standard_normal(n))
+        sim.bootstrap(); sim.step(6)
+        d = sim.dump()
+        print("r2", numx, cell, agg, float(d["ke"][1]), float(d["rows_e"][:, 0].max()), sim.computeKE(ION))
+with Simulation(Params(40, 56, nm["dx"], nm["dt"], nm["mass_i"], 20000, 20000, solverType=2, flags=64 | 1)) as sim:
+    sim.fill_synthetic(ION, 20000, seed=5, vth=nm["vth_i"]); sim.fill_synthetic(ELECTRON, 20000, seed=6, vth=5.0)
+    sim.bootstrap(); sim.step(5)
+    print("walls", sim.solve_status(), sim.repush_count(ELECTRON), int(np.isnan(sim.get_species(ELECTRON)[0]).sum()))
