@@ -755,9 +755,32 @@ __device__ __forceinline__ unsigned long long warp_sum52(unsigned m, unsigned lo
 // Returns true when the deposit stayed inside the window.
 __device__ __forceinline__ bool deposit_commit(const Deposit &dp, unsigned act, bool aggregate, const PushConst &c, unsigned *sLo,
                                                unsigned *sHi, long long *__restrict__ acc) {
+    if (!(PICSP_AGG_ROUNDS > 0 && aggregate && act == 0xffffffffu)) {
+        // the plain commit (every lane for itself), kept as a block of its own so that the common case carries none of
+        // the aggregation's register traffic.  Full warps only aggregate; the tail slice of a chunk comes here too.
+        if (dp.mode == 1) {
+            int k = dp.k;
+            if (REPL > 1) {
+                const unsigned peers = __match_any_sync(__activemask(), k & 7);
+                const int rank = __popc(peers & ((1u << (threadIdx.x & 31u)) - 1u));
+                const int r = (((k & 7) + 8 * (rank & 3) - k) >> 3) & 3;
+                k += r * ACC_COPY;
+            }
+            add64_limbs(sLo, sHi, k, dp.w00);
+            add64_limbs(sLo, sHi, k + WIN, dp.w10);
+            add64_limbs(sLo, sHi, k + 1, dp.w01);
+            add64_limbs(sLo, sHi, k + WIN + 1, dp.w11);
+            return true;
+        }
+        if (dp.mode == 2) {
+            unsigned long long *g = reinterpret_cast<unsigned long long *>(acc) + ((long long)dp.i * c.niy + dp.j);
+            atomicAdd(g, dp.w00); atomicAdd(g + c.niy, dp.w10); atomicAdd(g + 1, dp.w01); atomicAdd(g + c.niy + 1, dp.w11);
+        }
+        return false;
+    }
     unsigned long long v00 = dp.w00, v10 = dp.w10, v01 = dp.w01, v11 = dp.w11;
     bool own = dp.mode == 1;
-    if (PICSP_AGG_ROUNDS > 0 && aggregate && act == 0xffffffffu) {       // full warps only; the tail slice of a chunk takes the plain path
+    {
         const unsigned lane = threadIdx.x & 31u;
         const int key = dp.mode == 1 ? dp.k : -1 - (int)lane;                 // lanes without a window deposit match nobody
         unsigned done = 0u;
