@@ -264,6 +264,19 @@ def main_ours(args, rank, world, local_rank):
     def make_sim():
         sim = Simulation(Params(args.cells, args.cells, nm["dx"], nm["dt"], nm["mass_i"], n_species, n_species,
                                 solverType=1, device=local_rank, capacity=(n_local, n_local), flags=args.flags))
+        # tuning switches first: the first binning happens inside the fill / upload
+        if args.sort_period_e > 0:
+            sim.set_sort_period(ELECTRON, args.sort_period_e)
+        if args.sort_period_i > 0:
+            sim.set_sort_period(ION, args.sort_period_i)
+        if args.cell_period_e >= 0:
+            sim.set_cell_sort_period(ELECTRON, args.cell_period_e)
+        if args.cell_period_i >= 0:
+            sim.set_cell_sort_period(ION, args.cell_period_i)
+        if args.bank_order_e is not None:
+            sim.set_bank_order(ELECTRON, args.bank_order_e)
+        if args.bank_order_i is not None:
+            sim.set_bank_order(ION, args.bank_order_i)
         if args.load == "synthetic":
             sim.fill_synthetic(ION, n_local, first_index=lo, seed=1, vth=nm["vth_i"], xdrift=0.0)
             sim.fill_synthetic(ELECTRON, n_local, first_index=lo, seed=2, vth=nm["vth_e"], xdrift=nm["drift_e"])
@@ -288,14 +301,6 @@ def main_ours(args, rank, world, local_rank):
             u = [Simulation.comm_unique_id() if rank == 0 else None]     # one NCCL communicator per context
             dist.broadcast_object_list(u, src=0)
             sim.comm_attach(u[0], rank, world)
-        if args.sort_period_e > 0:
-            sim.set_sort_period(ELECTRON, args.sort_period_e)
-        if args.sort_period_i > 0:
-            sim.set_sort_period(ION, args.sort_period_i)
-        if args.cell_period_e >= 0:
-            sim.set_cell_sort_period(ELECTRON, args.cell_period_e)
-        if args.cell_period_i >= 0:
-            sim.set_cell_sort_period(ION, args.cell_period_i)
         if args.agg is not None:
             sim.set_deposit_aggregation(ION, args.agg); sim.set_deposit_aggregation(ELECTRON, args.agg)
         return sim
@@ -498,6 +503,8 @@ def main():
     ap.add_argument("--agg", type=int, default=None, choices=[-1, 0, 1], help="warp-aggregated deposit: -1 automatic (library default), 0 off, 1 on")
     ap.add_argument("--cell-period-e", type=int, default=-1, help="steps between electron cell orderings (-1: library default, 0: never)")
     ap.add_argument("--cell-period-i", type=int, default=-1, help="steps between ion cell orderings (-1: library default, 0: never)")
+    ap.add_argument("--bank-order-e", type=int, default=None, choices=[-1, 0, 1], help="bank order inside the electron chunks after a re-binning: -1 automatic (library default: off), 0 off, 1 on")
+    ap.add_argument("--bank-order-i", type=int, default=None, choices=[-1, 0, 1], help="the same for ions (library default: on)")
     ap.add_argument("--sort-period-e", type=int, default=0, help="steps between electron tile sorts (0: library default)")
     ap.add_argument("--sort-period-i", type=int, default=0, help="steps between ion tile sorts (0: library default)")
     ap.add_argument("--flags", type=int, default=0, help="PICSP_FLAG_* bits for A/B runs (16: stand-alone re-sort instead of the re-binning mover)")

@@ -167,6 +167,12 @@ int picsp_set_sort_period(picsp_ctx *ctx, int species, int period);
  * on B200 the ordered store halves the shared-memory traffic of the mover but the aggregation costs as many issue slots
  * as it saves, profiles/r02_mover_aggregation.md). */
 int picsp_set_cell_sort_period(picsp_ctx *ctx, int species, int period);
+/* Bank order inside the mover's work items (chunks of <= 4096 particles of one tile): after every (re-)binning of the
+ * species its particles are permuted, in place, so that the lanes of a warp sit on distinct shared-memory banks when
+ * they gather E and deposit (no bank conflicts, no extra instruction in the mover).  -1 automatic (default: species that
+ * are re-binned every >= 32 steps, i.e. ions, whose particles keep their cells in between), 0 off, 1 on.  Storage order
+ * only: results are bit-identical. */
+int picsp_set_bank_order(picsp_ctx *ctx, int species, int mode);
 /* Warp-aggregated deposit (lanes of a warp whose particles share a cell combine their weights with REDUX before touching
  * shared memory): -1 automatic (default: on for a cell-ordered store and for loads concentrated on few bins, such as the
  * reference's diagonal loadType 2), 0 off, 1 on.  Speed only: integer accumulation makes the result bit-identical. */

@@ -121,6 +121,8 @@ void compute_frac(picsp_ctx *c, int s) {
 
 // -- tile binning -------------------------------------------------------------------------
 int mover_grid(const Species &sp);
+bool bank_order_on(const Species &sp);
+void op_bank_order(picsp_ctx *c, int s);
 
 // Particles per CTA work item: CHUNK (4096) for big populations; smaller when there are too few particles to give
 // every SM several waves of CTAs (tail effect), never below 512, always a multiple of the slice size.
@@ -183,6 +185,7 @@ void op_sort(picsp_ctx *c, int s) {
         PICSP_LAUNCH(c, (k_sort_pass<false>), blocks, SORT2_THREADS, SORT2_SMEM_BYTES, sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2, (long long)sp.n,
                      push_const(c, s), shift, sp.tile_off, sp.cursor, sp.x, sp.y, sp.vx, sp.vy, sp.id);
         sort_finish(c, s, false);
+        if (bank_order_on(sp)) op_bank_order(c, s);
         return;
     }
     if (sp.n > 0) {
@@ -195,6 +198,7 @@ void op_sort(picsp_ctx *c, int s) {
                          (long long)sp.n, push_const(c, s), sp.tile_off, sp.cursor, sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2);
     }
     sort_finish(c, s);
+    if (bank_order_on(sp)) op_bank_order(c, s);
 }
 
 // Cell order inside every bin (stand-alone; see tile_kernels.cuh).  Particles stay in their bin's range; the result is
@@ -231,6 +235,20 @@ void op_cell_sort(picsp_ctx *c, int s) {
 int mover_grid(const Species &sp) {
     long long b = sp.n / sp.chunk + sp.ntiles + 1;   // upper bound on the number of chunks
     return (int)std::max<long long>(1, std::min<long long>(b, sp.max_chunks));
+}
+
+// Bank order inside every chunk (see tile_kernels.cuh): in place, chunk table and counts untouched.  Automatic mode:
+// species that are re-binned rarely (ions: every 96 steps), whose particles keep their cells between two re-binnings.
+bool bank_order_on(const Species &sp) { return sp.bank_order < 0 ? (sp.sort_period >= 32 && sp.cell_period == 0) : sp.bank_order > 0; }
+void op_bank_order(picsp_ctx *c, int s) {
+    Species &sp = c->sp[s];
+    if (!BULK_PIPE || !sp.sorted || !sp.has_perm || sp.n <= 0) return;       // (callers open the PICSP_PHASE_SORT scope)
+    if (!c->bankorder_opted_in) {
+        PICSP_CUDA(cudaFuncSetAttribute(k_bank_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BANKORDER_SMEM_BYTES));
+        c->bankorder_opted_in = true;
+    }
+    PICSP_LAUNCH(c, k_bank_order, mover_grid(sp), SORT2_THREADS, BANKORDER_SMEM_BYTES, sp.x, sp.y, sp.vx, sp.vy, sp.id,
+                 (const Chunk *)sp.chunks, sp.nchunks, push_const(c, s), sp.frac);
 }
 
 template <int MODE> void launch_tile_mover(picsp_ctx *c, int s) {
@@ -445,34 +463,38 @@ void op_push(picsp_ctx *c, int s) {
     if (rebin_in_mover) { PhaseScope phs(c, PICSP_PHASE_SORT); sort_prepare(c, s); }
     if (fuse || tile) ensure_hist(c, s);   // histogram of the positions about to be pushed -> bound for acc
     if (fuse) compute_frac(c, s);
-    PhaseScope ph(c, PICSP_PHASE_PUSH);
-    PhaseScope phs(c, s == 0 ? PICSP_PHASE_PUSH_IONS : PICSP_PHASE_PUSH_ELECTRONS);
-    PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
-    const int nt = c->g.ntx * c->g.nty;
-    if (fuse || tile) PICSP_CUDA(cudaMemsetAsync(sp.hist_next, 0, sizeof(unsigned int) * nt, c->stream));
-    if (fuse && sp.acc_valid)   // a previous fused push was never consumed by a deposit: drop it
-        PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
-    if (sp.n > 0) {
-        if (tile) {
-            if (rebin_in_mover && sp.cnt_valid) {
-                // the previous launch counted, per chunk, where its particles went: reserve the ranges up front
-                const long long q = 9ll * mover_grid(sp);
-                PICSP_LAUNCH(c, k_rebin_bases, (int)((q + 255) / 256), 256, 0, (const Chunk *)sp.chunks, sp.nchunks, c->g.ntx, c->g.nty,
-                             sp.chunk_cnt, sp.tile_off, sp.cursor, sp.chunk_base, c->d_error);
-                launch_tile_mover<4>(c, s); sort_finish(c, s);
-            } else if (rebin_in_mover) { launch_tile_mover<3>(c, s); sort_finish(c, s); }
-            else if (fuse) { launch_tile_mover<0>(c, s); sp.cnt_valid = sp.chunk_cnt != nullptr; }
-            else launch_tile_mover<2>(c, s);
-        } else {
-            const int blocks = particle_blocks(c, sp.n, 256);
-            if (fuse)
-                PICSP_LAUNCH(c, (k_push<true>), blocks, 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n, push_const(c, s),
-                             c->E, sp.acc, sp.frac, sp.hist_next, sp.counters, c->d_error);
-            else
-                PICSP_LAUNCH(c, (k_push<false>), blocks, 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n, push_const(c, s),
-                             c->E, sp.acc, sp.frac, sp.hist_next, sp.counters, c->d_error);
+    bool rebinned = false;
+    {
+        PhaseScope ph(c, PICSP_PHASE_PUSH);
+        PhaseScope phs(c, s == 0 ? PICSP_PHASE_PUSH_IONS : PICSP_PHASE_PUSH_ELECTRONS);
+        PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
+        const int nt = c->g.ntx * c->g.nty;
+        if (fuse || tile) PICSP_CUDA(cudaMemsetAsync(sp.hist_next, 0, sizeof(unsigned int) * nt, c->stream));
+        if (fuse && sp.acc_valid)   // a previous fused push was never consumed by a deposit: drop it
+            PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
+        if (sp.n > 0) {
+            if (tile) {
+                if (rebin_in_mover && sp.cnt_valid) {
+                    // the previous launch counted, per chunk, where its particles went: reserve the ranges up front
+                    const long long q = 9ll * mover_grid(sp);
+                    PICSP_LAUNCH(c, k_rebin_bases, (int)((q + 255) / 256), 256, 0, (const Chunk *)sp.chunks, sp.nchunks, c->g.ntx, c->g.nty,
+                                 sp.chunk_cnt, sp.tile_off, sp.cursor, sp.chunk_base, c->d_error);
+                    launch_tile_mover<4>(c, s); sort_finish(c, s); rebinned = true;
+                } else if (rebin_in_mover) { launch_tile_mover<3>(c, s); sort_finish(c, s); rebinned = true; }
+                else if (fuse) { launch_tile_mover<0>(c, s); sp.cnt_valid = sp.chunk_cnt != nullptr; }
+                else launch_tile_mover<2>(c, s);
+            } else {
+                const int blocks = particle_blocks(c, sp.n, 256);
+                if (fuse)
+                    PICSP_LAUNCH(c, (k_push<true>), blocks, 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n, push_const(c, s),
+                                 c->E, sp.acc, sp.frac, sp.hist_next, sp.counters, c->d_error);
+                else
+                    PICSP_LAUNCH(c, (k_push<false>), blocks, 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n, push_const(c, s),
+                                 c->E, sp.acc, sp.frac, sp.hist_next, sp.counters, c->d_error);
+            }
         }
     }
+    if (rebinned && bank_order_on(sp)) { PhaseScope phs(c, PICSP_PHASE_SORT); op_bank_order(c, s); }    // the new layout, in bank order
     if (fuse || tile) {
         std::swap(sp.hist, sp.hist_next);
         sp.hist_valid = true;
@@ -1311,6 +1333,14 @@ int picsp_set_cell_sort_period(picsp_ctx *c, int s, int period) {
     check_ctx(c); check_species(s);
     c->sp[s].cell_period = period > 0 ? period : 0;
     c->sp[s].steps_since_cellsort = c->sp[s].cell_period;       // due at the next push
+    PICSP_API_END
+}
+
+int picsp_set_bank_order(picsp_ctx *c, int s, int mode) {
+    PICSP_API_BEGIN
+    check_ctx(c); check_species(s);
+    PICSP_REQUIRE(mode >= -1 && mode <= 1, PICSP_ERR_INVALID, "bank order mode must be -1 (automatic), 0 (off) or 1 (on)");
+    c->sp[s].bank_order = mode;
     PICSP_API_END
 }
 

@@ -102,6 +102,7 @@ struct Species {
     int cell_period = 0;           // steps between two cell orderings (0: never)
     int aggregate = -1;            // warp-aggregated deposit: -1 automatic (cell-ordered store or concentrated load), 0 off, 1 on
     int steps_since_cellsort = 0;
+    int bank_order = -1;           // bank order inside the chunks after every (re-)binning (k_bank_order): -1 automatic (slow species), 0 off, 1 on
     unsigned int *cell_cnt = nullptr;    // [chunks][CELLKEYS] populations, then first slots
     long long cell_cnt_chunks = 0;
     int *tile_chunk0 = nullptr;          // [ntiles] first chunk of every bin
@@ -148,6 +149,7 @@ struct picsp_ctx {
     bool hist_smem_opted_in = false;
     bool sort2_opted_in = false;
     bool cellsort_opted_in = false;
+    bool bankorder_opted_in = false;
 
     // staging for grid component uploads/downloads
     double *stage = nullptr; int64_t stage_cap = 0;

@@ -38,6 +38,7 @@ namespace picsp {
 #ifndef PICSP_CHUNK
 #define PICSP_CHUNK 4096
 #endif
+
 constexpr int HALO = PICSP_HALO;              // cells of drift a window tolerates on each side
 constexpr int WIN = TILE + 1 + 2 * HALO;      // window edge in nodes (25)
 // Bank-conflict avoidance by replication.  Particle positions inside a tile are random, so the 16-byte E
@@ -48,10 +49,18 @@ constexpr int WIN = TILE + 1 + 2 * HALO;      // window edge in nodes (25)
 // that lands it on a bank of its own.  All copies hold the same E and the accumulator copies are summed at
 // the flush, so ANY choice is correct: the choice only decides speed.
 constexpr int REPL = PICSP_REPL;
-constexpr int WPITCH = (REPL > 1) ? WIN + 2 * (REPL - 1) : WIN;        // E row pitch in nodes (copy r starts 2r nodes in)
+// Row pitch of the window in nodes.  With pitch 26 the 16 x 16 cells of a tile spread EVENLY over the 32 residues of
+// (row * pitch + column) mod 32 (8 cells each; with pitch 25 it is 6..10), which suits k_bank_order — but the unordered
+// electrons run 2 % slower with it (same-box A/B, profiles/r02b_mover_bank_order.md), so the pitch stays WIN.
+#ifndef PICSP_WIN_PAD
+#define PICSP_WIN_PAD 0       // 1: pitch 26 (even classes for k_bank_order) — measured 2 % slower for unordered particles, so 25 it is
+#endif
+constexpr int WPITCH = (REPL > 1) ? WIN + 2 * (REPL - 1) : WIN + PICSP_WIN_PAD;    // E row pitch (replicated: copy r starts 2r nodes in)
+constexpr int APITCH = (REPL > 1) ? WIN : WIN + PICSP_WIN_PAD;                     // accumulator row pitch in words
 constexpr int E_COPY = ((WIN * WPITCH + 7) / 8) * 8;                   // nodes per E copy: multiple of 8 bank groups
-constexpr int ACC_COPY = (REPL > 1) ? (((WIN * WIN + 23) / 32) * 32 + 8) : WIN * WIN;   // words per accumulator copy: == 8 (mod 32)
+constexpr int ACC_COPY = (REPL > 1) ? (((WIN * WIN + 23) / 32) * 32 + 8) : WIN * APITCH;   // words per accumulator copy (replicated: == 8 (mod 32))
 static_assert(REPL == 1 || REPL == 4, "REPL must be 1 or 4");
+static_assert(REPL > 1 || APITCH == WPITCH, "k_bank_order assumes one pitch for the E window and the accumulators");
 static_assert(REPL == 1 || (ACC_COPY % 32 == 8 && ACC_COPY >= WIN * WIN), "accumulator copy stride must be 8 mod 32");
 constexpr size_t MOVER_WINDOW_BYTES = ((sizeof(double2) * (size_t)REPL * E_COPY + 2 * sizeof(unsigned) * (size_t)REPL * ACC_COPY + 127) / 128) * 128;
 constexpr int CHUNK = PICSP_CHUNK;            // particles per CTA work item
@@ -512,6 +521,104 @@ k_cell_permute(const double *__restrict__ x, const double *__restrict__ y, const
 }
 
 // ---------------------------------------------------------------------------
+// Bank order inside a chunk (slow species; after every (re-)binning).
+//
+// The mover's lane l of every warp processes particle (32 q + l) of its chunk.  Its shared-memory accesses are the
+// four 16-byte corner loads at window node e = li * pitch + lj (bank group e mod 8, one quarter-warp per wavefront)
+// and the eight 4-byte accumulator atomics at words e, e + 1, e + pitch, e + pitch + 1 of two planes (bank e mod 32).
+// With particles in arbitrary order those addresses collide like birthdays (2.7 and 3.7 wavefronts per access: 73
+// of the mover's 85 wavefronts per 32 particles).  Here the particles of a chunk are permuted, in place, so that
+// consecutive particles sit on consecutive values of e mod 32: the chunk is laid out in rows, row r holding the r-th
+// particle of every class (class = e mod 32, ascending) that has more than r particles.  While all 32 classes last
+// a row is exactly one warp: 32 distinct banks, 8 distinct bank groups per quarter-warp, every access one wavefront —
+// without a single extra instruction in the mover.  The shorter rows at the end of the chunk still keep the lanes of
+// a warp on mostly distinct banks.
+// Measured (profiles/r02b_mover_bank_order.md): the ion launch right after the ordering has 1.74e8 instead of 2.73e8
+// shared-memory wavefronts per 1e8 particles and is 7 % faster (0.89 of the measured HBM peak under ncu).  The order
+// is fragile, though: a warp instruction costs as many wavefronts as its WORST bank, so a single lane whose particle
+// has left its cell doubles it.  Ions move ~0.007 cells per step: the gain is 7 % for the first ~10 steps, ~4 % after
+// 30 and ~1 % after 60-80; thermal electrons (0.23 cells per step) lose the order within two steps, so it is off for
+// them.  Any order inside a chunk is correct (integer accumulation): results are bit-identical (tested).
+// One CTA per chunk; the chunk's four arrays and its slot map pass through shared memory one after the other.
+// ---------------------------------------------------------------------------
+constexpr int BANK_CLASSES = 32;
+constexpr size_t BANKORDER_SMEM_BYTES = sizeof(double) * CHUNK + sizeof(unsigned short) * CHUNK + sizeof(unsigned) * BANK_CLASSES;
+
+__global__ void __launch_bounds__(SORT2_THREADS, 2)
+k_bank_order(double *__restrict__ x, double *__restrict__ y, double *__restrict__ vx, double *__restrict__ vy,
+             uint32_t *__restrict__ id, const Chunk *__restrict__ chunks, const int *__restrict__ nchunks, PushConst c,
+             const int *__restrict__ frac) {
+    extern __shared__ __align__(16) unsigned char bo_smem[];
+    double *s_val = reinterpret_cast<double *>(bo_smem);                               // [CHUNK] one array of the chunk, in the new order
+    unsigned short *s_pos = reinterpret_cast<unsigned short *>(s_val + CHUNK);          // [CHUNK] new position of source element k
+    unsigned *s_cnt = reinterpret_cast<unsigned *>(s_pos + CHUNK);                      // [32] class populations
+    const int b = blockIdx.x;
+    if (b >= *nchunks) return;
+    if (frac[1] != 0) return;      // the load is concentrated on few cells and the deposit warp-aggregated: same-cell neighbours are wanted there
+    const Chunk ck = chunks[b];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tx = ck.tile / c.nty, ty = ck.tile - tx * c.nty;
+    const int wx0 = tx * TILE - HALO, wy0 = ty * TILE - HALO;
+    const double inv_dx = 1.0 / c.dx;
+    if (tid < BANK_CLASSES) s_cnt[tid] = 0u;
+    __syncthreads();
+    // 1. class and rank (inside the chunk and class) of every particle; warp-aggregated counters.  The codes stay in
+    //    registers: each thread owns CHUNK / SORT2_THREADS = 8 particles.
+    constexpr int PER = (CHUNK + SORT2_THREADS - 1) / SORT2_THREADS;
+    unsigned code[PER];
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+        const int k = u * SORT2_THREADS + tid;
+        const bool live = k < ck.count;                      // warp-uniform trip count: every lane takes part in the match
+        int cls = -1;
+        if (live) {
+            const double px = x[ck.start + k], py = y[ck.start + k];
+            cls = 0;
+            if (in_box(px, py, c)) {
+                double fi, fj;
+                const int ci = floor_nonneg(to_logical_fast(px, c.dx, inv_dx), fi);
+                const int cj = floor_nonneg(to_logical_fast(py, c.dx, inv_dx), fj);
+                cls = ((ci - wx0) * APITCH + (cj - wy0)) & (BANK_CLASSES - 1);      // stragglers outside the window: any class will do
+            }
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, cls);
+        const int leader = __ffs(peers) - 1;
+        unsigned r0 = 0;
+        if (live && lane == leader) r0 = atomicAdd(&s_cnt[cls], (unsigned)__popc(peers));
+        r0 = __shfl_sync(0xffffffffu, r0, leader);
+        code[u] = live ? (((unsigned)cls << 16) | (r0 + (unsigned)__popc(peers & ((1u << lane) - 1u)))) : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    // 2. position of (class, rank) in the row layout: all earlier rows (sum over classes of min(population, rank)) plus
+    //    the classes below mine that reach into my row
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+        if (code[u] == 0xFFFFFFFFu) continue;
+        const unsigned cls = code[u] >> 16, rank = code[u] & 0xFFFFu;
+        unsigned q = 0;
+#pragma unroll 8
+        for (unsigned k = 0; k < BANK_CLASSES; k++) {
+            const unsigned n = s_cnt[k];
+            q += min(n, rank) + ((k < cls && n > rank) ? 1u : 0u);
+        }
+        s_pos[u * SORT2_THREADS + tid] = (unsigned short)q;
+    }
+    __syncthreads();
+    // 3. each array: coalesced read -> shared memory in the new order -> coalesced write back to the same range
+    auto move = [&](double *__restrict__ a) {
+        for (int k = tid; k < ck.count; k += SORT2_THREADS) s_val[s_pos[k]] = a[ck.start + k];
+        __syncthreads();
+        for (int q = tid; q < ck.count; q += SORT2_THREADS) a[ck.start + q] = s_val[q];
+        __syncthreads();
+    };
+    move(x); move(y); move(vx); move(vy);
+    unsigned *s_ival = reinterpret_cast<unsigned *>(s_val);
+    for (int k = tid; k < ck.count; k += SORT2_THREADS) s_ival[s_pos[k]] = id[ck.start + k];
+    __syncthreads();
+    for (int q = tid; q < ck.count; q += SORT2_THREADS) id[ck.start + q] = s_ival[q];
+}
+
+// ---------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA tensor load
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -562,6 +669,10 @@ struct TileCtx {
 __device__ __forceinline__ bool in_range_bits(double v, unsigned long long limit_bits) {
     return (unsigned long long)__double_as_longlong(v) < limit_bits;
 }
+// (Round 2 measured two "instruction diets" here, same box: the test on the high words alone (4 instead of 8 integer
+// instructions per test) changed nothing, and a branch of its own for particles that start and end in the un-wrapped
+// 3 x 3 block of bins (20 instead of 50 instructions for most electron warps) was 2 % SLOWER with 62 instead of 56
+// registers — profiles/r02b_mover_bank_order.md.  Both were removed again.)
 
 // bilinear interpolation of E from the four corners of a cell (gather, src/main.cpp:671-681).  Written with
 // explicit roundings so that the window path and the straggler path are the same arithmetic bit for bit whatever the
@@ -711,7 +822,7 @@ __device__ __forceinline__ void deposit_prepare(double px, double py, const Push
     dp.w01 = (unsigned long long)__double_as_longlong(fma(a, dj, magic)) & mm;
     dp.w11 = (unsigned long long)__double_as_longlong(fma(d, dj, magic)) & mm;
     if ((unsigned)(i - tc.ilo) <= tc.ispan && (unsigned)(j - tc.jlo) <= tc.jspan) {
-        dp.k = (i - tc.wx0) * WIN + (j - tc.wy0);
+        dp.k = (i - tc.wx0) * APITCH + (j - tc.wy0);
         dp.mode = 1;
         return;
     }
@@ -767,9 +878,9 @@ __device__ __forceinline__ bool deposit_commit(const Deposit &dp, unsigned act, 
                 k += r * ACC_COPY;
             }
             add64_limbs(sLo, sHi, k, dp.w00);
-            add64_limbs(sLo, sHi, k + WIN, dp.w10);
+            add64_limbs(sLo, sHi, k + APITCH, dp.w10);
             add64_limbs(sLo, sHi, k + 1, dp.w01);
-            add64_limbs(sLo, sHi, k + WIN + 1, dp.w11);
+            add64_limbs(sLo, sHi, k + APITCH + 1, dp.w11);
             return true;
         }
         if (dp.mode == 2) {
@@ -814,9 +925,9 @@ __device__ __forceinline__ bool deposit_commit(const Deposit &dp, unsigned act, 
             k += r * ACC_COPY;
         }
         add64_limbs(sLo, sHi, k, v00);
-        add64_limbs(sLo, sHi, k + WIN, v10);
+        add64_limbs(sLo, sHi, k + APITCH, v10);
         add64_limbs(sLo, sHi, k + 1, v01);
-        add64_limbs(sLo, sHi, k + WIN + 1, v11);
+        add64_limbs(sLo, sHi, k + APITCH + 1, v11);
     } else if (dp.mode == 2) {
         unsigned long long *g = reinterpret_cast<unsigned long long *>(acc) + ((long long)dp.i * c.niy + dp.j);
         atomicAdd(g, dp.w00); atomicAdd(g + c.niy, dp.w10); atomicAdd(g + 1, dp.w01); atomicAdd(g + c.niy + 1, dp.w11);
@@ -896,8 +1007,7 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
     tc.ispan = (unsigned)(min(tc.wx0 + WIN - 2, c.nix - 2) - tc.ilo);
     tc.jspan = (unsigned)(min(tc.wy0 + WIN - 2, c.niy - 2) - tc.jlo);
     tc.ntx1 = c.ntx - 1; tc.nty1 = c.nty - 1;
-    tc.xl_bits = (unsigned long long)__double_as_longlong(c.xl);
-    tc.yl_bits = (unsigned long long)__double_as_longlong(c.yl);
+    tc.xl_bits = (unsigned long long)__double_as_longlong(c.xl); tc.yl_bits = (unsigned long long)__double_as_longlong(c.yl);
 
     if (tid == 0) {
         mbar_init(&sBar, 1);
@@ -1122,13 +1232,13 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
 
     // flush the window: limbs -> one native 64-bit integer RED per touched node
     if (MODE != 2) {
-        for (int q = tid; q < WIN * WIN; q += MOVER_THREADS) {
+        for (int q = tid; q < WIN * APITCH; q += MOVER_THREADS) {      // (the padding column holds zeros)
             unsigned long long v = 0;
 #pragma unroll
             for (int r = 0; r < REPL; r++)
                 v += ((unsigned long long)sHi[q + r * ACC_COPY] << 32) | (unsigned long long)sLo[q + r * ACC_COPY];
             if (v) {
-                int li = q / WIN, lj = q - li * WIN;
+                int li = q / APITCH, lj = q - li * APITCH;
                 long long gi = tc.wx0 + li, gj = tc.wy0 + lj;
                 atomicAdd(reinterpret_cast<unsigned long long *>(acc) + (gi * c.niy + gj), v);
             }

@@ -7,7 +7,8 @@ import re
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
-LIB_PATH = os.path.join(PKG, "libpicsp_b200.so")
+# PICSP_B200_LIB: another build of the same library (profiles/build_variant.sh), for same-box A/B measurements only
+LIB_PATH = os.environ.get("PICSP_B200_LIB") or os.path.join(PKG, "libpicsp_b200.so")
 HEADER = os.path.join(ROOT, "include", "picsp_b200.h")
 HOST_HEADER = os.path.join(ROOT, "include", "picsp_b200_host.h")
 
@@ -89,6 +90,7 @@ def load_library():
         "picsp_straggler_count": ([ctx, C.c_int, _i64p], C.c_int),
         "picsp_set_sort_period": ([ctx, C.c_int, C.c_int], C.c_int),
         "picsp_set_cell_sort_period": ([ctx, C.c_int, C.c_int], C.c_int),
+        "picsp_set_bank_order": ([ctx, C.c_int, C.c_int], C.c_int),
         "picsp_set_deposit_aggregation": ([ctx, C.c_int, C.c_int], C.c_int),
         "picsp_comm_unique_id": ([C.c_void_p], C.c_int),
         "picsp_comm_attach": ([ctx, C.c_void_p, C.c_int, C.c_int], C.c_int),
@@ -114,6 +116,8 @@ def load_library():
         "picsp_host_h5_close": ([C.c_void_p], C.c_int),
     }
     for name, (args, res) in sig.items():
+        if os.environ.get("PICSP_B200_LIB") and not hasattr(L, name):
+            continue                      # an older build under A/B test: entry points added since are simply absent
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = res

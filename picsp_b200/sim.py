@@ -181,6 +181,7 @@ class Simulation:
 
     def set_sort_period(self, s, period): check(self.L.picsp_set_sort_period(self.ctx, s, period))
     def set_cell_sort_period(self, s, period): check(self.L.picsp_set_cell_sort_period(self.ctx, s, period))
+    def set_bank_order(self, s, mode): check(self.L.picsp_set_bank_order(self.ctx, s, mode))
     def set_deposit_aggregation(self, s, mode): check(self.L.picsp_set_deposit_aggregation(self.ctx, s, mode))
 
     # -- multi-GPU ------------------------------------------------------------------------------
