@@ -263,7 +263,8 @@ def main_ours(args, rank, world, local_rank):
     n_local = hi - lo
     def make_sim():
         sim = Simulation(Params(args.cells, args.cells, nm["dx"], nm["dt"], nm["mass_i"], n_species, n_species,
-                                solverType=1, device=local_rank, capacity=(n_local, n_local), flags=args.flags))
+                                solverType=1, device=local_rank, capacity=(n_local, n_local), flags=args.flags,
+                                parts=args.parts))
         # tuning switches first: the first binning happens inside the fill / upload
         if args.sort_period_e > 0:
             sim.set_sort_period(ELECTRON, args.sort_period_e)
@@ -334,17 +335,19 @@ def main_ours(args, rank, world, local_rank):
     push_ms, push_calls = prof["push"]
     peak, peak_src = measured_peak_gbs()
     per_launch_s = push_ms * 1e-3 / max(push_calls, 1)
-    achieved = ALGO_BYTES_PER_PARTICLE_STEP * n_local / per_launch_s / 1e9
+    nparts = sim.parts()                       # a species split into parts is pushed by one launch per part
+    n_launch = n_local / nparts
+    achieved = ALGO_BYTES_PER_PARTICLE_STEP * n_launch / per_launch_s / 1e9
     traffic = args.traffic_bytes_per_launch
     if traffic is None and ncu_traffic_bytes_per_particle() is not None:
-        traffic = ncu_traffic_bytes_per_particle() * n_local     # per launch, like `achieved`
+        traffic = ncu_traffic_bytes_per_particle() * n_launch     # per launch, like `achieved`
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "kernel": "k_tile_mover<0> (leapfrog mover + CIC gather from a TMA-staged E tile + next-step CIC deposit); "
                           "the average includes the re-binning launches k_tile_mover<4> (every 8th electron launch, "
                           "73 B of DRAM traffic per particle instead of 64), charged at the same 64 algorithmic bytes",
                 "traffic_source": "profiles/ncu_traffic.json: ncu --set full dram bytes per particle x particles per launch",
-                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE_STEP * n_local,
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE_STEP * n_launch, "particles_per_launch": n_launch,
                 "avg_launch_ms": per_launch_s * 1e3, "launches_timed": push_calls, "peak_source": peak_src,
                 "share_of_step": push_ms / prof["step"][0] if prof["step"][0] else None}
     phases_ms = {k: v[0] / args.steps for k, v in prof.items()}
@@ -507,6 +510,8 @@ def main():
     ap.add_argument("--bank-order-i", type=int, default=None, choices=[-1, 0, 1], help="the same for ions (library default: on)")
     ap.add_argument("--sort-period-e", type=int, default=0, help="steps between electron tile sorts (0: library default)")
     ap.add_argument("--sort-period-i", type=int, default=0, help="steps between ion tile sorts (0: library default)")
+    ap.add_argument("--parts", type=int, default=0, help="picsp_params::parts: stores per species (0 = automatic: 1 unless the device memory asks for more; "
+                    "BASELINE config 5, 4e9 particles, on ONE GPU runs with 8)")
     ap.add_argument("--flags", type=int, default=0, help="PICSP_FLAG_* bits for A/B runs (16: stand-alone re-sort instead of the re-binning mover)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -96,7 +96,12 @@ typedef struct picsp_params {
     double  spwt[2];          /* ion_spwt, electron_spwt (main.cpp:401-402) */
     int64_t capacity[2];      /* max particles of each species held by THIS rank */
     int32_t device;           /* CUDA device ordinal */
-    int32_t reserved;
+    int32_t parts;            /* 0 (default): automatic.  Parts a species' store is split into (contiguous ranges of its
+                               * particles, each binned on its own, all depositing into the species' one grid) so that the
+                               * second buffer set of the re-binning is ONE part-sized spare instead of a copy of the whole
+                               * state: automatic = 1 unless the device cannot hold state + copy (e.g. 4e9 particles on one
+                               * 180 GB GPU -> 8).  Results do not depend on it (integer accumulation: bit-identical grids
+                               * and phase space).  A part holds at most 2^32-1 particles. */
 } picsp_params;
 
 /* ---- lifetime -------------------------------------------------------------- */
@@ -216,6 +221,8 @@ enum {
 int picsp_profile_enable(picsp_ctx *ctx, int on);                       /* CUDA events around every phase on the library's stream */
 int picsp_profile_get(picsp_ctx *ctx, int phase, double *ms, int64_t *calls); /* synchronises; accumulates since last reset */
 int picsp_profile_reset(picsp_ctx *ctx);
+/* Parts every species' store is split into (picsp_params::parts resolved; 1 = the whole species in one store). */
+int picsp_parts(picsp_ctx *ctx, int *parts);
 int picsp_kernel_launches(picsp_ctx *ctx, int64_t *n);                  /* number of this library's kernels launched so far */
 
 #ifdef __cplusplus

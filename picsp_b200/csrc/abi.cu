@@ -53,6 +53,22 @@ template <class T> void dalloc(T **p, size_t count) {
     PICSP_CUDA(cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T)));
 }
 
+// -- parts of a species (ctx.cuh) -----------------------------------------------------------
+Species &part_of(picsp_ctx *c, int s, int p) { return p == 0 ? c->sp[s] : c->more[s][(size_t)p - 1]; }
+template <class F> void for_parts(picsp_ctx *c, int s, F f) {
+    for (int p = 0; p < c->nparts; p++) f(part_of(c, s, p));
+}
+// the shared spare (several parts): a part borrows it as its second buffer set and, after a sort that left the result
+// there, keeps it and hands its old primary set back
+void borrow_spare(picsp_ctx *c, Species &sp) {
+    if (!sp.shares_spare) return;
+    sp.x2 = c->spare.x; sp.y2 = c->spare.y; sp.vx2 = c->spare.vx; sp.vy2 = c->spare.vy; sp.id2 = c->spare.id;
+}
+void return_spare(picsp_ctx *c, Species &sp) {
+    if (!sp.shares_spare) return;
+    c->spare.x = sp.x2; c->spare.y = sp.y2; c->spare.vx = sp.vx2; c->spare.vy = sp.vy2; c->spare.id = sp.id2;
+}
+
 // One buffer set of a species = ONE allocation holding x, y, vx, vy back to back (x is its base).  +2: bulk slices
 // are widened to even indices; the stride is a multiple of 32 doubles so every array stays 256-byte aligned.  The
 // idle set doubles as a contiguous staging block of 4*cap doubles (row-layout dumps).
@@ -88,8 +104,8 @@ void check_device_error(picsp_ctx *c) {
 }
 
 // -- histogram / fixed-point scale --------------------------------------------------
-void ensure_hist(picsp_ctx *c, int s) {
-    Species &sp = c->sp[s];
+void ensure_hist(picsp_ctx *c, Species &sp) {
+    const int s = sp.s;
     if (sp.hist_valid) return;
     const int nt = c->g.ntx * c->g.nty;
     PICSP_CUDA(cudaMemsetAsync(sp.hist, 0, sizeof(unsigned int) * nt, c->stream));
@@ -110,19 +126,29 @@ void ensure_hist(picsp_ctx *c, int s) {
 bool tiled(const picsp_ctx *c) { return !(c->prm.flags & PICSP_FLAG_NO_SORT); }
 bool walls(const picsp_ctx *c) { return (c->prm.flags & PICSP_FLAG_WALLS) != 0; }
 
+// species-level: the scale bounds the sums of ALL parts (they deposit into one accumulator grid), so with several
+// parts it is taken from the sum of their histograms (every part's histogram must be valid: ensure_hist)
 void compute_frac(picsp_ctx *c, int s) {
     Species &sp = c->sp[s];
     // the shared-memory limbs of the tiled path carry at most MAX_FRAC_TILED fraction bits
     const int nt = c->g.ntx * c->g.nty;
-    PICSP_LAUNCH(c, k_frac_from_hist, (nt + 255) / 256, 256, 0, sp.hist, c->g.ntx, c->g.nty, sp.frac,
-                 tiled(c) ? MAX_FRAC_TILED : 60, sp.frac_scratch, (long long)sp.n,
+    const unsigned int *hist = sp.hist;
+    if (c->nparts > 1) {
+        PICSP_CUDA(cudaMemsetAsync(c->hist_sum[s], 0, sizeof(unsigned int) * nt, c->stream));
+        for_parts(c, s, [&](Species &q) {
+            PICSP_LAUNCH(c, k_hist_add, (nt + 255) / 256, 256, 0, c->hist_sum[s], q.hist, nt);
+        });
+        hist = c->hist_sum[s];
+    }
+    PICSP_LAUNCH(c, k_frac_from_hist, (nt + 255) / 256, 256, 0, hist, c->g.ntx, c->g.nty, sp.frac,
+                 tiled(c) ? MAX_FRAC_TILED : 60, sp.frac_scratch, (long long)c->n_total[s],
                  sp.aggregate == 0 ? -1 : ((sp.aggregate > 0 || sp.cell_period > 0) ? 1 : 0));
 }
 
 // -- tile binning -------------------------------------------------------------------------
 int mover_grid(const Species &sp);
 bool bank_order_on(const Species &sp);
-void op_bank_order(picsp_ctx *c, int s);
+void op_bank_order(picsp_ctx *c, Species &sp);
 
 // Particles per CTA work item: CHUNK (4096) for big populations; smaller when there are too few particles to give
 // every SM several waves of CTAs (tail effect), never below 512, always a multiple of the slice size.
@@ -135,14 +161,15 @@ int pick_chunk(const picsp_ctx *c, int64_t n) {
 
 // allocates the second buffer set, scans the histogram of the stored positions into the NEW bin offsets and
 // chunk table (second table: the kernels that move the particles still walk the current one), zeroes the cursors
-void sort_prepare(picsp_ctx *c, int s) {
-    Species &sp = c->sp[s];
+void sort_prepare(picsp_ctx *c, Species &sp) {
     const Geom &g = c->g;
     const int nt = g.ntx * g.nty;
-    ensure_hist(c, s);
-    if (!sp.x2) {
-        alloc_particle_set(&sp.x2, &sp.y2, &sp.vx2, &sp.vy2, sp.cap);
-        dalloc(&sp.id, sp.cap + 8); dalloc(&sp.id2, sp.cap + 8);   // +8: bulk slices of ids are widened to multiples of 4
+    ensure_hist(c, sp);
+    borrow_spare(c, sp);
+    if (!sp.x2) alloc_particle_set(&sp.x2, &sp.y2, &sp.vx2, &sp.vy2, sp.cap);
+    if (!sp.id) dalloc(&sp.id, sp.cap + 8);        // +8: bulk slices of ids are widened to multiples of 4
+    if (!sp.id2) dalloc(&sp.id2, sp.cap + 8);
+    if (!sp.chunks2) {
         dalloc((Chunk **)&sp.chunks2, (size_t)sp.max_chunks); dalloc(&sp.nchunks2, 1);
         dalloc(&sp.chunk_cnt, (size_t)sp.max_chunks * 9); dalloc(&sp.chunk_base, (size_t)sp.max_chunks * 9);
     }
@@ -151,22 +178,22 @@ void sort_prepare(picsp_ctx *c, int s) {
     PICSP_LAUNCH(c, k_scan_tiles, 1, 1024, 0, sp.hist, nt, sp.tile_off, sp.scan_chunk0, sp.nchunks2, sp.cursor, sp.chunk2);
     PICSP_LAUNCH(c, k_fill_chunks, (nt * 32 + 255) / 256, 256, 0, sp.hist, nt, sp.tile_off, sp.scan_chunk0, (Chunk *)sp.chunks2, sp.chunk2);
 }
-void sort_finish(picsp_ctx *c, int s, bool result_in_second_set = true) {
-    Species &sp = c->sp[s];
+void sort_finish(picsp_ctx *c, Species &sp, bool result_in_second_set = true) {
     std::swap(sp.chunks, sp.chunks2); std::swap(sp.nchunks, sp.nchunks2); sp.chunk = sp.chunk2;
     if (result_in_second_set) {
         std::swap(sp.x, sp.x2); std::swap(sp.y, sp.y2); std::swap(sp.vx, sp.vx2); std::swap(sp.vy, sp.vy2);
         std::swap(sp.id, sp.id2);
+        return_spare(c, sp);       // several parts: the old primary set is the spare of whoever sorts next
     }
     sp.has_perm = true; sp.sorted = true; sp.steps_since_sort = 0;
     sp.cnt_valid = false;          // new chunk table
     sp.staged_v_valid = false;     // the staging buffers are now the live ones
 }
 
-void op_sort(picsp_ctx *c, int s) {
+void op_sort(picsp_ctx *c, Species &sp) {
     PhaseScope ph(c, PICSP_PHASE_SORT);
-    Species &sp = c->sp[s];
-    sort_prepare(c, s);
+    const int s = sp.s;
+    sort_prepare(c, sp);
     const uint32_t *ids = sp.has_perm ? sp.id : (const uint32_t *)nullptr;
     const int nt = c->g.ntx * c->g.nty;
     if (!sp.sorted && sp.n >= 100000 && nt >= 256) {
@@ -184,8 +211,8 @@ void op_sort(picsp_ctx *c, int s) {
         PICSP_CUDA(cudaMemsetAsync(sp.cursor, 0, sizeof(unsigned int) * nt, c->stream));
         PICSP_LAUNCH(c, (k_sort_pass<false>), blocks, SORT2_THREADS, SORT2_SMEM_BYTES, sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2, (long long)sp.n,
                      push_const(c, s), shift, sp.tile_off, sp.cursor, sp.x, sp.y, sp.vx, sp.vy, sp.id);
-        sort_finish(c, s, false);
-        if (bank_order_on(sp)) op_bank_order(c, s);
+        sort_finish(c, sp, false);
+        if (bank_order_on(sp)) op_bank_order(c, sp);
         return;
     }
     if (sp.n > 0) {
@@ -197,15 +224,16 @@ void op_sort(picsp_ctx *c, int s) {
             PICSP_LAUNCH(c, k_sort_scatter, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy, ids,
                          (long long)sp.n, push_const(c, s), sp.tile_off, sp.cursor, sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2);
     }
-    sort_finish(c, s);
-    if (bank_order_on(sp)) op_bank_order(c, s);
+    sort_finish(c, sp);
+    if (bank_order_on(sp)) op_bank_order(c, sp);
 }
 
 // Cell order inside every bin (stand-alone; see tile_kernels.cuh).  Particles stay in their bin's range; the result is
 // left in the second buffer set, which becomes the live one.
-void op_cell_sort(picsp_ctx *c, int s) {
+void op_cell_sort(picsp_ctx *c, Species &sp) {
     PhaseScope ph(c, PICSP_PHASE_SORT);
-    Species &sp = c->sp[s];
+    const int s = sp.s;
+    borrow_spare(c, sp);
     if (!sp.sorted || sp.n <= 0 || !sp.x2) return;
     const int grid = mover_grid(sp);
     if (sp.cell_cnt_chunks < grid) {
@@ -226,6 +254,7 @@ void op_cell_sort(picsp_ctx *c, int s) {
                  sp.x2, sp.y2, sp.vx2, sp.vy2, sp.id2);
     std::swap(sp.x, sp.x2); std::swap(sp.y, sp.y2); std::swap(sp.vx, sp.vx2); std::swap(sp.vy, sp.vy2);
     std::swap(sp.id, sp.id2);
+    return_spare(c, sp);
     sp.has_perm = true;
     sp.cnt_valid = false;          // the per-chunk neighbour counts described the old order
     sp.staged_v_valid = false;
@@ -240,8 +269,8 @@ int mover_grid(const Species &sp) {
 // Bank order inside every chunk (see tile_kernels.cuh): in place, chunk table and counts untouched.  Automatic mode:
 // species that are re-binned rarely (ions: every 96 steps), whose particles keep their cells between two re-binnings.
 bool bank_order_on(const Species &sp) { return sp.bank_order < 0 ? (sp.sort_period >= 32 && sp.cell_period == 0) : sp.bank_order > 0; }
-void op_bank_order(picsp_ctx *c, int s) {
-    Species &sp = c->sp[s];
+void op_bank_order(picsp_ctx *c, Species &sp) {
+    const int s = sp.s;
     if (!BULK_PIPE || !sp.sorted || !sp.has_perm || sp.n <= 0) return;       // (callers open the PICSP_PHASE_SORT scope)
     if (!c->bankorder_opted_in) {
         PICSP_CUDA(cudaFuncSetAttribute(k_bank_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BANKORDER_SMEM_BYTES));
@@ -251,8 +280,8 @@ void op_bank_order(picsp_ctx *c, int s) {
                  (const Chunk *)sp.chunks, sp.nchunks, push_const(c, s), sp.frac);
 }
 
-template <int MODE> void launch_tile_mover(picsp_ctx *c, int s) {
-    Species &sp = c->sp[s];
+template <int MODE> void launch_tile_mover(picsp_ctx *c, Species &sp) {
+    const int s = sp.s;
     RebinArgs rb = {};
     if (MODE == 3 || MODE == 4) {
         PICSP_REQUIRE(sp.has_perm, PICSP_ERR_STATE, "internal: re-binning mover on a store without a slot map");
@@ -310,20 +339,23 @@ void op_peer_reduce_rho(picsp_ctx *c);
 
 // makes sure acc_s holds the fixed-point deposit of the stored positions (scatter loop of scatterSpecies)
 void ensure_acc(picsp_ctx *c, int s) {
-    Species &sp = c->sp[s];
-    if (sp.acc_valid) return;
-    if (tiled(c) && !sp.sorted) op_sort(c, s);
-    ensure_hist(c, s);
+    if (c->sp[s].acc_valid) return;        // (a species-level flag, kept equal on all parts)
+    for_parts(c, s, [&](Species &sp) {
+        if (tiled(c) && !sp.sorted) op_sort(c, sp);
+        ensure_hist(c, sp);
+    });
     compute_frac(c, s);
-    PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
-    if (sp.n > 0) {
-        if (tiled(c))
-            launch_tile_mover<1>(c, s);
-        else
-            PICSP_LAUNCH(c, k_deposit, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, (long long)sp.n,
-                         push_const(c, s), sp.acc, sp.frac);
-    }
-    sp.acc_valid = true;
+    for_parts(c, s, [&](Species &sp) {
+        PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
+        if (sp.n > 0) {
+            if (tiled(c))
+                launch_tile_mover<1>(c, sp);
+            else
+                PICSP_LAUNCH(c, k_deposit, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, (long long)sp.n,
+                             push_const(c, s), sp.acc, sp.frac);
+        }
+        sp.acc_valid = true;
+    });
 }
 
 void op_deposit(picsp_ctx *c, int s) {
@@ -335,7 +367,7 @@ void op_deposit(picsp_ctx *c, int s) {
     const int clear = (c->prm.flags & PICSP_FLAG_CLEAR_DENSITY) ? 1 : 0;
     PICSP_LAUNCH(c, k_deposit_finalize, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, sp.den, sp.acc, sp.frac, weight, g.nn, clear);
     if (!walls(c)) PICSP_LAUNCH(c, k_fold_periodic, 1, 1024, 0, sp.den, g.nix, g.niy);
-    sp.acc_valid = false;
+    for_parts(c, s, [](Species &q) { q.acc_valid = false; });
 }
 
 // picsp_step's grid phase: scatterSpecies x2 (finalize + fold) and computeRho in ONE launch
@@ -352,7 +384,7 @@ void op_grid_phase(picsp_ctx *c) {
             Species &sp = c->sp[s];
             gs[s].den = sp.den; gs[s].acc = sp.acc; gs[s].frac = sp.frac;
             gs[s].weight = sp.spwt / (g.dx * g.dx); gs[s].q = sp.q;
-            sp.acc_valid = false;
+            for_parts(c, s, [](Species &q) { q.acc_valid = false; });
         }
         const int clear = (c->prm.flags & PICSP_FLAG_CLEAR_DENSITY) ? 1 : 0;
         double *rho_out = c->peer_ok ? c->peer_part[c->rank] : c->rho;      // sharded: the partial goes where the peers can read it
@@ -448,71 +480,81 @@ void op_compute_ef(picsp_ctx *c) {
     else PICSP_LAUNCH(c, k_compute_ef, blocks_for(g.nn, 256, c->num_sms * 8), 256, 0, c->phi, c->E, g.nix, g.niy, g.dx, g.dx);
 }
 
+// pushSpecies for one species: all its parts, one after the other on the library stream
 void op_push(picsp_ctx *c, int s) {
-    Species &sp = c->sp[s];
-    sp.staged_v_valid = false;
     const bool fuse = !(c->prm.flags & PICSP_FLAG_NO_FUSE);
     const bool tile = tiled(c);
-    const bool due = tile && sp.sorted && sp.steps_since_sort >= sp.sort_period;
-    // a periodic re-bin rides on the mover itself (MODE 3) when the fused bulk-pipeline mover is in use;
-    // the first binning of an arbitrary load, and the unfused mover, use the stand-alone sort
-    const bool rebin_in_mover = due && fuse && BULK_PIPE && sp.n > 0 && !(c->prm.flags & PICSP_FLAG_SEPARATE_SORT);
-    if (tile && (!sp.sorted || (due && !rebin_in_mover))) op_sort(c, s);
-    // cell order inside the bins: a pass of its own on the steps where no re-binning is due
-    if (tile && sp.sorted && !due && sp.cell_period > 0 && sp.steps_since_cellsort >= sp.cell_period && BULK_PIPE) op_cell_sort(c, s);
-    if (rebin_in_mover) { PhaseScope phs(c, PICSP_PHASE_SORT); sort_prepare(c, s); }
-    if (fuse || tile) ensure_hist(c, s);   // histogram of the positions about to be pushed -> bound for acc
+    const int nt = c->g.ntx * c->g.nty;
+    // every part: first binning of a new load / stand-alone sort when one is due; histogram of the positions about to be
+    // pushed.  The fixed-point scale of the fused deposit (species-level) needs ALL the histograms before the first launch.
+    for_parts(c, s, [&](Species &sp) {
+        sp.staged_v_valid = false;
+        const bool due = tile && sp.sorted && sp.steps_since_sort >= sp.sort_period;
+        // a periodic re-bin rides on the mover itself (MODE 3 / 4) when the fused bulk-pipeline mover is in use;
+        // the first binning of an arbitrary load, and the unfused mover, use the stand-alone sort
+        const bool rebin_in_mover = due && fuse && BULK_PIPE && sp.n > 0 && !(c->prm.flags & PICSP_FLAG_SEPARATE_SORT);
+        if (tile && (!sp.sorted || (due && !rebin_in_mover))) op_sort(c, sp);
+        // cell order inside the bins: a pass of its own on the steps where no re-binning is due
+        if (tile && sp.sorted && !due && sp.cell_period > 0 && sp.steps_since_cellsort >= sp.cell_period && BULK_PIPE) op_cell_sort(c, sp);
+        if (fuse || tile) ensure_hist(c, sp);   // histogram of the positions about to be pushed -> bound for acc
+    });
     if (fuse) compute_frac(c, s);
-    bool rebinned = false;
-    {
-        PhaseScope ph(c, PICSP_PHASE_PUSH);
-        PhaseScope phs(c, s == 0 ? PICSP_PHASE_PUSH_IONS : PICSP_PHASE_PUSH_ELECTRONS);
-        PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
-        const int nt = c->g.ntx * c->g.nty;
-        if (fuse || tile) PICSP_CUDA(cudaMemsetAsync(sp.hist_next, 0, sizeof(unsigned int) * nt, c->stream));
-        if (fuse && sp.acc_valid)   // a previous fused push was never consumed by a deposit: drop it
-            PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
-        if (sp.n > 0) {
-            if (tile) {
-                if (rebin_in_mover && sp.cnt_valid) {
-                    // the previous launch counted, per chunk, where its particles went: reserve the ranges up front
-                    const long long q = 9ll * mover_grid(sp);
-                    PICSP_LAUNCH(c, k_rebin_bases, (int)((q + 255) / 256), 256, 0, (const Chunk *)sp.chunks, sp.nchunks, c->g.ntx, c->g.nty,
-                                 sp.chunk_cnt, sp.tile_off, sp.cursor, sp.chunk_base, c->d_error);
-                    launch_tile_mover<4>(c, s); sort_finish(c, s); rebinned = true;
-                } else if (rebin_in_mover) { launch_tile_mover<3>(c, s); sort_finish(c, s); rebinned = true; }
-                else if (fuse) { launch_tile_mover<0>(c, s); sp.cnt_valid = sp.chunk_cnt != nullptr; }
-                else launch_tile_mover<2>(c, s);
-            } else {
-                const int blocks = particle_blocks(c, sp.n, 256);
-                if (fuse)
-                    PICSP_LAUNCH(c, (k_push<true>), blocks, 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n, push_const(c, s),
-                                 c->E, sp.acc, sp.frac, sp.hist_next, sp.counters, c->d_error);
-                else
-                    PICSP_LAUNCH(c, (k_push<false>), blocks, 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n, push_const(c, s),
-                                 c->E, sp.acc, sp.frac, sp.hist_next, sp.counters, c->d_error);
+    if (fuse && c->sp[s].acc_valid)   // a previous fused push was never consumed by a deposit: drop it
+        PICSP_CUDA(cudaMemsetAsync(c->sp[s].acc, 0, sizeof(long long) * c->g.nn, c->stream));
+    for_parts(c, s, [&](Species &sp) {
+        // (a stand-alone sort above has reset steps_since_sort, so `due` here means: re-binning inside the mover)
+        const bool rebin_in_mover = tile && sp.sorted && sp.steps_since_sort >= sp.sort_period && fuse && BULK_PIPE && sp.n > 0 &&
+                                    !(c->prm.flags & PICSP_FLAG_SEPARATE_SORT);
+        if (rebin_in_mover) { PhaseScope phs(c, PICSP_PHASE_SORT); sort_prepare(c, sp); }
+        bool rebinned = false;
+        {
+            PhaseScope ph(c, PICSP_PHASE_PUSH);
+            PhaseScope phs(c, s == 0 ? PICSP_PHASE_PUSH_IONS : PICSP_PHASE_PUSH_ELECTRONS);
+            PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
+            if (fuse || tile) PICSP_CUDA(cudaMemsetAsync(sp.hist_next, 0, sizeof(unsigned int) * nt, c->stream));
+            if (sp.n > 0) {
+                if (tile) {
+                    if (rebin_in_mover && sp.cnt_valid) {
+                        // the previous launch counted, per chunk, where its particles went: reserve the ranges up front
+                        const long long q = 9ll * mover_grid(sp);
+                        PICSP_LAUNCH(c, k_rebin_bases, (int)((q + 255) / 256), 256, 0, (const Chunk *)sp.chunks, sp.nchunks, c->g.ntx, c->g.nty,
+                                     sp.chunk_cnt, sp.tile_off, sp.cursor, sp.chunk_base, c->d_error);
+                        launch_tile_mover<4>(c, sp); sort_finish(c, sp); rebinned = true;
+                    } else if (rebin_in_mover) { launch_tile_mover<3>(c, sp); sort_finish(c, sp); rebinned = true; }
+                    else if (fuse) { launch_tile_mover<0>(c, sp); sp.cnt_valid = sp.chunk_cnt != nullptr; }
+                    else launch_tile_mover<2>(c, sp);
+                } else {
+                    const int blocks = particle_blocks(c, sp.n, 256);
+                    if (fuse)
+                        PICSP_LAUNCH(c, (k_push<true>), blocks, 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n, push_const(c, s),
+                                     c->E, sp.acc, sp.frac, sp.hist_next, sp.counters, c->d_error);
+                    else
+                        PICSP_LAUNCH(c, (k_push<false>), blocks, 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n, push_const(c, s),
+                                     c->E, sp.acc, sp.frac, sp.hist_next, sp.counters, c->d_error);
+                }
             }
         }
-    }
-    if (rebinned && bank_order_on(sp)) { PhaseScope phs(c, PICSP_PHASE_SORT); op_bank_order(c, s); }    // the new layout, in bank order
-    if (fuse || tile) {
-        std::swap(sp.hist, sp.hist_next);
-        sp.hist_valid = true;
-    } else {
-        sp.hist_valid = false;
-    }
-    sp.acc_valid = fuse;
-    sp.steps_since_sort++;
-    sp.steps_since_cellsort++;
+        if (rebinned && bank_order_on(sp)) { PhaseScope phs(c, PICSP_PHASE_SORT); op_bank_order(c, sp); }    // the new layout, in bank order
+        if (fuse || tile) {
+            std::swap(sp.hist, sp.hist_next);
+            sp.hist_valid = true;
+        } else {
+            sp.hist_valid = false;
+        }
+        sp.acc_valid = fuse;
+        sp.steps_since_sort++;
+        sp.steps_since_cellsort++;
+    });
 }
 
 void op_rewind(picsp_ctx *c, int s) {
     PhaseScope ph(c, PICSP_PHASE_PUSH);
-    Species &sp = c->sp[s];
-    sp.staged_v_valid = false;
-    if (sp.n > 0)
-        PICSP_LAUNCH(c, k_rewind, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n,
-                     push_const(c, s), c->E);
+    for_parts(c, s, [&](Species &sp) {
+        sp.staged_v_valid = false;
+        if (sp.n > 0)
+            PICSP_LAUNCH(c, k_rewind, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)sp.n,
+                         push_const(c, s), c->E);
+    });
 }
 
 double read_scalar(picsp_ctx *c, const double *dptr) {
@@ -653,8 +695,7 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
         PICSP_REQUIRE(p->capacity[0] >= 0 && p->capacity[1] >= 0, PICSP_ERR_INVALID, "negative capacity");
         PICSP_REQUIRE(!((p->flags & PICSP_FLAG_WALLS) && (p->flags & PICSP_FLAG_NO_SORT)), PICSP_ERR_INVALID,
                       "PICSP_FLAG_WALLS needs the tiled store (not combinable with PICSP_FLAG_NO_SORT)");
-        PICSP_REQUIRE(p->capacity[0] <= 0xFFFFFFFFll && p->capacity[1] <= 0xFFFFFFFFll, PICSP_ERR_INVALID,
-                      "per-rank species capacity is limited to 2^32-1 particles");
+        PICSP_REQUIRE(p->parts >= 0 && p->parts <= 64, PICSP_ERR_INVALID, "parts must be 0 (automatic) .. 64");
         int ndev = 0;
         cudaError_t e = cudaGetDeviceCount(&ndev);
         if (e != cudaSuccess || ndev == 0) {
@@ -682,28 +723,72 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
         c->num_sms = prop.multiProcessorCount;
         PICSP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 
+        // Parts per species.  One part = each species with a full second buffer set of its own (allocated at its first
+        // binning).  When the device cannot hold that (state + as much again), the species are split so that ONE part-sized
+        // spare serves all parts of both species: 2 * 36 B * capacity * (1 + 1 / (2 * parts)).
+        const int64_t cap_max = std::max(p->capacity[0], p->capacity[1]);
+        int nparts = p->parts;
+        if (nparts == 0) {
+            nparts = 1;
+            if (!(p->flags & PICSP_FLAG_NO_SORT)) {
+                size_t free_b = 0, total_b = 0;
+                PICSP_CUDA(cudaMemGetInfo(&free_b, &total_b));
+                const double state = 36.0 * ((double)p->capacity[0] + (double)p->capacity[1]);
+                const double grids = 16.0 * 8.0 * (double)g.nn + 3e9;                  // grids, FFT work area, tables, head room
+                while (nparts < 64 && state * (nparts == 1 ? 2.0 : 1.0 + 0.5 / nparts) + grids > (double)free_b) nparts *= 2;
+            }
+        }
+        PICSP_REQUIRE(nparts == 1 || !(p->flags & PICSP_FLAG_NO_SORT), PICSP_ERR_INVALID, "parts > 1 need the tiled store");
+        c->nparts = nparts;
+        c->part_cap = nparts == 1 ? 0 : (cap_max + nparts - 1) / nparts;
+        PICSP_REQUIRE((nparts == 1 ? cap_max : c->part_cap) <= 0xFFFFFFFFll, PICSP_ERR_INVALID,
+                      "a part of a species is limited to 2^32-1 particles (slot map): raise picsp_params::parts");
+        const size_t ntl = (size_t)g.ntx * g.nty;
         for (int s = 0; s < 2; s++) {
-            Species &sp = c->sp[s];
-            sp.cap = p->capacity[s]; sp.q = p->charge[s]; sp.m = p->mass[s]; sp.spwt = p->spwt[s];
-            alloc_particle_set(&sp.x, &sp.y, &sp.vx, &sp.vy, sp.cap);
-            dalloc(&sp.den, g.nn); dalloc(&sp.acc, g.nn); dalloc(&sp.frac, 2); dalloc(&sp.frac_scratch, 3);
-            dalloc(&sp.hist, (size_t)g.ntx * g.nty); dalloc(&sp.hist_next, (size_t)g.ntx * g.nty);
-            dalloc(&sp.counters, 2);
-            sp.sort_period = (s == 0) ? 96 : 8;     // steps between re-binnings (ions barely move; electrons: profiles/r01_sweeps.md)
-            sp.cell_period = 0;                     // steps between cell orderings inside the bins: off (profiles/r02_mover_aggregation.md)
-            sp.steps_since_cellsort = sp.cell_period;   // the first push after a load orders it
-            sp.ntiles = g.ntx * g.nty;
-            sp.max_chunks = sp.cap / 512 + (long long)g.ntx * g.nty + 1;   // 512 = smallest chunk pick_chunk() returns
-            dalloc(&sp.tile_off, (size_t)g.ntx * g.nty + 1);
-            dalloc((Chunk **)&sp.chunks, (size_t)sp.max_chunks);
-            dalloc(&sp.nchunks, 1);
-            dalloc(&sp.cursor, (size_t)g.ntx * g.nty);
-            PICSP_CUDA(cudaMemsetAsync(sp.nchunks, 0, sizeof(int), c->stream));
-            PICSP_CUDA(cudaMemsetAsync(sp.den, 0, sizeof(double) * g.nn, c->stream));      // src/main.cpp:427,431
-            PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * g.nn, c->stream));
-            PICSP_CUDA(cudaMemsetAsync(sp.frac, 0, 2 * sizeof(int), c->stream));
-            PICSP_CUDA(cudaMemsetAsync(sp.frac_scratch, 0, 3 * sizeof(unsigned long long), c->stream));
-            PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
+            c->cap_total[s] = p->capacity[s];
+            c->more[s].resize((size_t)nparts - 1);
+            for (int q = 0; q < nparts; q++) {
+                Species &sp = part_of(c, s, q);
+                sp.s = s; sp.part = q;
+                sp.q = p->charge[s]; sp.m = p->mass[s]; sp.spwt = p->spwt[s];
+                sp.shares_spare = nparts > 1;
+                if (nparts == 1) { sp.first = 0; sp.cap = p->capacity[s]; }
+                else {
+                    sp.first = (int64_t)q * c->part_cap;
+                    sp.cap = c->part_cap;      // every set the same size: any of them can become the spare (the LAST part of a species may hold fewer particles)
+                }
+                alloc_particle_set(&sp.x, &sp.y, &sp.vx, &sp.vy, sp.cap);
+                if (nparts > 1) dalloc(&sp.id, sp.cap + 8);
+                if (q == 0) {
+                    dalloc(&sp.den, g.nn); dalloc(&sp.acc, g.nn); dalloc(&sp.frac, 2); dalloc(&sp.frac_scratch, 3);
+                    PICSP_CUDA(cudaMemsetAsync(sp.den, 0, sizeof(double) * g.nn, c->stream));      // src/main.cpp:427,431
+                    PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * g.nn, c->stream));
+                    PICSP_CUDA(cudaMemsetAsync(sp.frac, 0, 2 * sizeof(int), c->stream));
+                    PICSP_CUDA(cudaMemsetAsync(sp.frac_scratch, 0, 3 * sizeof(unsigned long long), c->stream));
+                } else {                       // species-level members: aliases of part 0's
+                    const Species &p0 = c->sp[s];
+                    sp.den = p0.den; sp.acc = p0.acc; sp.frac = p0.frac; sp.frac_scratch = p0.frac_scratch;
+                }
+                dalloc(&sp.hist, ntl); dalloc(&sp.hist_next, ntl);
+                dalloc(&sp.counters, 2);
+                sp.sort_period = (s == 0) ? 96 : 8;     // steps between re-binnings (ions barely move; electrons: profiles/r01_sweeps.md)
+                sp.cell_period = 0;                     // steps between cell orderings inside the bins: off (profiles/r02_mover_aggregation.md)
+                sp.steps_since_cellsort = sp.cell_period;   // the first push after a load orders it
+                sp.ntiles = g.ntx * g.nty;
+                sp.max_chunks = sp.cap / 512 + (long long)ntl + 1;   // 512 = smallest chunk pick_chunk() returns
+                dalloc(&sp.tile_off, ntl + 1);
+                dalloc((Chunk **)&sp.chunks, (size_t)sp.max_chunks);
+                dalloc(&sp.nchunks, 1);
+                dalloc(&sp.cursor, ntl);
+                PICSP_CUDA(cudaMemsetAsync(sp.nchunks, 0, sizeof(int), c->stream));
+                PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
+            }
+            if (nparts > 1) dalloc(&c->hist_sum[s], ntl);
+        }
+        if (nparts > 1) {
+            alloc_particle_set(&c->spare.x, &c->spare.y, &c->spare.vx, &c->spare.vy, c->part_cap);
+            dalloc(&c->spare.id, (size_t)c->part_cap + 8);
+            dalloc(&c->d_part_sums, (size_t)nparts);
         }
         dalloc(&c->rho, g.nn); dalloc(&c->phi, g.nn);
         dalloc(&c->E_alloc, (size_t)(g.nn + 2 * g.guard));
@@ -756,14 +841,19 @@ void picsp_destroy(picsp_ctx *c) {
     if (c->comm) { try { nccl().CommDestroy(c->comm); } catch (...) {} }
     if (c->have_plans) { cufftDestroy(c->plan_fwd); cufftDestroy(c->plan_inv); }
     for (int s = 0; s < 2; s++) {
-        Species &sp = c->sp[s];
-        cudaFree(sp.x); cudaFree(sp.id);            // x is the base of the set's single allocation
-        cudaFree(sp.den); cudaFree(sp.acc); cudaFree(sp.frac); cudaFree(sp.frac_scratch); cudaFree(sp.hist); cudaFree(sp.hist_next); cudaFree(sp.counters);
-        cudaFree(sp.x2); cudaFree(sp.id2);
-        cudaFree(sp.tile_off); cudaFree(sp.chunks); cudaFree(sp.nchunks); cudaFree(sp.cursor);
-        cudaFree(sp.chunks2); cudaFree(sp.nchunks2); cudaFree(sp.chunk_cnt); cudaFree(sp.chunk_base);
-        cudaFree(sp.cell_cnt); cudaFree(sp.tile_chunk0); cudaFree(sp.scan_chunk0);
+        for (int q = 0; q < 1 + (int)c->more[s].size(); q++) {
+            Species &sp = part_of(c, s, q);
+            cudaFree(sp.x); cudaFree(sp.id);            // x is the base of the set's single allocation
+            if (q == 0) { cudaFree(sp.den); cudaFree(sp.acc); cudaFree(sp.frac); cudaFree(sp.frac_scratch); }   // parts >= 1 alias these
+            cudaFree(sp.hist); cudaFree(sp.hist_next); cudaFree(sp.counters);
+            if (!sp.shares_spare) { cudaFree(sp.x2); cudaFree(sp.id2); }     // (borrowed from the spare otherwise)
+            cudaFree(sp.tile_off); cudaFree(sp.chunks); cudaFree(sp.nchunks); cudaFree(sp.cursor);
+            cudaFree(sp.chunks2); cudaFree(sp.nchunks2); cudaFree(sp.chunk_cnt); cudaFree(sp.chunk_base);
+            cudaFree(sp.cell_cnt); cudaFree(sp.tile_chunk0); cudaFree(sp.scan_chunk0);
+        }
+        cudaFree(c->hist_sum[s]);
     }
+    cudaFree(c->spare.x); cudaFree(c->spare.id); cudaFree(c->d_part_sums);
     cudaFree(c->rho); cudaFree(c->phi); cudaFree(c->E_alloc); cudaFree(c->rhok); cudaFree(c->phik);
     cudaFree(c->d_walls_partial);
     cudaFree(c->d_red); cudaFree(c->d_scalars); cudaFree(c->d_sor_status); cudaFree(c->d_sor_progress); cudaFree(c->d_error); cudaFree(c->stage);
@@ -802,14 +892,22 @@ static void ensure_copy_stream(picsp_ctx *c) {
     for (int k = 0; k < 4; k++) PICSP_CUDA(cudaEventCreateWithFlags(&c->ev_ready[k], cudaEventDisableTiming));
 }
 
+// particles of part `sp` when the species holds n in all: parts are filled in order, only the last one may be short
+static int64_t part_count(const Species &sp, int64_t n) { return std::max<int64_t>(0, std::min<int64_t>(sp.cap, n - sp.first)); }
+
+// a new load has been written into the part's arrays: every derived state is stale
+static void reset_part_state(picsp_ctx *c, Species &sp, int64_t n_part) {
+    sp.n = n_part; sp.hist_valid = false; sp.acc_valid = false;
+    sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0; sp.cnt_valid = false; sp.staged_v_valid = false;
+    sp.steps_since_cellsort = sp.cell_period;
+}
+
 int picsp_species_upload(picsp_ctx *c, int s, const double *x, const double *y, const double *vx, const double *vy, int64_t n) {
     PICSP_API_BEGIN
     check_ctx(c); check_species(s);
     PICSP_CUDA(cudaSetDevice(c->prm.device));
-    Species &sp = c->sp[s];
-    PICSP_REQUIRE(n >= 0 && n <= sp.cap, PICSP_ERR_INVALID, "particle count exceeds the capacity given to picsp_create");
+    PICSP_REQUIRE(n >= 0 && n <= c->cap_total[s], PICSP_ERR_INVALID, "particle count exceeds the capacity given to picsp_create");
     PICSP_REQUIRE(n == 0 || (x && y && vx && vy), PICSP_ERR_INVALID, "null particle array");
-    const size_t bytes = sizeof(double) * (size_t)n;
     // The copies run on the copy stream; the library stream is only waited for when work that may touch THIS species
     // is still queued on it.  The first binning of the new load is enqueued before returning and not waited for, so
     // it runs while the caller uploads the other species (a 5e8-particle binning is ~70 ms, an upload ~290 ms).
@@ -818,17 +916,23 @@ int picsp_species_upload(picsp_ctx *c, int s, const double *x, const double *y, 
         c->busy[0] = c->busy[1] = false;
     }
     ensure_copy_stream(c);
-    PICSP_CUDA(cudaMemcpyAsync(sp.x, x, bytes, cudaMemcpyHostToDevice, c->copy_stream));
-    PICSP_CUDA(cudaMemcpyAsync(sp.y, y, bytes, cudaMemcpyHostToDevice, c->copy_stream));
-    PICSP_CUDA(cudaMemcpyAsync(sp.vx, vx, bytes, cudaMemcpyHostToDevice, c->copy_stream));
-    PICSP_CUDA(cudaMemcpyAsync(sp.vy, vy, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    for_parts(c, s, [&](Species &sp) {
+        const int64_t np = part_count(sp, n);
+        const size_t bytes = sizeof(double) * (size_t)np;
+        if (np == 0) return;
+        PICSP_CUDA(cudaMemcpyAsync(sp.x, x + sp.first, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        PICSP_CUDA(cudaMemcpyAsync(sp.y, y + sp.first, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        PICSP_CUDA(cudaMemcpyAsync(sp.vx, vx + sp.first, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        PICSP_CUDA(cudaMemcpyAsync(sp.vy, vy + sp.first, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    });
     PICSP_CUDA(cudaStreamSynchronize(c->copy_stream));        // the caller's buffers are free again
     const bool other_busy = c->busy[1 - s];
-    if (sp.acc_valid) PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
-    sp.n = n; sp.hist_valid = false; sp.acc_valid = false;
-    sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0; sp.cnt_valid = false; sp.staged_v_valid = false;
-    sp.steps_since_cellsort = sp.cell_period;
-    if (tiled(c) && n > 0) op_sort(c, s);
+    if (c->sp[s].acc_valid) PICSP_CUDA(cudaMemsetAsync(c->sp[s].acc, 0, sizeof(long long) * c->g.nn, c->stream));
+    c->n_total[s] = n;
+    for_parts(c, s, [&](Species &sp) {
+        reset_part_state(c, sp, part_count(sp, n));
+        if (tiled(c) && sp.n > 0) op_sort(c, sp);
+    });
     c->busy[s] = true; c->busy[1 - s] = other_busy;           // what was enqueued here touches species s only
     PICSP_API_END
 }
@@ -844,32 +948,42 @@ int picsp_species_download(picsp_ctx *c, int s, double *x, double *y, double *vx
     PICSP_API_BEGIN
     check_ctx(c); check_species(s);
     PICSP_CUDA(cudaSetDevice(c->prm.device));
-    Species &sp = c->sp[s];
-    const size_t bytes = sizeof(double) * (size_t)sp.n;
-    double *src[4] = {sp.x, sp.y, sp.vx, sp.vy};
     double *dst[4] = {x, y, vx, vy};
-    if (sp.has_perm && sp.n > 0) {
-        // Binned store: bring every array back to upload order on the device (out[id[slot]] = in[slot]) and copy it
-        // out.  The idle half of the sort's ping-pong buffers is the staging area (its contents are dead between
-        // sorts), one buffer per array, so the four un-permutes run back to back on the library stream while the
-        // device->host copies follow them on a second stream: only the first un-permute is exposed.
-        ensure_copy_stream(c);
-        double *stage[4] = {sp.x2, sp.y2, sp.vx2, sp.vy2};
-        for (int k = 0; k < 4; k++) {
-            if (!dst[k]) continue;
-            PICSP_LAUNCH(c, k_unpermute, particle_blocks(c, sp.n, 256), 256, 0, src[k], sp.id, stage[k], (long long)sp.n);
-            PICSP_CUDA(cudaEventRecord(c->ev_ready[k], c->stream));
-            PICSP_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_ready[k], 0));
-            PICSP_CUDA(cudaMemcpyAsync(dst[k], stage[k], bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    for_parts(c, s, [&](Species &sp) {
+        const size_t bytes = sizeof(double) * (size_t)sp.n;
+        double *src[4] = {sp.x, sp.y, sp.vx, sp.vy};
+        borrow_spare(c, sp);
+        if (sp.has_perm && sp.n > 0) {
+            // Binned store: bring every array back to upload order on the device (out[id[slot]] = in[slot]) and copy it
+            // out.  The idle half of the sort's ping-pong buffers is the staging area (its contents are dead between
+            // sorts), one buffer per array, so the four un-permutes run back to back on the library stream while the
+            // device->host copies follow them on a second stream: only the first un-permute is exposed.
+            ensure_copy_stream(c);
+            double *stage[4] = {sp.x2, sp.y2, sp.vx2, sp.vy2};
+            for (int k = 0; k < 4; k++) {
+                if (!dst[k]) continue;
+                PICSP_LAUNCH(c, k_unpermute, particle_blocks(c, sp.n, 256), 256, 0, src[k], sp.id, stage[k], (long long)sp.n);
+                PICSP_CUDA(cudaEventRecord(c->ev_ready[k], c->stream));
+                PICSP_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_ready[k], 0));
+                PICSP_CUDA(cudaMemcpyAsync(dst[k] + sp.first, stage[k], bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+            }
+            PICSP_CUDA(cudaStreamSynchronize(c->copy_stream));     // (several parts share the staging area: one part at a time)
+            sp.staged_v_valid = !sp.shares_spare && dst[2] && dst[3];     // a KE request right after the dump can reduce these directly
+        } else if (sp.n > 0) {
+            for (int k = 0; k < 4; k++)
+                if (dst[k]) PICSP_CUDA(cudaMemcpyAsync(dst[k] + sp.first, src[k], bytes, cudaMemcpyDeviceToHost, c->stream));
         }
-        PICSP_CUDA(cudaStreamSynchronize(c->copy_stream));
-        sp.staged_v_valid = dst[2] && dst[3];     // a KE request right after the dump can reduce these directly
-    } else if (sp.n > 0) {
-        for (int k = 0; k < 4; k++)
-            if (dst[k]) PICSP_CUDA(cudaMemcpyAsync(dst[k], src[k], bytes, cudaMemcpyDeviceToHost, c->stream));
-    }
+    });
     check_device_error(c);
     PICSP_API_END
+}
+
+// writeSpecies row layout {x, y, vx, vy} (src/main.cpp:1156-1159) of one part, built on the device: every particle's
+// 32 bytes go to row id[slot] of `part_rows` (one whole sector per particle)
+static void rows_of_part(picsp_ctx *c, Species &sp, double *part_rows) {
+    if (sp.n <= 0) return;
+    PICSP_LAUNCH(c, k_rows_unpermute, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy,
+                 sp.has_perm ? sp.id : (const uint32_t *)nullptr, (long long)sp.n, reinterpret_cast<double2 *>(part_rows));
 }
 
 int picsp_species_download_rows(picsp_ctx *c, int s, double *rows) {
@@ -877,25 +991,29 @@ int picsp_species_download_rows(picsp_ctx *c, int s, double *rows) {
     check_ctx(c); check_species(s);
     PICSP_REQUIRE(rows != nullptr, PICSP_ERR_INVALID, "null rows");
     PICSP_CUDA(cudaSetDevice(c->prm.device));
-    Species &sp = c->sp[s];
-    if (sp.n > 0 && sp.x2) {
-        // writeSpecies row layout {x, y, vx, vy} (src/main.cpp:1156-1159) built on the device: every particle's 32 bytes
-        // go to row id[slot] of the idle buffer set (one whole sector per particle), then one device->host copy
-        PICSP_LAUNCH(c, k_rows_unpermute, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy,
-                     sp.has_perm ? sp.id : (const uint32_t *)nullptr, (long long)sp.n, reinterpret_cast<double2 *>(sp.x2));
-        sp.staged_v_valid = false;                  // the staging block has been overwritten
-        PICSP_CUDA(cudaMemcpyAsync(rows, sp.x2, sizeof(double) * 4 * (size_t)sp.n, cudaMemcpyDeviceToHost, c->stream));
-        check_device_error(c);
-    } else if (sp.n > 0) {                          // store without a second buffer set (PICSP_FLAG_NO_SORT): interleave on the host
-        std::vector<double> tmp((size_t)sp.n * 4);
+    bool host_interleave = false;
+    for_parts(c, s, [&](Species &sp) {
+        borrow_spare(c, sp);
+        if (sp.n > 0 && sp.x2) {
+            // built in the idle buffer set (a contiguous block of 4 * cap doubles), then one device->host copy
+            rows_of_part(c, sp, sp.x2);
+            sp.staged_v_valid = false;                  // the staging block has been overwritten
+            PICSP_CUDA(cudaMemcpyAsync(rows + 4 * sp.first, sp.x2, sizeof(double) * 4 * (size_t)sp.n, cudaMemcpyDeviceToHost, c->stream));
+            if (sp.shares_spare) PICSP_CUDA(cudaStreamSynchronize(c->stream));
+        } else if (sp.n > 0) host_interleave = true;
+    });
+    if (host_interleave) {                              // store without a second buffer set (PICSP_FLAG_NO_SORT): interleave on the host
+        const int64_t n = c->n_total[s];
+        std::vector<double> tmp((size_t)n * 4);
         double *a = tmp.data();
-        int rc = picsp_species_download(c, s, a, a + sp.n, a + 2 * sp.n, a + 3 * sp.n);
+        int rc = picsp_species_download(c, s, a, a + n, a + 2 * n, a + 3 * n);
         if (rc != PICSP_OK) return rc;
-        for (int64_t p = 0; p < sp.n; p++) {
-            rows[4 * p + 0] = a[p]; rows[4 * p + 1] = a[sp.n + p];
-            rows[4 * p + 2] = a[2 * sp.n + p]; rows[4 * p + 3] = a[3 * sp.n + p];
+        for (int64_t p = 0; p < n; p++) {
+            rows[4 * p + 0] = a[p]; rows[4 * p + 1] = a[n + p];
+            rows[4 * p + 2] = a[2 * n + p]; rows[4 * p + 3] = a[3 * n + p];
         }
     }
+    check_device_error(c);
     PICSP_API_END
 }
 
@@ -903,7 +1021,7 @@ int picsp_species_count(picsp_ctx *c, int s, int64_t *n) {
     PICSP_API_BEGIN
     check_ctx(c); check_species(s);
     PICSP_REQUIRE(n != nullptr, PICSP_ERR_INVALID, "null output");
-    *n = c->sp[s].n;
+    *n = c->n_total[s];
     PICSP_API_END
 }
 
@@ -1029,7 +1147,7 @@ static void one_step(picsp_ctx *c) {
 constexpr long long STEP_GRAPH_MAX_PARTICLES = 1ll << 26;   // above this a step is >= 1 ms of kernels and the launches hide behind them
 
 static bool step_graph_eligible(const picsp_ctx *c) {
-    if (c->profiling || c->comm || c->graphs_disabled || (c->prm.flags & (PICSP_FLAG_NO_GRAPH | PICSP_FLAG_NO_FUSE | PICSP_FLAG_NO_SORT | PICSP_FLAG_WALLS))) return false;
+    if (c->profiling || c->comm || c->graphs_disabled || c->nparts > 1 || (c->prm.flags & (PICSP_FLAG_NO_GRAPH | PICSP_FLAG_NO_FUSE | PICSP_FLAG_NO_SORT | PICSP_FLAG_WALLS))) return false;
     if (c->sp[0].n + c->sp[1].n > STEP_GRAPH_MAX_PARTICLES) return false;
     for (int s = 0; s < 2; s++) {
         const Species &sp = c->sp[s];
@@ -1145,10 +1263,9 @@ static bool ensure_snapshot(picsp_ctx *c) {
         }
     }
     for (int s = 0; s < 2; s++) {
-        const Species &sp = c->sp[s];
-        if (c->snap_rows_cap[s] >= sp.n) continue;
+        if (c->snap_rows_cap[s] >= c->n_total[s]) continue;
         cudaFree(c->snap_rows[s]); c->snap_rows[s] = nullptr; c->snap_rows_cap[s] = 0;
-        const int64_t cap = std::max<int64_t>(sp.cap, 1);
+        const int64_t cap = std::max<int64_t>(c->cap_total[s], 1);
         if (cudaMalloc((void **)&c->snap_rows[s], sizeof(double) * 4 * (size_t)cap) != cudaSuccess) {
             cudaGetLastError(); c->snapshot_unavailable = true; return false;   // e.g. 4e9 particles on one GPU: synchronous dumps
         }
@@ -1209,11 +1326,10 @@ int picsp_dump_begin(picsp_ctx *c, double *rows_i, double *rows_e, double *den_i
     const size_t gbytes = sizeof(double) * (size_t)g.nn;
     for (int s = 0; s < 2; s++) {
         Species &sp = c->sp[s];
-        if ((rows[s] || ke2) && sp.n > 0)
-            PICSP_LAUNCH(c, k_rows_unpermute, particle_blocks(c, sp.n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy,
-                         sp.has_perm ? sp.id : (const uint32_t *)nullptr, (long long)sp.n, reinterpret_cast<double2 *>(c->snap_rows[s]));
+        if (rows[s] || ke2)      // (the parts' rows are contiguous in the snapshot: only the last part may be short)
+            for_parts(c, s, [&](Species &q) { rows_of_part(c, q, c->snap_rows[s] + 4 * q.first); });
         if (ke2) {
-            PICSP_LAUNCH(c, k_ke_rows_partial, RED_BLOCKS, RED_THREADS, 0, c->snap_rows[s], (long long)sp.n, c->d_red);
+            PICSP_LAUNCH(c, k_ke_rows_partial, RED_BLOCKS, RED_THREADS, 0, c->snap_rows[s], (long long)c->n_total[s], c->d_red);
             PICSP_LAUNCH(c, k_sum_final, 1, 1024, 0, c->d_red, RED_BLOCKS, c->snap_ke + s);
         }
         // density: the sum over ranks lands on rank 0 only ("at dump steps only: reduce den_i, den_e to rank 0")
@@ -1240,8 +1356,8 @@ int picsp_dump_begin(picsp_ctx *c, double *rows_i, double *rows_e, double *den_i
     // (a copy KERNEL on a high-priority stream instead of the copy engines was tried: it takes SM slots from the mover and
     // is no faster over PCIe — e2e 5.1e10 -> 4.9e10 / 4.3e10 / 3.5e10 with 8 / 32 / 128 CTAs, profiles/r02_e2e_dumps.md)
     for (int s = 0; s < 2; s++)
-        if (rows[s] && c->sp[s].n > 0)
-            PICSP_CUDA(cudaMemcpyAsync(rows[s], c->snap_rows[s], sizeof(double) * 4 * (size_t)c->sp[s].n, cudaMemcpyDeviceToHost,
+        if (rows[s] && c->n_total[s] > 0)
+            PICSP_CUDA(cudaMemcpyAsync(rows[s], c->snap_rows[s], sizeof(double) * 4 * (size_t)c->n_total[s], cudaMemcpyDeviceToHost,
                                        s == 0 ? c->copy_stream : c->copy_stream2));
     PICSP_CUDA(cudaEventRecord(c->ev_dump_done, c->copy_stream));
     PICSP_CUDA(cudaEventRecord(c->ev_dump_done2, c->copy_stream2));
@@ -1264,18 +1380,23 @@ int picsp_compute_ke(picsp_ctx *c, int s, double *ke) {
     PICSP_REQUIRE(ke != nullptr, PICSP_ERR_INVALID, "null output");
     PICSP_CUDA(cudaSetDevice(c->prm.device));
     Species &sp = c->sp[s];
-    if (sp.has_perm && sp.n > 0 && sp.staged_v_valid) {
-        // the download that preceded this call left the velocities in upload order in the staging buffers
-        PICSP_LAUNCH(c, k_ke_partial, RED_BLOCKS, RED_THREADS, 0, sp.vx2, sp.vy2, (long long)sp.n, c->d_red);
-    } else if (sp.has_perm && sp.n > 0) {
-        // sorted store: reduce in upload order so the sum is reproducible regardless of the storage order
-        // (staging = the idle half of the sort's ping-pong buffers, dead between sorts)
-        PICSP_LAUNCH(c, k_ke_terms, particle_blocks(c, sp.n, 256), 256, 0, sp.vx, sp.vy, sp.id, (long long)sp.n, sp.x2);
-        PICSP_LAUNCH(c, k_sum_partial, RED_BLOCKS, RED_THREADS, 0, sp.x2, (long long)sp.n, c->d_red);
-    } else {
-        PICSP_LAUNCH(c, k_ke_partial, RED_BLOCKS, RED_THREADS, 0, sp.vx, sp.vy, (long long)sp.n, c->d_red);
-    }
-    PICSP_LAUNCH(c, k_sum_final, 1, 1024, 0, c->d_red, RED_BLOCKS, c->d_scalars + 0);
+    for_parts(c, s, [&](Species &q) {
+        borrow_spare(c, q);
+        if (q.has_perm && q.n > 0 && q.staged_v_valid) {
+            // the download that preceded this call left the velocities in upload order in the staging buffers
+            PICSP_LAUNCH(c, k_ke_partial, RED_BLOCKS, RED_THREADS, 0, q.vx2, q.vy2, (long long)q.n, c->d_red);
+        } else if (q.has_perm && q.n > 0) {
+            // sorted store: reduce in upload order so the sum is reproducible regardless of the storage order
+            // (staging = the idle half of the sort's ping-pong buffers, dead between sorts)
+            PICSP_LAUNCH(c, k_ke_terms, particle_blocks(c, q.n, 256), 256, 0, q.vx, q.vy, q.id, (long long)q.n, q.x2);
+            PICSP_LAUNCH(c, k_sum_partial, RED_BLOCKS, RED_THREADS, 0, q.x2, (long long)q.n, c->d_red);
+        } else {
+            PICSP_LAUNCH(c, k_ke_partial, RED_BLOCKS, RED_THREADS, 0, q.vx, q.vy, (long long)q.n, c->d_red);
+        }
+        // one part: the species' sum; several: per-part sums, added up (in part order) below
+        PICSP_LAUNCH(c, k_sum_final, 1, 1024, 0, c->d_red, RED_BLOCKS, c->nparts > 1 ? c->d_part_sums + q.part : c->d_scalars + 0);
+    });
+    if (c->nparts > 1) PICSP_LAUNCH(c, k_sum_final, 1, 1024, 0, c->d_part_sums, c->nparts, c->d_scalars + 0);
     if (c->comm) PICSP_NCCL(nccl().AllReduce(c->d_scalars, c->d_scalars, 1, ncclFloat64, ncclSum, c->comm, c->stream));
     double sum = read_scalar(c, c->d_scalars + 0);
     sum += 0.5 * (sp.spwt * sp.m);   // src/main.cpp:1198: added, not multiplied (Q10)
@@ -1303,9 +1424,12 @@ int picsp_repush_count(picsp_ctx *c, int s, int64_t *n) {
     PICSP_REQUIRE(n != nullptr, PICSP_ERR_INVALID, "null output");
     PICSP_CUDA(cudaSetDevice(c->prm.device));
     unsigned long long *h = reinterpret_cast<unsigned long long *>(c->h_pinned + 24);
-    PICSP_CUDA(cudaMemcpyAsync(h, c->sp[s].counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    PICSP_CUDA(cudaStreamSynchronize(c->stream));
-    *n = (int64_t)*h;
+    *n = 0;
+    for_parts(c, s, [&](Species &q) {
+        PICSP_CUDA(cudaMemcpyAsync(h, q.counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        PICSP_CUDA(cudaStreamSynchronize(c->stream));
+        *n += (int64_t)*h;
+    });
     PICSP_API_END
 }
 
@@ -1315,24 +1439,29 @@ int picsp_straggler_count(picsp_ctx *c, int s, int64_t *n) {
     PICSP_REQUIRE(n != nullptr, PICSP_ERR_INVALID, "null output");
     PICSP_CUDA(cudaSetDevice(c->prm.device));
     unsigned long long *h = reinterpret_cast<unsigned long long *>(c->h_pinned + 24);
-    PICSP_CUDA(cudaMemcpyAsync(h, c->sp[s].counters + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    PICSP_CUDA(cudaStreamSynchronize(c->stream));
-    *n = (int64_t)*h;
+    *n = 0;
+    for_parts(c, s, [&](Species &q) {
+        PICSP_CUDA(cudaMemcpyAsync(h, q.counters + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        PICSP_CUDA(cudaStreamSynchronize(c->stream));
+        *n += (int64_t)*h;
+    });
     PICSP_API_END
 }
 
 int picsp_set_sort_period(picsp_ctx *c, int s, int period) {
     PICSP_API_BEGIN
     check_ctx(c); check_species(s);
-    c->sp[s].sort_period = period > 0 ? period : (s == 0 ? 96 : 8);
+    for_parts(c, s, [&](Species &q) { q.sort_period = period > 0 ? period : (s == 0 ? 96 : 8); });
     PICSP_API_END
 }
 
 int picsp_set_cell_sort_period(picsp_ctx *c, int s, int period) {
     PICSP_API_BEGIN
     check_ctx(c); check_species(s);
-    c->sp[s].cell_period = period > 0 ? period : 0;
-    c->sp[s].steps_since_cellsort = c->sp[s].cell_period;       // due at the next push
+    for_parts(c, s, [&](Species &q) {
+        q.cell_period = period > 0 ? period : 0;
+        q.steps_since_cellsort = q.cell_period;       // due at the next push
+    });
     PICSP_API_END
 }
 
@@ -1340,7 +1469,7 @@ int picsp_set_bank_order(picsp_ctx *c, int s, int mode) {
     PICSP_API_BEGIN
     check_ctx(c); check_species(s);
     PICSP_REQUIRE(mode >= -1 && mode <= 1, PICSP_ERR_INVALID, "bank order mode must be -1 (automatic), 0 (off) or 1 (on)");
-    c->sp[s].bank_order = mode;
+    for_parts(c, s, [&](Species &q) { q.bank_order = mode; });
     PICSP_API_END
 }
 
@@ -1348,7 +1477,7 @@ int picsp_set_deposit_aggregation(picsp_ctx *c, int s, int mode) {
     PICSP_API_BEGIN
     check_ctx(c); check_species(s);
     PICSP_REQUIRE(mode >= -1 && mode <= 1, PICSP_ERR_INVALID, "aggregation mode must be -1 (automatic), 0 (off) or 1 (on)");
-    c->sp[s].aggregate = mode;
+    for_parts(c, s, [&](Species &q) { q.aggregate = mode; });
     PICSP_API_END
 }
 
@@ -1393,15 +1522,16 @@ int picsp_species_fill_synthetic(picsp_ctx *c, int s, int64_t n, int64_t first_i
     PICSP_API_BEGIN
     check_ctx(c); check_species(s);
     PICSP_CUDA(cudaSetDevice(c->prm.device));
-    Species &sp = c->sp[s];
-    PICSP_REQUIRE(n >= 0 && n <= sp.cap, PICSP_ERR_INVALID, "particle count exceeds capacity");
-    if (n > 0)
-        PICSP_LAUNCH(c, k_fill_synthetic, particle_blocks(c, n, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)n,
-                     (long long)first_index, seed, c->g.xl, c->g.yl, vth, xdrift);
-    if (sp.acc_valid) PICSP_CUDA(cudaMemsetAsync(sp.acc, 0, sizeof(long long) * c->g.nn, c->stream));
-    sp.n = n; sp.hist_valid = false; sp.acc_valid = false;
-    sp.has_perm = false; sp.sorted = false; sp.steps_since_sort = 0; sp.cnt_valid = false; sp.staged_v_valid = false;
-    sp.steps_since_cellsort = sp.cell_period;
+    PICSP_REQUIRE(n >= 0 && n <= c->cap_total[s], PICSP_ERR_INVALID, "particle count exceeds capacity");
+    if (c->sp[s].acc_valid) PICSP_CUDA(cudaMemsetAsync(c->sp[s].acc, 0, sizeof(long long) * c->g.nn, c->stream));
+    c->n_total[s] = n;
+    for_parts(c, s, [&](Species &sp) {
+        const int64_t np = part_count(sp, n);
+        if (np > 0)
+            PICSP_LAUNCH(c, k_fill_synthetic, particle_blocks(c, np, 256), 256, 0, sp.x, sp.y, sp.vx, sp.vy, (long long)np,
+                         (long long)(first_index + sp.first), seed, c->g.xl, c->g.yl, vth, xdrift);
+        reset_part_state(c, sp, np);
+    });
     PICSP_CUDA(cudaStreamSynchronize(c->stream));
     PICSP_API_END
 }
@@ -1431,6 +1561,13 @@ int picsp_profile_reset(picsp_ctx *c) {
     PICSP_CUDA(cudaStreamSynchronize(c->stream));
     profile_collect(c);
     for (auto &t : c->timers) { t.ms = 0.0; t.calls = 0; }
+    PICSP_API_END
+}
+int picsp_parts(picsp_ctx *c, int *parts) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    PICSP_REQUIRE(parts != nullptr, PICSP_ERR_INVALID, "null output");
+    *parts = c->nparts;
     PICSP_API_END
 }
 int picsp_kernel_launches(picsp_ctx *c, int64_t *n) {

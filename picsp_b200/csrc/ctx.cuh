@@ -63,10 +63,19 @@ struct Geom {
 // ---------------------------------------------------------------------------
 // per-species device store: structure of arrays, double precision
 // ---------------------------------------------------------------------------
+// A species may be split into several PARTS (contiguous ranges of its particles in upload order), each a store of its
+// own — bins, chunk table, histogram, slot map — that deposit into the species' one accumulator grid.  Parts exist so
+// that the second buffer set of the re-binning (the sort destination) can be ONE part-sized spare shared by all
+// parts of both species instead of a full copy of the state: 4e9 particles (144 GB with their slot maps) then fit one
+// 180 GB device.  Every part is a Species object; the species-level members (q, m, spwt, den, acc, frac, ...) of the
+// parts >= 1 alias those of part 0 (= picsp_ctx::sp[s]).  One part (the normal case) is exactly the old layout.
 struct Species {
+    int s = 0, part = 0;           // species index, part index
+    int64_t first = 0;             // index (in the species' upload order) of this part's first particle
+    bool shares_spare = false;     // x2.. / id2 are borrowed from picsp_ctx::spare (several parts) instead of owned
     double *x = nullptr, *y = nullptr, *vx = nullptr, *vy = nullptr;
     uint32_t *id = nullptr;        // slot -> index in upload order; nullptr == identity
-    int64_t n = 0, cap = 0;
+    int64_t n = 0, cap = 0;        // particles / capacity of THIS part
     double q = 0, m = 0, spwt = 0;
     double *den = nullptr;         // nn, accumulating
     long long *acc = nullptr;      // nn, fixed-point deposit accumulator (order-independent => deterministic)
@@ -123,7 +132,14 @@ struct picsp_ctx {
     picsp_params prm;
     picsp::Geom g;
     cudaStream_t stream = nullptr;
-    picsp::Species sp[2];
+    picsp::Species sp[2];                        // part 0 of every species (the whole species when nparts == 1)
+    int nparts = 1;                              // parts per species (picsp_params::reserved, 0 = as many as the device memory asks for)
+    std::vector<picsp::Species> more[2];         // parts 1 .. nparts-1
+    int64_t n_total[2] = {0, 0}, cap_total[2] = {0, 0};
+    int64_t part_cap = 0;                        // capacity of every part (all parts of both species are the same size, so any set can be the spare)
+    struct Spare { double *x = nullptr, *y = nullptr, *vx = nullptr, *vy = nullptr; uint32_t *id = nullptr; } spare;   // nparts > 1: THE second buffer set
+    unsigned int *hist_sum[2] = {nullptr, nullptr};   // nparts > 1: sum of the parts' tile histograms (fixed-point scale)
+    double *d_part_sums = nullptr;               // nparts > 1: per-part partial results of reductions
 
     double *rho = nullptr, *phi = nullptr;
     double2 *E_alloc = nullptr, *E = nullptr;     // interleaved {efx, efy}; E = E_alloc + guard

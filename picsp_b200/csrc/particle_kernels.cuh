@@ -151,6 +151,12 @@ __global__ void k_tile_hist(const double *__restrict__ x, const double *__restri
 // Multi-CTA: every thread sums one tile's neighbourhood (25 independent L2 loads), the CTA maximum goes
 // to scratch[0] with atomicMax, and the last CTA to finish (ticket in scratch[1]) converts the maximum into
 // the fraction-bit count and resets the scratch for the next call.
+// sum of the parts' histograms (a species split into several stores deposits into ONE accumulator grid)
+__global__ void k_hist_add(unsigned int *__restrict__ sum, const unsigned int *__restrict__ h, int nt) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nt) sum[t] += h[t];
+}
+
 __global__ void __launch_bounds__(256)
 k_frac_from_hist(const unsigned int *__restrict__ hist, int ntx, int nty, int *__restrict__ frac, int cap,
                  unsigned long long *__restrict__ scratch, long long n, int force_agg) {

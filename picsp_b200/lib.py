@@ -32,7 +32,7 @@ class CRunConfig(C.Structure):
 class CParams(C.Structure):
     _fields_ = [("numxCells", C.c_int32), ("numyCells", C.c_int32), ("stepSize", C.c_double), ("timeStep", C.c_double),
                 ("solverType", C.c_int32), ("flags", C.c_int32), ("charge", C.c_double * 2), ("mass", C.c_double * 2),
-                ("spwt", C.c_double * 2), ("capacity", C.c_int64 * 2), ("device", C.c_int32), ("reserved", C.c_int32)]
+                ("spwt", C.c_double * 2), ("capacity", C.c_int64 * 2), ("device", C.c_int32), ("parts", C.c_int32)]
 
 
 def abi_symbols():
@@ -101,6 +101,7 @@ def load_library():
         "picsp_profile_get": ([ctx, C.c_int, _dp, _i64p], C.c_int),
         "picsp_profile_reset": ([ctx], C.c_int),
         "picsp_kernel_launches": ([ctx, _i64p], C.c_int),
+        "picsp_parts": ([ctx, C.POINTER(C.c_int)], C.c_int),
         "picsp_host_parse_ini": ([C.c_char_p, C.POINTER(CRunConfig), C.c_int], C.c_int),
         "picsp_host_ini_dump": ([C.c_char_p, C.c_char_p, C.c_int64], C.c_int64),
         "picsp_host_loader_create": ([C.c_uint32], C.c_void_p),

@@ -41,6 +41,7 @@ class Params:
     flags: int = 0
     device: int = 0
     capacity: tuple | None = None   # per-rank capacity; defaults to the global counts
+    parts: int = 0                  # picsp_params::parts (0 = automatic: 1 unless the device memory asks for more)
     spwt: list = field(default_factory=list)
 
     def __post_init__(self):
@@ -63,6 +64,7 @@ class Simulation:
         cap = p.capacity or (p.nParticlesI, p.nParticlesE)
         cp.capacity[0], cp.capacity[1] = cap
         cp.device = p.device
+        cp.parts = p.parts
         self.nix, self.niy = p.numxCells + 1, p.numyCells + 1
         self.ctx = C.c_void_p()
         check(self.L.picsp_create(C.byref(cp), C.byref(self.ctx)))
@@ -209,6 +211,11 @@ class Simulation:
             check(self.L.picsp_profile_get(self.ctx, i, C.byref(ms), C.byref(calls)))
             out[name] = (ms.value, calls.value)
         return out
+
+    def parts(self):
+        n = C.c_int()
+        check(self.L.picsp_parts(self.ctx, C.byref(n)))
+        return n.value
 
     def kernel_launches(self):
         n = C.c_int64()
