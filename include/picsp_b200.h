@@ -79,7 +79,9 @@ enum {
      * repo's own CPU restatement oracle/walls_check.c, which is NOT the reference.  Needs the tiled store
      * (not combinable with PICSP_FLAG_NO_SORT); usually combined with PICSP_FLAG_CLEAR_DENSITY. */
     PICSP_FLAG_WALLS          = 1 << 6,
-    PICSP_FLAG_NCCL_ONLY      = 1 << 7  /* sharded runs: sum the partial rho with ncclAllReduce instead of the library's own peer-memory kernels (cross-check path) */
+    PICSP_FLAG_NCCL_ONLY      = 1 << 7, /* sharded runs: sum the partial rho with ncclAllReduce instead of the library's own peer-memory kernels (cross-check path) */
+    PICSP_FLAG_CUFFT_ONLY     = 1 << 8, /* spectral solver: always cuFFT (cross-check path; by default node counts with a prime factor > 127, e.g. 2049 = 3 * 683, use the library's own shared-memory transform) */
+    PICSP_FLAG_OWN_FFT        = 1 << 9  /* spectral solver: always the library's own transform, whatever the node count (cross-check path for small grids) */
 };
 
 /* Normalised quantities, i.e. the reference's globals after parse_ini_file

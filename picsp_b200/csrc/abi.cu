@@ -14,6 +14,7 @@
 #include "particle_kernels.cuh"
 #include "peer_kernels.cuh"
 #include "tile_kernels.cuh"
+#include "fft_kernels.cuh"
 
 using namespace picsp;
 
@@ -415,12 +416,130 @@ void op_compute_rho(picsp_ctx *c) {
     }
 }
 
+// -- own shared-memory DFT (fft_kernels.cuh) -----------------------------------------------------
+int largest_prime_factor(int m) {
+    int best = 1;
+    for (int f = 2; (long long)f * f <= m; f++) while (m % f == 0) { best = std::max(best, f); m /= f; }
+    return std::max(best, m);
+}
+int gcd_int(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+constexpr size_t OWN_FFT_MAX_SMEM = 200 * 1024;
+
+// M = P * Q with gcd(P, Q) = 1 and P <= 32 that needs the least shared memory (P * L complex, L = 2^k >= 2Q - 1)
+bool choose_fft_split(int M, int *P, int *Q, int *L, int *logL) {
+    long long best = -1;
+    for (int p = 1; p <= 32 && p <= M; p++) {
+        if (M % p) continue;
+        const int q = M / p;
+        if (gcd_int(p, q) != 1) continue;
+        int l = 2, ll = 1;
+        while (l < 2 * q - 1) { l <<= 1; ll++; }
+        const long long cost = (long long)p * l;
+        if (best < 0 || cost < best) { best = cost; *P = p; *Q = q; *L = l; *logL = ll; }
+    }
+    return best > 0 && fft_padded((size_t)best) * sizeof(double2) <= OWN_FFT_MAX_SMEM;
+}
+
+template <class T> void upload_table(void **dev, const std::vector<T> &h, cudaStream_t st) {
+    PICSP_CUDA(cudaMalloc(dev, std::max<size_t>(h.size(), 1) * sizeof(T)));
+    PICSP_CUDA(cudaMemcpyAsync(*dev, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    PICSP_CUDA(cudaStreamSynchronize(st));       // the host vector dies with the caller
+}
+
+void build_own_fft_plan(picsp_ctx *c, int which, int M) {
+    picsp_ctx::OwnFft &f = c->fft;
+    int P = 1, Q = M, L = 2, logL = 1;
+    PICSP_REQUIRE(choose_fft_split(M, &P, &Q, &L, &logL), PICSP_ERR_INVALID, "own FFT: the transform does not fit shared memory");
+    f.M[which] = M; f.P[which] = P; f.Q[which] = Q; f.L[which] = L; f.logL[which] = logL;
+    const long double PI = 3.141592653589793238462643383279502884L;
+    std::vector<double2> chirp((size_t)Q), b((size_t)L, make_double2(0.0, 0.0)), tw((size_t)L / 2), wp((size_t)P * P);
+    for (int n = 0; n < Q; n++) {                      // c[n] = exp(-i pi n^2 / Q), the argument reduced exactly
+        const long long r = ((long long)n * n) % (2ll * Q);
+        const long double a = PI * (long double)r / (long double)Q;
+        chirp[(size_t)n] = make_double2((double)cosl(a), (double)-sinl(a));
+    }
+    for (int m = 0; m < Q; m++) {                      // b[m] = conj(c[|m|]), m = -(Q-1) .. Q-1, wrapped to length L
+        const double2 v = make_double2(chirp[(size_t)m].x, -chirp[(size_t)m].y);
+        b[(size_t)m] = v;
+        if (m > 0) b[(size_t)(L - m)] = v;
+    }
+    for (int k = 0; k < L / 2; k++) {
+        const long double a = 2.0L * PI * (long double)k / (long double)L;
+        tw[(size_t)k] = make_double2((double)cosl(a), (double)-sinl(a));
+    }
+    for (int k1 = 0; k1 < P; k1++)
+        for (int n1 = 0; n1 < P; n1++) {
+            const long double a = 2.0L * PI * (long double)((k1 * n1) % P) / (long double)P;
+            wp[(size_t)k1 * P + n1] = make_double2((double)cosl(a), (double)-sinl(a));
+        }
+    std::vector<int> in_pos((size_t)M), out_idx((size_t)M);
+    for (int n1 = 0; n1 < P; n1++)
+        for (int n2 = 0; n2 < Q; n2++) in_pos[(size_t)(((long long)n1 * Q + (long long)n2 * P) % M)] = n1 * L + n2;
+    for (int k = 0; k < M; k++) out_idx[(size_t)(k % P) * Q + (k % Q)] = k;
+    upload_table(&f.chirp[which], chirp, c->stream); upload_table(&f.tw[which], tw, c->stream);
+    upload_table(&f.wp[which], wp, c->stream);
+    upload_table(&f.in_pos[which], in_pos, c->stream); upload_table(&f.out_idx[which], out_idx, c->stream);
+    void *b_dev = nullptr;
+    upload_table(&b_dev, b, c->stream);
+    PICSP_CUDA(cudaMalloc(&f.bhat[which], (size_t)L * sizeof(double2)));
+    const size_t bsm = fft_padded((size_t)L) * sizeof(double2);
+    PICSP_CUDA(cudaFuncSetAttribute(k_blue_bhat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OWN_FFT_MAX_SMEM));
+    PICSP_LAUNCH(c, k_blue_bhat, 1, FFT_THREADS, bsm, (const double2 *)b_dev, (double2 *)f.bhat[which], L, logL, (const double2 *)f.tw[which]);
+    PICSP_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(b_dev);
+    f.smem[which] = fft_padded((size_t)P * L) * sizeof(double2);
+}
+
+BluePlanDev own_fft_plan(const picsp_ctx *c, int which) {
+    const picsp_ctx::OwnFft &f = c->fft;
+    BluePlanDev pl;
+    pl.M = f.M[which]; pl.P = f.P[which]; pl.Q = f.Q[which]; pl.L = f.L[which]; pl.logL = f.logL[which];
+    pl.chirp = (const double2 *)f.chirp[which]; pl.bhat = (const double2 *)f.bhat[which]; pl.tw = (const double2 *)f.tw[which];
+    pl.in_pos = (const int *)f.in_pos[which]; pl.out_idx = (const int *)f.out_idx[which]; pl.wp = (const double2 *)f.wp[which];
+    return pl;
+}
+
+// cuFFT unless a node count has a prime factor > 127 (cuFFT then runs Bluestein through global memory: 2049^2 takes
+// 1.5-1.7 ms, the shared-memory transform a fraction of that; measured in profiles/r02b_own_fft.md)
+void setup_own_fft(picsp_ctx *c) {
+    const Geom &g = c->g;
+    const int flags = c->prm.flags;
+    if (flags & PICSP_FLAG_CUFFT_ONLY) return;
+    const bool wanted = (flags & PICSP_FLAG_OWN_FFT) || largest_prime_factor(g.nix) > 127 || largest_prime_factor(g.niy) > 127;
+    if (!wanted) return;
+    int P, Q, L, logL;
+    if (!choose_fft_split(g.niy, &P, &Q, &L, &logL) || !choose_fft_split(g.nix, &P, &Q, &L, &logL)) {
+        PICSP_REQUIRE(!(flags & PICSP_FLAG_OWN_FFT), PICSP_ERR_INVALID, "PICSP_FLAG_OWN_FFT: a transform of this length does not fit shared memory");
+        return;                                        // too long for shared memory: cuFFT
+    }
+    build_own_fft_plan(c, 0, g.niy);
+    build_own_fft_plan(c, 1, g.nix);
+    picsp_ctx::OwnFft &f = c->fft;
+    PICSP_CUDA(cudaFuncSetAttribute(k_fft_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem[0]));
+    PICSP_CUDA(cudaFuncSetAttribute(k_fft_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem[0]));
+    PICSP_CUDA(cudaFuncSetAttribute(k_fft_cols<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem[1]));
+    PICSP_CUDA(cudaFuncSetAttribute(k_fft_cols<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem[1]));
+    f.on = true;
+}
+
 void op_solve_spectral(picsp_ctx *c) {
     PhaseScope ph(c, PICSP_PHASE_SOLVE);
     const Geom &g = c->g;
+    const int Nh = g.niy / 2 + 1;
+    if (c->fft.on) {
+        // D2Z = rows forward (two real rows per transform) + columns forward; Z2D = columns inverse + rows inverse
+        const BluePlanDev py = own_fft_plan(c, 0), px = own_fft_plan(c, 1);
+        double2 *rhok = reinterpret_cast<double2 *>(c->rhok), *phik = reinterpret_cast<double2 *>(c->phik);
+        PICSP_LAUNCH(c, k_fft_rows_fwd, (g.nix + 1) / 2, FFT_THREADS, c->fft.smem[0], py, c->rho, rhok, g.nix);
+        PICSP_LAUNCH(c, (k_fft_cols<false>), Nh, FFT_THREADS, c->fft.smem[1], px, rhok, Nh);
+        PICSP_LAUNCH(c, k_kspace_green, blocks_for((long long)g.nix * Nh, 256, c->num_sms * 8), 256, 0, c->rhok, c->phik,
+                     g.nix, g.niy, g.xl, g.yl);
+        PICSP_LAUNCH(c, (k_fft_cols<true>), Nh, FFT_THREADS, c->fft.smem[1], px, phik, Nh);
+        PICSP_LAUNCH(c, k_fft_rows_inv, (g.nix + 1) / 2, FFT_THREADS, c->fft.smem[0], py, (const double2 *)phik, c->phi, g.nix);
+        return;
+    }
     PICSP_REQUIRE(c->have_plans, PICSP_ERR_STATE, "cuFFT plans missing");
     PICSP_CUFFT(cufftExecD2Z(c->plan_fwd, c->rho, c->rhok));
-    const int Nh = g.niy / 2 + 1;
     PICSP_LAUNCH(c, k_kspace_green, blocks_for((long long)g.nix * Nh, 256, c->num_sms * 8), 256, 0, c->rhok, c->phik,
                  g.nix, g.niy, g.xl, g.yl);
     PICSP_CUFFT(cufftExecZ2D(c->plan_inv, c->phik, c->phi));
@@ -808,11 +927,14 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
         if (p->solverType == PICSP_SOLVER_SPECTRAL) {
             const size_t nk = (size_t)g.nix * (g.niy / 2 + 1);
             dalloc(&c->rhok, nk); dalloc(&c->phik, nk);
-            PICSP_CUFFT(cufftPlan2d(&c->plan_fwd, g.nix, g.niy, CUFFT_D2Z));
-            PICSP_CUFFT(cufftPlan2d(&c->plan_inv, g.nix, g.niy, CUFFT_Z2D));
-            PICSP_CUFFT(cufftSetStream(c->plan_fwd, c->stream));
-            PICSP_CUFFT(cufftSetStream(c->plan_inv, c->stream));
-            c->have_plans = true;
+            setup_own_fft(c);
+            if (!c->fft.on) {
+                PICSP_CUFFT(cufftPlan2d(&c->plan_fwd, g.nix, g.niy, CUFFT_D2Z));
+                PICSP_CUFFT(cufftPlan2d(&c->plan_inv, g.nix, g.niy, CUFFT_Z2D));
+                PICSP_CUFFT(cufftSetStream(c->plan_fwd, c->stream));
+                PICSP_CUFFT(cufftSetStream(c->plan_inv, c->stream));
+                c->have_plans = true;
+            }
         }
         PICSP_CUDA(cudaStreamSynchronize(c->stream));
         *out = c;
@@ -840,6 +962,9 @@ void picsp_destroy(picsp_ctx *c) {
     }
     if (c->comm) { try { nccl().CommDestroy(c->comm); } catch (...) {} }
     if (c->have_plans) { cufftDestroy(c->plan_fwd); cufftDestroy(c->plan_inv); }
+    for (int w = 0; w < 2; w++) {
+        cudaFree(c->fft.chirp[w]); cudaFree(c->fft.bhat[w]); cudaFree(c->fft.tw[w]); cudaFree(c->fft.in_pos[w]); cudaFree(c->fft.out_idx[w]); cudaFree(c->fft.wp[w]);
+    }
     for (int s = 0; s < 2; s++) {
         for (int q = 0; q < 1 + (int)c->more[s].size(); q++) {
             Species &sp = part_of(c, s, q);
@@ -1099,7 +1224,7 @@ int picsp_deposit(picsp_ctx *c, int s) { PICSP_OP(check_species(s); op_deposit(c
 int picsp_compute_rho(picsp_ctx *c) { PICSP_OP(op_compute_rho(c)) }
 int picsp_solve(picsp_ctx *c) { PICSP_OP(op_solve(c)) }
 int picsp_solve_spectral(picsp_ctx *c) {
-    PICSP_OP(PICSP_REQUIRE(c->have_plans, PICSP_ERR_STATE, "context was created with solverType 2: no cuFFT plans"); op_solve_spectral(c))
+    PICSP_OP(PICSP_REQUIRE(c->have_plans || c->fft.on, PICSP_ERR_STATE, "context was created with solverType 2: no FFT plans"); op_solve_spectral(c))
 }
 int picsp_solve_sor(picsp_ctx *c, int64_t *sweeps, double *l2) {
     PICSP_API_BEGIN

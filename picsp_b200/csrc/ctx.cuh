@@ -146,6 +146,14 @@ struct picsp_ctx {
     cufftHandle plan_fwd = 0, plan_inv = 0;
     bool have_plans = false;
     cufftDoubleComplex *rhok = nullptr, *phik = nullptr;
+    // own shared-memory DFT for node counts with a large prime factor (fft_kernels.cuh); plan 0: length niy (rows),
+    // plan 1: length nix (columns; the same tables when nix == niy)
+    struct OwnFft {
+        bool on = false;
+        int M[2] = {0, 0}, P[2] = {0, 0}, Q[2] = {0, 0}, L[2] = {0, 0}, logL[2] = {0, 0};
+        void *chirp[2] = {}, *bhat[2] = {}, *tw[2] = {}, *in_pos[2] = {}, *out_idx[2] = {}, *wp[2] = {};
+        size_t smem[2] = {0, 0};
+    } fft;
 
     // small device scratch
     double *d_red = nullptr;        // reduction partials

@@ -1,0 +1,259 @@
+// picsp_b200/csrc/fft_kernels.cuh — the 2-D real DFT of spectralPotentialSolver (src/main.cpp:960-1058) for node
+// counts with a LARGE PRIME FACTOR, each 1-D transform resident in shared memory.
+//
+// The reference transforms the (N+1) x (N+1) NODE array (Q7), so a power-of-two cell count gives awkward lengths:
+// 2049 = 3 * 683, 257 (prime), 4097 = 17 * 241.  cuFFT falls back to Bluestein's algorithm through global memory there
+// (2049^2: 1.5-1.7 ms per solve, 19 % of BASELINE config 5's step on 8 GPUs).  Here a length M = P * Q, gcd(P, Q) = 1, is
+// split by the prime-factor map (Good-Thomas, no twiddle factors) into P transforms of length Q and Q of length P:
+//   * length Q (any Q, prime or not) by Bluestein's chirp-z identity
+//         X[k] = c[k] * sum_n (x[n] c[n]) conj(c)[k - n],   c[n] = exp(-i pi n^2 / Q),
+//     i.e. one circular convolution of power-of-two length L >= 2Q - 1: decimation in frequency forward (natural ->
+//     bit-reversed order), product with the pre-transformed chirp filter (stored in that same order, 1/L folded in),
+//     decimation in time inverse (bit-reversed -> natural): no reordering pass.  Three radix-2 stages per pass on 8
+//     elements held in registers (radix 8: 4 passes over shared memory for L = 2048 instead of 11), one twiddle
+//     look-up per thread and pass;
+//   * length P (<= 32) as a direct DFT from a P x P table.
+// All P rows of a transform sit in shared memory at once (P * L complex doubles: 96 KB for 2049), one CTA per
+// transform; the four passes of the 2-D transform are
+//   rows forward   two REAL rows packed into one complex transform, separated into two half spectra,
+//   columns forward / inverse   in place on the [Nx][Ny/2+1] half-spectrum array (same layout as cuFFT's D2Z),
+//   rows inverse   two Hermitian half rows packed into one complex transform whose real / imaginary parts are the rows.
+// The inverse transform is conj(DFT(conj(.))).  Tables are computed on the host in long double.
+// Semantics are exactly cuFFT's D2Z / Z2D (unnormalised), so k_kspace_green sits between the passes unchanged and the
+// cuFFT path stays as a cross-check (PICSP_FLAG_CUFFT_ONLY).
+#pragma once
+#include "ctx.cuh"
+
+namespace picsp {
+
+constexpr int FFT_THREADS = 256;
+
+struct BluePlanDev {
+    int M, P, Q, L, logL;
+    const double2 *chirp;    // [Q]      c[n]
+    const double2 *bhat;     // [L]      DIF(b) / L, b[m] = conj(c[|m|]) wrapped, in DIF output order
+    const double2 *tw;       // [L/2]    exp(-2 pi i k / L)
+    const int *in_pos;       // [M]      n -> n1 * L + n2   (n = (n1 Q + n2 P) mod M)
+    const int *out_idx;      // [P * Q]  k1 * Q + k2 -> k   (k = k1 mod P, k = k2 mod Q)
+    const double2 *wp;       // [P * P]  exp(-2 pi i k1 n1 / P)
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {     // a * conj(b)
+    return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -a.x * b.y));
+}
+
+// Shared-memory index with one complex of padding per 8: a thread of the last passes owns 8 CONSECUTIVE elements, so
+// without it the lanes of a quarter-warp would all hit the same 16-byte bank group.
+__device__ __forceinline__ int padx(int i) { return i + (i >> 3); }
+__host__ __device__ constexpr size_t fft_padded(size_t n) { return n + (n >> 3) + 1; }
+
+// multiply by exp(-2 pi i j / 2^(T+1)), j < 2^T: the rotations inside a radix-2^R butterfly
+template <int T> __device__ __forceinline__ double2 rot_fwd(double2 d, int j) {
+    constexpr double H = 0.70710678118654752440;
+    if (T == 0 || j == 0) return d;
+    if (T == 1) return make_double2(d.y, -d.x);                                   // -i
+    if (j == 1) return make_double2((d.x + d.y) * H, (d.y - d.x) * H);             // exp(-i pi/4)
+    if (j == 2) return make_double2(d.y, -d.x);
+    return make_double2((d.y - d.x) * H, -(d.x + d.y) * H);                        // exp(-3 i pi/4)
+}
+template <int T> __device__ __forceinline__ double2 rot_inv(double2 d, int j) {   // the conjugate rotations
+    constexpr double H = 0.70710678118654752440;
+    if (T == 0 || j == 0) return d;
+    if (T == 1) return make_double2(-d.y, d.x);                                   // +i
+    if (j == 1) return make_double2((d.x - d.y) * H, (d.x + d.y) * H);
+    if (j == 2) return make_double2(-d.y, d.x);
+    return make_double2(-(d.x + d.y) * H, (d.x - d.y) * H);
+}
+
+// R radix-2 stages on the 2^R elements a thread holds in registers (halves s * 2^(R-1) .. s).  The twiddle of the pair
+// (m, m + 2^t) in stage t is b^(2^(R-1-t)) * exp(-2 pi i (m mod 2^t) / 2^(t+1)), b = W_L^(lowpart * L / (2 hmax)):
+// ONE table look-up per thread and pass, the rest are squarings and fixed rotations.
+template <int R, int T> struct DifStage {
+    static __device__ __forceinline__ void run(double2 (&v)[1 << R], double2 bt) {
+#pragma unroll
+        for (int m = 0; m < (1 << R); m++) {
+            if (m & (1 << T)) continue;
+            const double2 a = v[m], c = v[m + (1 << T)];
+            v[m] = make_double2(a.x + c.x, a.y + c.y);
+            v[m + (1 << T)] = rot_fwd<T>(cmul(make_double2(a.x - c.x, a.y - c.y), bt), m & ((1 << T) - 1));
+        }
+        DifStage<R, T - 1>::run(v, cmul(bt, bt));
+    }
+};
+template <int R> struct DifStage<R, -1> { static __device__ __forceinline__ void run(double2 (&)[1 << R], double2) {} };
+
+template <int R, int T> struct DitStage {       // stages t = 0 .. R-1; bpow[t] = b^(2^(R-1-t))
+    static __device__ __forceinline__ void run(double2 (&v)[1 << R], const double2 (&bpow)[R]) {
+#pragma unroll
+        for (int m = 0; m < (1 << R); m++) {
+            if (m & (1 << T)) continue;
+            const double2 a = v[m];
+            const double2 c = cmulc(rot_inv<T>(v[m + (1 << T)], m & ((1 << T) - 1)), bpow[T]);
+            v[m] = make_double2(a.x + c.x, a.y + c.y);
+            v[m + (1 << T)] = make_double2(a.x - c.x, a.y - c.y);
+        }
+        DitStage<R, T + 1>::run(v, bpow);
+    }
+};
+template <int R> struct DitStage<R, R> { static __device__ __forceinline__ void run(double2 (&)[1 << R], const double2 (&)[R]) {} };
+
+// one pass of R stages over `rows` rows of length L; ltop = log2 of the largest half of the pass.
+// FWD: decimation in frequency (halves descending); otherwise the mirrored decimation in time with conjugated twiddles.
+// MULB (inverse passes only): the elements are multiplied by bhat as they are loaded (the convolution product).
+template <int R, bool FWD, bool MULB>
+__device__ __forceinline__ void fft_pass(double2 *w, int rows, int L, int logL, int ltop, const double2 *__restrict__ tw,
+                                         const double2 *__restrict__ bhat) {
+    const int ls = ltop - R + 1, s = 1 << ls;
+    const int gpr = L >> R, ng = rows * gpr;
+    for (int g = threadIdx.x; g < ng; g += blockDim.x) {
+        const int row = g >> (logL - R), gg = g & (gpr - 1);
+        const int low = gg & (s - 1);
+        const int off = ((gg >> ls) << (ls + R)) + low, base = row * L + off;
+        double2 v[1 << R];
+#pragma unroll
+        for (int m = 0; m < (1 << R); m++) {
+            v[m] = w[padx(base + m * s)];
+            if (MULB) v[m] = cmul(v[m], bhat[off + m * s]);
+        }
+        const double2 b = tw[low << (logL - 1 - ltop)];
+        if (FWD) {
+            DifStage<R, R - 1>::run(v, b);
+        } else {
+            double2 bpow[R];
+            bpow[R - 1] = b;
+#pragma unroll
+            for (int t = R - 2; t >= 0; t--) bpow[t] = cmul(bpow[t + 1], bpow[t + 1]);
+            DitStage<R, 0>::run(v, bpow);
+        }
+#pragma unroll
+        for (int m = 0; m < (1 << R); m++) w[padx(base + m * s)] = v[m];
+    }
+    __syncthreads();
+}
+
+// forward transform of every row (natural order in, bit-reversed out): passes of 3 bits, the remainder last
+__device__ __forceinline__ void fft_dif(double2 *w, int rows, int L, int logL, const double2 *__restrict__ tw) {
+    int ltop = logL - 1;
+    for (; ltop >= 2; ltop -= 3) fft_pass<3, true, false>(w, rows, L, logL, ltop, tw, nullptr);
+    if (ltop == 1) fft_pass<2, true, false>(w, rows, L, logL, ltop, tw, nullptr);
+    else if (ltop == 0) fft_pass<1, true, false>(w, rows, L, logL, ltop, tw, nullptr);
+}
+// its mirror image (bit-reversed in, natural out; un-normalised inverse), the product with bhat folded into the first pass
+__device__ __forceinline__ void fft_dit_inv_mulb(double2 *w, int rows, int L, int logL, const double2 *__restrict__ tw,
+                                                 const double2 *__restrict__ bhat) {
+    const int rem = logL % 3;                  // the forward transform ended with a pass of `rem` bits: start with it
+    int ltop;
+    if (rem == 2) { fft_pass<2, false, true>(w, rows, L, logL, 1, tw, bhat); ltop = 4; }
+    else if (rem == 1) { fft_pass<1, false, true>(w, rows, L, logL, 0, tw, bhat); ltop = 3; }
+    else { fft_pass<3, false, true>(w, rows, L, logL, 2, tw, bhat); ltop = 5; }
+    for (; ltop <= logL - 1; ltop += 3) fft_pass<3, false, false>(w, rows, L, logL, ltop, tw, nullptr);
+}
+
+// One length-M DFT in shared memory.  load(n) yields input element n, store(k, v) receives output element k; with
+// INVERSE the un-normalised inverse transform is computed (conjugate in, conjugate out).  `work` holds P * L complex.
+template <bool INVERSE, class Load, class Store>
+__device__ __forceinline__ void blue_transform(const BluePlanDev &pl, double2 *work, Load load, Store store) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int PL = pl.P * pl.L;
+    for (int i = tid; i < PL; i += nt)
+        if ((i & (pl.L - 1)) >= pl.Q) work[padx(i)] = make_double2(0.0, 0.0);       // zero padding of every row
+    for (int n = tid; n < pl.M; n += nt) {
+        double2 v = load(n);
+        if (INVERSE) v.y = -v.y;
+        const int pos = pl.in_pos[n];
+        work[padx(pos)] = cmul(v, pl.chirp[pos & (pl.L - 1)]);
+    }
+    __syncthreads();
+    fft_dif(work, pl.P, pl.L, pl.logL, pl.tw);
+    fft_dit_inv_mulb(work, pl.P, pl.L, pl.logL, pl.tw, pl.bhat);
+    // length-P transforms across the rows, one output element per (k1, k2)
+    const int PQ = pl.P * pl.Q;
+    for (int o = tid; o < PQ; o += nt) {
+        const int k1 = o / pl.Q, k2 = o - k1 * pl.Q;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int n1 = 0; n1 < pl.P; n1++) {
+            const double2 y = work[padx(n1 * pl.L + k2)], wv = pl.wp[k1 * pl.P + n1];
+            acc.x += fma(y.x, wv.x, -y.y * wv.y);
+            acc.y += fma(y.x, wv.y, y.y * wv.x);
+        }
+        double2 v = cmul(acc, pl.chirp[k2]);
+        if (INVERSE) v.y = -v.y;
+        store(pl.out_idx[o], v);
+    }
+}
+
+// bhat = DIF(b) / L, computed with the very routine that will consume it (so the order matches by construction)
+__global__ void __launch_bounds__(FFT_THREADS)
+k_blue_bhat(const double2 *__restrict__ b, double2 *__restrict__ bhat, int L, int logL, const double2 *__restrict__ tw) {
+    extern __shared__ __align__(16) unsigned char fft_smem[];
+    double2 *w = reinterpret_cast<double2 *>(fft_smem);
+    for (int i = threadIdx.x; i < L; i += blockDim.x) w[padx(i)] = b[i];
+    __syncthreads();
+    fft_dif(w, 1, L, logL, tw);
+    const double s = 1.0 / (double)L;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) bhat[i] = make_double2(w[padx(i)].x * s, w[padx(i)].y * s);
+}
+
+// rows forward: real rows 2a, 2a+1 of x[nrows][M] -> half spectra T[2a][0..Nh), T[2a+1][0..Nh)
+__global__ void __launch_bounds__(FFT_THREADS)
+k_fft_rows_fwd(BluePlanDev pl, const double *__restrict__ x, double2 *__restrict__ T, int nrows) {
+    extern __shared__ __align__(16) unsigned char fft_smem[];
+    double2 *work = reinterpret_cast<double2 *>(fft_smem);
+    // the packed spectrum Z[k] goes to the columns [Q, 2Q) of the work rows (free once the convolution is done; L >= 2Q):
+    // element k sits in row k / Q, column Q + k % Q
+    const int M = pl.M, Nh = M / 2 + 1, Q = pl.Q, L = pl.L;
+    auto zpos = [Q, L](int k) { const int r = k / Q; return padx(r * L + Q + (k - r * Q)); };
+    const int ra = 2 * blockIdx.x, rb = ra + 1;
+    const double *xa = x + (size_t)ra * M, *xb = x + (size_t)rb * M;
+    const bool has_b = rb < nrows;
+    blue_transform<false>(pl, work,
+                          [&](int n) { return make_double2(xa[n], has_b ? xb[n] : 0.0); },
+                          [&](int k, double2 v) { work[zpos(k)] = v; });
+    __syncthreads();
+    for (int k = threadIdx.x; k < Nh; k += blockDim.x) {
+        const double2 zk = work[zpos(k)], zm = work[zpos(k == 0 ? 0 : M - k)];
+        // A = (Z[k] + conj Z[M-k]) / 2,  B = (Z[k] - conj Z[M-k]) / (2i)
+        T[(size_t)ra * Nh + k] = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+        if (has_b) T[(size_t)rb * Nh + k] = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
+    }
+}
+
+// columns, in place on T[M][Nh]: column blockIdx.x
+template <bool INVERSE>
+__global__ void __launch_bounds__(FFT_THREADS)
+k_fft_cols(BluePlanDev pl, double2 *__restrict__ T, int Nh) {
+    extern __shared__ __align__(16) unsigned char fft_smem[];
+    double2 *work = reinterpret_cast<double2 *>(fft_smem);
+    double2 *col = T + blockIdx.x;
+    blue_transform<INVERSE>(pl, work,
+                            [&](int n) { return col[(size_t)n * Nh]; },
+                            [&](int k, double2 v) { col[(size_t)k * Nh] = v; });      // every load is done before the first store
+}
+
+// rows inverse: Hermitian half rows U[2a], U[2a+1] -> real rows 2a, 2a+1 of out[nrows][M] (un-normalised, like Z2D)
+__global__ void __launch_bounds__(FFT_THREADS)
+k_fft_rows_inv(BluePlanDev pl, const double2 *__restrict__ U, double *__restrict__ out, int nrows) {
+    extern __shared__ __align__(16) unsigned char fft_smem[];
+    double2 *work = reinterpret_cast<double2 *>(fft_smem);
+    const int M = pl.M, Nh = M / 2 + 1;
+    const int ra = 2 * blockIdx.x, rb = ra + 1;
+    const bool has_b = rb < nrows;
+    const double2 *ua = U + (size_t)ra * Nh, *ub = U + (size_t)rb * Nh;
+    double *oa = out + (size_t)ra * M, *ob = out + (size_t)rb * M;
+    blue_transform<true>(pl, work,
+                         [&](int k) {
+                             // Z[k] = A[k] + i B[k]; beyond the stored half the rows are Hermitian: conj of the mirror
+                             const bool lo = k < Nh;
+                             const int q = lo ? k : M - k;
+                             double2 a = ua[q], b = has_b ? ub[q] : make_double2(0.0, 0.0);
+                             if (!lo) { a.y = -a.y; b.y = -b.y; }
+                             if (q == 0 || 2 * q == M) { a.y = 0.0; b.y = 0.0; }     // self-conjugate bins are real (a c2r transform ignores their imaginary part)
+                             return make_double2(a.x - b.y, a.y + b.x);
+                         },
+                         [&](int n, double2 v) { oa[n] = v.x; if (has_b) ob[n] = v.y; });
+}
+
+}  // namespace picsp

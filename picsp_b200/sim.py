@@ -19,6 +19,7 @@ ION, ELECTRON = 0, 1
 GRID_IDS = {"den_i": 0, "den_e": 1, "rho": 2, "phi": 3, "efx": 4, "efy": 5}
 PHASES = ("deposit", "rho", "allreduce", "solve", "ef", "push", "sort", "step", "push_ions", "push_electrons")
 FLAG_CLEAR_DENSITY, FLAG_NO_SORT, FLAG_NO_FUSE, FLAG_SOR_SINGLE_CTA, FLAG_SEPARATE_SORT, FLAG_NO_GRAPH, FLAG_WALLS, FLAG_NCCL_ONLY = 1, 2, 4, 8, 16, 32, 64, 128
+FLAG_CUFFT_ONLY, FLAG_OWN_FFT = 256, 512
 
 _dp = C.POINTER(C.c_double)
 
