@@ -220,13 +220,17 @@ def workload_config(args, n_local):
                       f"total; BASELINE.json configs[2] as an EXTENSION WITHOUT REFERENCE SEMANTICS (the reference is periodic-only)")),
         "load": args.load,
         "cells": args.cells, "particles_total": int(args.particles),
-        "solver": "red-black SOR, Dirichlet walls (k_rb_sor, one cooperative launch)" if bounded else "spectral (cuFFT D2Z/Z2D)",
+        "solver": "red-black SOR, Dirichlet walls (k_rb_sor, one cooperative launch)" if bounded else
+                  {"own": "spectral (the library's own shared-memory DFT: prime-factor split + Bluestein, fft_kernels.cuh)",
+                   "cufft": "spectral (cuFFT D2Z/Z2D)"}.get(getattr(args, "spectral_engine", "cufft"), "spectral"),
         "sharding": f"particles by index range over {args.gpus} rank(s), grid replicated, the partial rho summed once per step "
                     f"({getattr(args, 'rho_reduction', 'n/a')})",
         "l2_policy": "inputs exceed L2 (particle state per rank >> 126 MB); no explicit flush",
     }
     if n_local is not None:
         cfg["particles_per_rank_per_species"] = int(n_local)
+    if getattr(args, "store_parts", 1) > 1:
+        cfg["store_parts_per_species"] = args.store_parts      # picsp_params::parts resolved (one shared spare buffer set)
     return cfg
 
 
@@ -307,6 +311,8 @@ def main_ours(args, rank, world, local_rank):
         return sim
 
     sim = make_sim()
+    args.spectral_engine = sim.spectral_engine()
+    args.store_parts = sim.parts()
     args.rho_reduction = ("single rank: none" if world == 1 else
                           ("own reduce-scatter + all-gather kernel over NVLink peer memory (CUDA IPC)" if sim.comm_peer_reduction() else "ncclAllReduce"))
     sim.bootstrap()

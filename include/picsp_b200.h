@@ -223,6 +223,9 @@ enum {
 int picsp_profile_enable(picsp_ctx *ctx, int on);                       /* CUDA events around every phase on the library's stream */
 int picsp_profile_get(picsp_ctx *ctx, int phase, double *ms, int64_t *calls); /* synchronises; accumulates since last reset */
 int picsp_profile_reset(picsp_ctx *ctx);
+/* Transform behind picsp_solve_spectral: 1 = the library's own shared-memory DFT (node counts with a prime factor > 127 such
+ * as 2049 = 3 * 683, and small grids), 0 = cuFFT. */
+int picsp_spectral_engine(picsp_ctx *ctx, int *own);
 /* Parts every species' store is split into (picsp_params::parts resolved; 1 = the whole species in one store). */
 int picsp_parts(picsp_ctx *ctx, int *parts);
 int picsp_kernel_launches(picsp_ctx *ctx, int64_t *n);                  /* number of this library's kernels launched so far */

@@ -490,6 +490,13 @@ void build_own_fft_plan(picsp_ctx *c, int which, int M) {
     f.smem[which] = fft_padded((size_t)P * L) * sizeof(double2);
 }
 
+// threads per transform: the radix-8 groups of a pass (P * L / 8) spread evenly, two or three per thread
+int fft_threads(const picsp_ctx *c, int which) {
+    if (const char *e = getenv("PICSP_FFT_THREADS")) return std::max(32, std::min(FFT_THREADS, atoi(e)));
+    const int ng = std::max(1, c->fft.P[which] * c->fft.L[which] / 8);
+    return (ng % 384 == 0) ? 384 : 256;          // measured at 2049^2: 128 / 192 / 256 / 384 / 512 threads -> 633 / 549 / 513 / 490 / 499 us
+}
+
 BluePlanDev own_fft_plan(const picsp_ctx *c, int which) {
     const picsp_ctx::OwnFft &f = c->fft;
     BluePlanDev pl;
@@ -505,7 +512,10 @@ void setup_own_fft(picsp_ctx *c) {
     const Geom &g = c->g;
     const int flags = c->prm.flags;
     if (flags & PICSP_FLAG_CUFFT_ONLY) return;
-    const bool wanted = (flags & PICSP_FLAG_OWN_FFT) || largest_prime_factor(g.nix) > 127 || largest_prime_factor(g.niy) > 127;
+    // ... and the small grids where cuFFT's launches cost more than the transform (65^2 .. 257^2 nodes: 1.2-1.5x, same file)
+    const int big = std::max(g.nix, g.niy);
+    const bool wanted = (flags & PICSP_FLAG_OWN_FFT) || largest_prime_factor(g.nix) > 127 || largest_prime_factor(g.niy) > 127 ||
+                        (big >= 65 && big <= 257);
     if (!wanted) return;
     int P, Q, L, logL;
     if (!choose_fft_split(g.niy, &P, &Q, &L, &logL) || !choose_fft_split(g.nix, &P, &Q, &L, &logL)) {
@@ -530,12 +540,12 @@ void op_solve_spectral(picsp_ctx *c) {
         // D2Z = rows forward (two real rows per transform) + columns forward; Z2D = columns inverse + rows inverse
         const BluePlanDev py = own_fft_plan(c, 0), px = own_fft_plan(c, 1);
         double2 *rhok = reinterpret_cast<double2 *>(c->rhok), *phik = reinterpret_cast<double2 *>(c->phik);
-        PICSP_LAUNCH(c, k_fft_rows_fwd, (g.nix + 1) / 2, FFT_THREADS, c->fft.smem[0], py, c->rho, rhok, g.nix);
-        PICSP_LAUNCH(c, (k_fft_cols<false>), Nh, FFT_THREADS, c->fft.smem[1], px, rhok, Nh);
+        PICSP_LAUNCH(c, k_fft_rows_fwd, (g.nix + 1) / 2, fft_threads(c, 0), c->fft.smem[0], py, c->rho, rhok, g.nix);
+        PICSP_LAUNCH(c, (k_fft_cols<false>), Nh, fft_threads(c, 1), c->fft.smem[1], px, rhok, Nh);
         PICSP_LAUNCH(c, k_kspace_green, blocks_for((long long)g.nix * Nh, 256, c->num_sms * 8), 256, 0, c->rhok, c->phik,
                      g.nix, g.niy, g.xl, g.yl);
-        PICSP_LAUNCH(c, (k_fft_cols<true>), Nh, FFT_THREADS, c->fft.smem[1], px, phik, Nh);
-        PICSP_LAUNCH(c, k_fft_rows_inv, (g.nix + 1) / 2, FFT_THREADS, c->fft.smem[0], py, (const double2 *)phik, c->phi, g.nix);
+        PICSP_LAUNCH(c, (k_fft_cols<true>), Nh, fft_threads(c, 1), c->fft.smem[1], px, phik, Nh);
+        PICSP_LAUNCH(c, k_fft_rows_inv, (g.nix + 1) / 2, fft_threads(c, 0), c->fft.smem[0], py, (const double2 *)phik, c->phi, g.nix);
         return;
     }
     PICSP_REQUIRE(c->have_plans, PICSP_ERR_STATE, "cuFFT plans missing");
@@ -1686,6 +1696,13 @@ int picsp_profile_reset(picsp_ctx *c) {
     PICSP_CUDA(cudaStreamSynchronize(c->stream));
     profile_collect(c);
     for (auto &t : c->timers) { t.ms = 0.0; t.calls = 0; }
+    PICSP_API_END
+}
+int picsp_spectral_engine(picsp_ctx *c, int *own) {
+    PICSP_API_BEGIN
+    check_ctx(c);
+    PICSP_REQUIRE(own != nullptr, PICSP_ERR_INVALID, "null output");
+    *own = c->fft.on ? 1 : 0;
     PICSP_API_END
 }
 int picsp_parts(picsp_ctx *c, int *parts) {

@@ -26,7 +26,7 @@
 
 namespace picsp {
 
-constexpr int FFT_THREADS = 256;
+constexpr int FFT_THREADS = 512;       // launch bound; the launch uses fft_threads() <= this
 
 struct BluePlanDev {
     int M, P, Q, L, logL;

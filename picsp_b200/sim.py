@@ -213,6 +213,12 @@ class Simulation:
             out[name] = (ms.value, calls.value)
         return out
 
+    def spectral_engine(self):
+        """'own' (shared-memory DFT of fft_kernels.cuh) or 'cufft'."""
+        n = C.c_int()
+        check(self.L.picsp_spectral_engine(self.ctx, C.byref(n)))
+        return "own" if n.value else "cufft"
+
     def parts(self):
         n = C.c_int()
         check(self.L.picsp_parts(self.ctx, C.byref(n)))
