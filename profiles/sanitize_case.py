@@ -40,3 +40,21 @@ with Simulation(Params(40, 56, nm["dx"], nm["dt"], nm["mass_i"], 20000, 20000, s
     sim.fill_synthetic(ION, 20000, seed=5, vth=nm["vth_i"]); sim.fill_synthetic(ELECTRON, 20000, seed=6, vth=5.0)
     sim.bootstrap(); sim.step(5)
     print("walls", sim.solve_status(), sim.repush_count(ELECTRON), int(np.isnan(sim.get_species(ELECTRON)[0]).sum()))
+# round 2, second session: bank order inside the chunks for both species (k_bank_order, after every re-binning), a
+# species split into 3 parts sharing one spare (uneven last part; upload, re-binning mover, stand-alone re-sort, dumps),
+# the library's own DFT (prime-factor split 3 x 11 / plain Bluestein 49 / even length 48 / two different plans)
+for numx, numy, n, parts, flags in ((48, 40, 30001, 1, 0), (64, 56, 20011, 3, 0), (40, 40, 15001, 3, 16)):
+    with Simulation(Params(numx, numy, nm["dx"], nm["dt"], nm["mass_i"], n, n, solverType=1, flags=flags, parts=parts)) as sim:
+        sim.set_sort_period(ELECTRON, 2); sim.set_sort_period(ION, 3)
+        sim.set_bank_order(ION, 1); sim.set_bank_order(ELECTRON, 1)
+        for s, vth in ((ION, nm["vth_i"]), (ELECTRON, 2.0)):
+            sim.set_species(s, rng.random(n) * numx * nm["dx"], rng.random(n) * numy * nm["dx"],
+                            vth * rng.standard_normal(n), vth * rng.standard_normal(n))
+        sim.bootstrap(); sim.step(7)
+        d = sim.dump()
+        print("r2b", numx, parts, flags, sim.parts(), float(d["ke"][1]), float(sim.get_species_rows(ELECTRON)[:, 0].max()), sim.computeKE(ION))
+for numx, numy in ((32, 32), (48, 48), (47, 47), (64, 130)):
+    with Simulation(Params(numx, numy, nm["dx"], nm["dt"], nm["mass_i"], 5000, 5000, solverType=1, flags=512)) as sim:
+        sim.fill_synthetic(ION, 5000, seed=7, vth=nm["vth_i"]); sim.fill_synthetic(ELECTRON, 5000, seed=8, vth=1.0)
+        sim.bootstrap(); sim.step(2)
+        print("fft", numx, numy, sim.spectral_engine(), sim.delta_phi())
