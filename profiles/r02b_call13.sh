@@ -1,0 +1,1 @@
+timeout 900 python -m pytest tests/test_gpu_parts.py -x -q -m gpu 2>&1 | tail -5

@@ -37,8 +37,8 @@ def run(parts, solver, numx, n, flags=0, upload=None, steps=(9, 8)):
     return out
 
 
-@pytest.mark.parametrize("solver,numx,n,flags", [(1, 128, 300_001, 0), (2, 80, 150_000, 0), (1, 96, 200_000, 16)],
-                         ids=["spectral", "sor", "separate-sort"])
+@pytest.mark.parametrize("solver,numx,n,flags", [(1, 128, 300_001, 0), (2, 80, 150_000, 0), (1, 96, 200_000, 16), (1, 256, 1_500_001, 0)],
+                         ids=["spectral", "sor", "separate-sort", "two-pass-first-binning-own-fft"])
 def test_parts_do_not_change_the_result(solver, numx, n, flags):
     """1, 3 and 4 parts (uneven split: the last part is short), device loader, several re-binnings of both species
     through the shared spare (re-binning mover, or the stand-alone re-sort with flag 16)."""
