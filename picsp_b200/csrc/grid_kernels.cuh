@@ -292,6 +292,13 @@ __device__ __forceinline__ void sor_cp_async16(void *smem_dst, const double *gme
     const unsigned long long a = reinterpret_cast<unsigned long long>(gmem_elem) & ~15ull;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(a) : "memory");
 }
+// Operands that THIS SM alone writes during the sweep (old phi(i,j+1), old phi(i+1,j)) or nobody writes (rho) can go
+// through L1: 8-byte cp.async.ca, no pair selection afterwards.  (Operands another band produces this sweep — new
+// phi(i-1,.) for thread 0, new phi(1,.) for row nix-1 — must bypass L1, which could hold the line from before they
+// were written: those keep the 16-byte .cg form.)
+__device__ __forceinline__ void sor_cp_async8(double *smem_dst, const double *gmem_elem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_elem) : "memory");
+}
 __device__ __forceinline__ double sor_pick(const double2 &pair, const double *gmem_elem) {
     return (reinterpret_cast<unsigned long long>(gmem_elem) & 8ull) ? pair.y : pair.x;
 }
@@ -322,48 +329,58 @@ k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int 
     const bool up_from_global = (t == 0);   // previous band's last row (b > 0), or the i == 0 wrap (old values)
     int granted = (b == 0) ? niy : 0;       // columns of the previous band known to be complete (polling threads only)
 
-    // start the copies of column jj's operands into ring slot k (one cp.async group per call)
-    auto fetch = [&](int k, int jj) {
-        if (active && jj >= 0 && jj < niy) {
+    // start the copies of the next column's operands into ring slot k (one cp.async group per call).  Calls come in
+    // column order (jf = -t, -t+1, ...), so the operand addresses are running pointers, not recomputed indices.
+    int jf = -t;
+    const double *pf_right = row + (jf + 1), *pf_q = row_q + jf, *pf_rho = rrho + jf, *pf_p = row_p + jf;
+    auto fetch = [&](int k) {
+        if (active && jf >= 0 && jf < niy) {
             // Threads that read values ANOTHER band produces this sweep — thread 0 (new phi(i-1,.)) and the row
             // nix-1 (new phi(1,.), implied by the previous band's progress) — wait for the previous band first,
             // (progress is published 16 columns at a time; this also covers the fetches issued before the first barrier).
-            if ((up_from_global || q_is_new) && b > 0 && jj >= granted) {
-                const int want = min(jj + 1, niy);
+            if ((up_from_global || q_is_new) && b > 0 && jf >= granted) {
+                const int want = min(jf + 1, niy);
                 while ((granted = *(volatile int *)&progress[b - 1]) < want) { }
                 __threadfence();
             }
-            if (jj < niy - 1) sor_cp_async16(&s_ring[k][0][t], &row[jj + 1]);      // old phi(i,jj+1); jj == niy-1 uses saved_col1
-            if (q_prefetch_ok) sor_cp_async16(&s_ring[k][1][t], &row_q[jj]);       // old phi(i+1,jj) | new phi(1,jj)
-            sor_cp_async16(&s_ring[k][2][t], &rrho[jj]);
-            if (up_from_global) sor_cp_async16(&s_ring[k][3][t], &row_p[jj]);
+            if (jf < niy - 1) sor_cp_async8(&s_ring[k][0][t].x, pf_right);        // old phi(i,jf+1); jf == niy-1 uses saved_col1
+            if (q_prefetch_ok) {
+                if (q_is_new) sor_cp_async16(&s_ring[k][1][t], pf_q);              // new phi(1,jf): written by another SM, L2 only
+                else sor_cp_async8(&s_ring[k][1][t].x, pf_q);                      // old phi(i+1,jf)
+            }
+            sor_cp_async8(&s_ring[k][2][t].x, pf_rho);
+            if (up_from_global) sor_cp_async16(&s_ring[k][3][t], pf_p);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        jf++; pf_right++; pf_q++; pf_rho++; pf_p++;
     };
 
     double left = 0.0, center = 0.0, saved_col1 = 0.0;
     if (active) { left = __ldcg(&row[niy - 2]); center = __ldcg(&row[0]); }   // r wrap for j == 0 (old), phi_old(i,0)
 #pragma unroll
-    for (int k = 0; k < D; k++) fetch(k, k - t);
+    for (int k = 0; k < D; k++) fetch(k);
 
     const int nsteps = niy + rows_here - 1;
+    int j = -t;                                                   // column of this step
+    double *pout = phi + ((long long)(active ? i : 0) * niy + j);    // &phi[i][j], advanced with j
     for (int s0 = 0; s0 < nsteps; s0 += D) {
 #pragma unroll
         for (int k = 0; k < D; k++) {
             const int s = s0 + k;
             if (s < nsteps) {               // uniform across the CTA
-                const int j = s - t;
                 const bool work = active && j >= 0 && j < niy;
                 asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");   // the group that filled slot k has landed
                 if (work) {
-                    const double right = (j == niy - 1) ? saved_col1 : sor_pick(s_ring[k][0][t], &row[j + 1]);
-                    const double down = q_prefetch_ok ? sor_pick(s_ring[k][1][t], &row_q[j]) : __ldcg(&row_q[j]);
-                    const double rh = sor_pick(s_ring[k][2][t], &rrho[j]);
-                    const double up = up_from_global ? sor_pick(s_ring[k][3][t], &row_p[j])
+                    const double right = (j == niy - 1) ? saved_col1 : s_ring[k][0][t].x;
+                    // (the fetch pointers are D columns ahead of j)
+                    const double down = q_prefetch_ok ? (q_is_new ? sor_pick(s_ring[k][1][t], pf_q - D) : s_ring[k][1][t].x)
+                                                      : __ldcg(&row_q[j]);
+                    const double rh = s_ring[k][2][t].x;
+                    const double up = up_from_global ? sor_pick(s_ring[k][3][t], pf_p - D)
                                                      : s_new[(s + 1) & 1][t - 1];   // written at step s-1 by thread t-1
                     const double g = coef * (sor_div(up + down, dx2, rdx2) + sor_div(left + right, dy2, rdy2) + (rh / eps));
                     const double v = center + 1.4 * (g - center);
-                    __stcg(&phi[(long long)i * niy + j], v);
+                    __stcg(pout, v);
                     s_new[s & 1][t] = v;
                     if (j == 1) saved_col1 = v;
                     left = v;
@@ -373,7 +390,8 @@ k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int 
                         *(volatile int *)&progress[b] = j + 1;
                     }
                 }
-                fetch(k, j + D);            // refill this slot for step s + D
+                fetch(k);                   // refill this slot for step s + D
+                j++; pout++;
                 __syncthreads();
             }
         }
