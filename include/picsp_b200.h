@@ -43,7 +43,10 @@ enum {
     PICSP_ERR_CUFFT = -4,
     PICSP_ERR_NCCL = -5,
     PICSP_ERR_STATE = -6,       /* call sequence error (e.g. download before upload) */
-    PICSP_ERR_DISPLACEMENT = -7,/* a particle moved >= one particle tile in one step */
+    PICSP_ERR_DISPLACEMENT = -7,/* so many particles moved more than one particle tile (16 cells) in ONE step that the fixed-point
+                                 * deposit could overflow (>= 2^(62 - fraction bits): 2048 for the sparsest load, millions for a
+                                 * dense one), or a particle needed more than 64 consecutive re-pushes.  Fewer fast particles are
+                                 * handled like any other, as in the reference. */
     PICSP_ERR_NOT_CONVERGED = -8/* SOR hit the reference's 200000-sweep cap (main.cpp:955) */
 };
 

@@ -46,7 +46,9 @@ PushConst push_const(const picsp_ctx *c, int s) {
     pc.xl = g.xl; pc.yl = g.yl;
     pc.nix = g.nix; pc.niy = g.niy; pc.ntx = g.ntx; pc.nty = g.nty;
     pc.nn = g.nn; pc.guard = g.guard;
-    pc.walls = (c->prm.flags & PICSP_FLAG_WALLS) ? 1 : 0; pc.pad_ = 0;
+    pc.walls = (c->prm.flags & PICSP_FLAG_WALLS) ? 1 : 0;
+    pc.far_shift = 0;
+    while ((1 << pc.far_shift) < c->nparts) pc.far_shift++;
     return pc;
 }
 
@@ -100,7 +102,8 @@ void check_device_error(picsp_ctx *c) {
             throw Error(PICSP_ERR_STATE, "internal: a re-binning mover overflowed a bin (histogram and bin function disagree)");
         if (v & ERR_BIT_RUNAWAY)
             throw Error(PICSP_ERR_DISPLACEMENT, "a particle needed more than 64 consecutive re-pushes (non-finite or absurd velocity)");
-        throw Error(PICSP_ERR_DISPLACEMENT, "a particle moved by more than one particle tile (16 cells) in a single step");
+        throw Error(PICSP_ERR_DISPLACEMENT, "too many particles moved by more than one particle tile (16 cells) in a single step: "
+                                            "the fixed-point deposit could overflow (see far_mover() in particle_kernels.cuh)");
     }
 }
 
@@ -347,7 +350,7 @@ void ensure_acc(picsp_ctx *c, int s) {
     });
     compute_frac(c, s);
     for_parts(c, s, [&](Species &sp) {
-        PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
+        PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 4 * sizeof(unsigned long long), c->stream));
         if (sp.n > 0) {
             if (tiled(c))
                 launch_tile_mover<1>(c, sp);
@@ -639,7 +642,7 @@ void op_push(picsp_ctx *c, int s) {
         {
             PhaseScope ph(c, PICSP_PHASE_PUSH);
             PhaseScope phs(c, s == 0 ? PICSP_PHASE_PUSH_IONS : PICSP_PHASE_PUSH_ELECTRONS);
-            PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
+            PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 4 * sizeof(unsigned long long), c->stream));
             if (fuse || tile) PICSP_CUDA(cudaMemsetAsync(sp.hist_next, 0, sizeof(unsigned int) * nt, c->stream));
             if (sp.n > 0) {
                 if (tile) {
@@ -899,7 +902,7 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
                     sp.den = p0.den; sp.acc = p0.acc; sp.frac = p0.frac; sp.frac_scratch = p0.frac_scratch;
                 }
                 dalloc(&sp.hist, ntl); dalloc(&sp.hist_next, ntl);
-                dalloc(&sp.counters, 2);
+                dalloc(&sp.counters, 4);
                 sp.sort_period = (s == 0) ? 96 : 8;     // steps between re-binnings (ions barely move; electrons: profiles/r01_sweeps.md)
                 sp.cell_period = 0;                     // steps between cell orderings inside the bins: off (profiles/r02_mover_aggregation.md)
                 sp.steps_since_cellsort = sp.cell_period;   // the first push after a load orders it
@@ -910,7 +913,7 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
                 dalloc(&sp.nchunks, 1);
                 dalloc(&sp.cursor, ntl);
                 PICSP_CUDA(cudaMemsetAsync(sp.nchunks, 0, sizeof(int), c->stream));
-                PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 2 * sizeof(unsigned long long), c->stream));
+                PICSP_CUDA(cudaMemsetAsync(sp.counters, 0, 4 * sizeof(unsigned long long), c->stream));
             }
             if (nparts > 1) dalloc(&c->hist_sum[s], ntl);
         }

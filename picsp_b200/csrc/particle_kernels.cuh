@@ -22,7 +22,7 @@ struct PushConst {
     int ntx, nty;
     long long nn, guard;
     int walls;        // PICSP_FLAG_WALLS (extension, no reference semantics): a particle that leaves the box is absorbed
-    int pad_;
+    int far_shift;    // log2 (rounded up) of the stores that deposit into this species' accumulator grid (parts): see far_mover()
 };
 
 // XtoL / YtoL, src/main.cpp:643-652: true division, x0 = y0 = 0.
@@ -223,6 +223,20 @@ __global__ void k_deposit(const double *__restrict__ x, const double *__restrict
 // pushed AGAIN from its wrapped position, until a push ends inside the box (Q4).
 // ---------------------------------------------------------------------------
 constexpr int ERR_BIT_DISPLACEMENT = 1;
+
+// A particle that moves MORE THAN ONE particle tile in a step ("far mover") is legal in the reference and is handled
+// here too (global gather, global deposit, individual slot at a re-binning); but the fixed-point scale of the fused
+// deposit (2^frac with 2^frac * P < 2^62, P = the largest 5 x 5-tile population before the push) only bounds what the
+// particles of a node's OWN neighbourhood can add to it.  Far movers may land anywhere, so they are counted
+// (counters[2]): while fewer than 2^(62 - frac) of them exist in one launch — 2048 for the sparsest load, millions
+// for a dense one — even all of them on one node keep its sum below 2^63.  Only beyond that does the launch raise
+// PICSP_ERR_DISPLACEMENT (an absurd population: a plasma that far out of its CFL range has long stopped meaning anything).
+__device__ __forceinline__ void far_mover(unsigned long long *__restrict__ counters, const int *__restrict__ frac, int far_shift,
+                                          int *__restrict__ err) {
+    const unsigned long long seen = atomicAdd(&counters[2], 1ull) + 1ull;
+    const int room = 62 - frac[0] - far_shift;
+    if (room < 0 || seen >= (1ull << room)) atomicOr(err, ERR_BIT_DISPLACEMENT);
+}
 constexpr int ERR_BIT_RUNAWAY = 2;
 constexpr int ERR_BIT_REBIN = 4;
 
@@ -259,7 +273,7 @@ k_push(double *__restrict__ x, double *__restrict__ y, double *__restrict__ vx, 
             const int t1 = tile_of(px, py, c);
             int dtx = abs(t1 / c.nty - t0 / c.nty), dty = abs(t1 % c.nty - t0 % c.nty);
             dtx = min(dtx, c.ntx - dtx); dty = min(dty, c.nty - dty);
-            if (dtx > 1 || dty > 1) atomicOr(err, ERR_BIT_DISPLACEMENT);
+            if (dtx > 1 || dty > 1) far_mover(counters, frac, c.far_shift, err);
             atomicAdd(&hist_next[t1], 1u);
             scatter_fixed(acc, c, px, py, scale);
         }

@@ -1084,13 +1084,13 @@ k_tile_mover(const __grid_constant__ CUtensorMap tmapE, double *__restrict__ x, 
                     else
                         atomicAdd(&hist_next[ux * c.nty + uy], 1u);
                 }
-                // the fixed-point scale assumes no particle moves more than one tile in ONE step
+                // the fixed-point scale bounds the particles that move at most one tile in ONE step; the others are counted
                 const int ox = oi >= 0 ? min((int)((unsigned)oi / TILE), tc.ntx1) : 0;
                 const int oy = oi >= 0 ? min((int)((unsigned)oj / TILE), tc.nty1) : 0;
                 if ((ox != ux || oy != uy) && !(c.walls && ci < 0)) {        // an absorbed particle is filed under bin 0: not a displacement
                     int ax = abs(ux - ox), ay = abs(uy - oy);
                     ax = min(ax, c.ntx - ax); ay = min(ay, c.nty - ay);
-                    if (ax > 1 || ay > 1) atomicOr(err, ERR_BIT_DISPLACEMENT);
+                    if (MODE != 2 && (ax > 1 || ay > 1)) far_mover(counters, frac, c.far_shift, err);   // (MODE 2 deposits later, from the histogram of the positions it finds)
                 }
             }
         }

@@ -561,20 +561,49 @@ def test_empty_species_and_single_particle():
 
 
 def test_displacement_guard_reports_an_error():
-    """The fixed-point scale assumes no particle crosses more than one 16-cell tile per step; a violation is not
-    silently wrong, it surfaces as PICSP_ERR_DISPLACEMENT at the next synchronising call."""
+    """The fixed-point scale of the fused deposit bounds the particles that cross at most one 16-cell tile per step; the
+    ones that cross more are counted, and only when there are so many of them that a node could overflow (here
+    2^(62 - 49) = 8192 of 20000) does the launch report PICSP_ERR_DISPLACEMENT at the next synchronising call."""
     nm = normalise()
-    numx, n = 128, 1000
+    numx, n = 128, 20000
     rng = np.random.default_rng(2)
     xl = numx * nm["dx"]
     x, y = rng.random(n) * xl, rng.random(n) * xl
-    vx = np.zeros(n); vx[0] = 40 * nm["dx"] / nm["dt"]                 # 40 cells in one step
+    vx = np.zeros(n); vx[:12000] = 40 * nm["dx"] / nm["dt"]            # 40 cells in one step
     with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n)) as sim:
         sim.set_species(ION, x, y, np.zeros(n), np.zeros(n)); sim.set_species(ELECTRON, x, y, vx, np.zeros(n))
         sim.bootstrap(); sim.step(1)
         with pytest.raises(picsp_b200.PicspError) as ei:
             sim.sync()
         assert ei.value.code == -7
+
+
+@pytest.mark.parametrize("flags", [0, 2, 4], ids=["tiled-fused", "unsorted", "tiled-unfused"])
+def test_fast_particles_are_handled_like_in_the_reference(flags):
+    """A few particles that cross SEVERAL tiles per step (40 and 70 cells, one of them through the periodic boundary): the
+    reference has no speed limit, and neither has the mover — global gather, global deposit, individual slots at the
+    re-binnings.  Four steps against the oracle."""
+    nm = normalise()
+    numx, n = 128, 30000
+    rng = np.random.default_rng(8)
+    xl = numx * nm["dx"]
+    x, y = rng.random(n) * xl, rng.random(n) * xl
+    vx = 0.3 * rng.standard_normal(n); vy = 0.3 * rng.standard_normal(n)
+    vx[:5] = 40 * nm["dx"] / nm["dt"]; vy[5:9] = -70 * nm["dx"] / nm["dt"]; x[0] = 0.95 * xl
+    o = Oracle(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, vth_i=nm["vth_i"], solver=1)
+    o.set_species(ION, x, y, np.zeros(n), np.zeros(n)); o.set_species(ELECTRON, x, y, vx, vy)
+    with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n, flags=flags)) as sim:
+        sim.set_sort_period(ELECTRON, 2)
+        sim.set_species(ION, x, y, np.zeros(n), np.zeros(n)); sim.set_species(ELECTRON, x, y, vx, vy)
+        o.bootstrap(); sim.bootstrap()
+        for st in range(4):
+            o.step(1); sim.step(1)
+            for name in GRIDS:
+                assert_grid_close(sim.grid(name), o.grid(name), sim.nix, sim.niy, 10 * RTOL, f"step{st}/{name}")
+            got, want = sim.get_species(ELECTRON), o.get_species(ELECTRON)
+            for k in range(4):
+                assert relerr(got[k], want[k]) <= 10 * RTOL
+        sim.sync()
 
 
 def test_error_codes():

@@ -219,11 +219,11 @@ def test_picsp_step_reports_a_violation_of_an_earlier_call():
     """A displacement violation is flagged on the device by the mover; the grid phase of the next step mirrors the flag
     into mapped host memory and the next picsp_step call returns PICSP_ERR_DISPLACEMENT without an explicit sync."""
     nm = normalise()
-    numx, n = 128, 1000
+    numx, n = 128, 20000
     rng = np.random.default_rng(2)
     xl = numx * nm["dx"]
     x, y = rng.random(n) * xl, rng.random(n) * xl
-    vx = np.zeros(n); vx[0] = 40 * nm["dx"] / nm["dt"]
+    vx = np.zeros(n); vx[:12000] = 40 * nm["dx"] / nm["dt"]      # more far movers than the fixed-point deposit has room for
     with Simulation(Params(numx, numx, nm["dx"], nm["dt"], nm["mass_i"], n, n)) as sim:
         sim.set_species(ION, x, y, np.zeros(n), np.zeros(n)); sim.set_species(ELECTRON, x, y, vx, np.zeros(n))
         sim.bootstrap(); sim.step(1)
