@@ -221,7 +221,7 @@ def workload_config(args, n_local):
         "load": args.load,
         "cells": args.cells, "particles_total": int(args.particles),
         "solver": "red-black SOR, Dirichlet walls (k_rb_sor, one cooperative launch)" if bounded else
-                  {"own": "spectral (the library's own shared-memory DFT: prime-factor split + Bluestein, fft_kernels.cuh)",
+                  {"own": "spectral (the library's own shared-memory DFT, fft_kernels.cuh: prime-factor split into two direct factors, or Bluestein on 2^k)",
                    "cufft": "spectral (cuFFT D2Z/Z2D)"}.get(getattr(args, "spectral_engine", "cufft"), "spectral"),
         "sharding": f"particles by index range over {args.gpus} rank(s), grid replicated, the partial rho summed once per step "
                     f"({getattr(args, 'rho_reduction', 'n/a')})",

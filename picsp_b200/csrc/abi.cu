@@ -443,14 +443,44 @@ bool choose_fft_split(int M, int *P, int *Q, int *L, int *logL) {
     return best > 0 && fft_padded((size_t)best) * sizeof(double2) <= OWN_FFT_MAX_SMEM;
 }
 
+// M = P * Q, coprime, both <= 64 (1025 = 25 * 41, 513 = 19 * 27, 65 = 5 * 13 ...): both factors as direct DFTs (kind 1)
+bool choose_direct_split(int M, int *P, int *Q) {
+    int best = -1;
+    for (int p = 2; p <= 64 && (long long)p * p <= M; p++) {
+        if (M % p) continue;
+        const int q = M / p;
+        if (q > 64 || gcd_int(p, q) != 1) continue;
+        if (best < 0 || p + q < best) { best = p + q; *P = p; *Q = q; }
+    }
+    return best > 0;
+}
+
 template <class T> void upload_table(void **dev, const std::vector<T> &h, cudaStream_t st) {
     PICSP_CUDA(cudaMalloc(dev, std::max<size_t>(h.size(), 1) * sizeof(T)));
     PICSP_CUDA(cudaMemcpyAsync(*dev, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
     PICSP_CUDA(cudaStreamSynchronize(st));       // the host vector dies with the caller
 }
 
+void build_direct_fft_plan(picsp_ctx *c, int which, int M, int P, int Q) {
+    picsp_ctx::OwnFft &f = c->fft;
+    f.kind[which] = 1; f.M[which] = M; f.P[which] = P; f.Q[which] = Q; f.L[which] = 0; f.logL[which] = 0;
+    const long double PI = 3.141592653589793238462643383279502884L;
+    std::vector<double2> rp((size_t)P), rq((size_t)Q);
+    for (int m = 0; m < P; m++) { const long double a = 2.0L * PI * m / P; rp[(size_t)m] = make_double2((double)cosl(a), (double)-sinl(a)); }
+    for (int m = 0; m < Q; m++) { const long double a = 2.0L * PI * m / Q; rq[(size_t)m] = make_double2((double)cosl(a), (double)-sinl(a)); }
+    std::vector<int> in_pos((size_t)M), out_idx((size_t)M);
+    for (int n1 = 0; n1 < P; n1++)
+        for (int n2 = 0; n2 < Q; n2++) in_pos[(size_t)(((long long)n1 * Q + (long long)n2 * P) % M)] = n1 * Q + n2;
+    for (int k = 0; k < M; k++) out_idx[(size_t)(k % P) * Q + (k % Q)] = k;
+    upload_table(&f.rootP[which], rp, c->stream); upload_table(&f.rootQ[which], rq, c->stream);
+    upload_table(&f.in_pos[which], in_pos, c->stream); upload_table(&f.out_idx[which], out_idx, c->stream);
+    f.smem[which] = (size_t)(2 * M + P + Q) * sizeof(double2);
+}
+
 void build_own_fft_plan(picsp_ctx *c, int which, int M) {
     picsp_ctx::OwnFft &f = c->fft;
+    int dp = 0, dq = 0;
+    if (!getenv("PICSP_FFT_NO_DIRECT") && choose_direct_split(M, &dp, &dq)) { build_direct_fft_plan(c, which, M, dp, dq); return; }
     int P = 1, Q = M, L = 2, logL = 1;
     PICSP_REQUIRE(choose_fft_split(M, &P, &Q, &L, &logL), PICSP_ERR_INVALID, "own FFT: the transform does not fit shared memory");
     f.M[which] = M; f.P[which] = P; f.Q[which] = Q; f.L[which] = L; f.logL[which] = logL;
@@ -495,7 +525,12 @@ void build_own_fft_plan(picsp_ctx *c, int which, int M) {
 
 // threads per transform: the radix-8 groups of a pass (P * L / 8) spread evenly, two or three per thread
 int fft_threads(const picsp_ctx *c, int which) {
-    if (const char *e = getenv("PICSP_FFT_THREADS")) return std::max(32, std::min(FFT_THREADS, atoi(e)));
+    if (const char *e = getenv("PICSP_FFT_THREADS")) return std::max(32, std::min(BLUE_THREADS, atoi(e)));
+    if (c->fft.kind[which] == 1) {       // one round per stage: threads = work items of the larger stage
+        const int P = c->fft.P[which], Q = c->fft.Q[which];
+        const int i1 = P * ((Q / 2 + 1 + PFA2_KP - 1) / PFA2_KP), i2 = Q * ((P / 2 + 1 + PFA2_KP - 1) / PFA2_KP);
+        return std::max(64, std::min(PFA2_THREADS, ((std::max(i1, i2) + 31) / 32) * 32));
+    }
     const int ng = std::max(1, c->fft.P[which] * c->fft.L[which] / 8);
     return (ng % 384 == 0) ? 384 : 256;          // measured at 2049^2: 128 / 192 / 256 / 384 / 512 threads -> 633 / 549 / 513 / 490 / 499 us
 }
@@ -503,6 +538,8 @@ int fft_threads(const picsp_ctx *c, int which) {
 BluePlanDev own_fft_plan(const picsp_ctx *c, int which) {
     const picsp_ctx::OwnFft &f = c->fft;
     BluePlanDev pl;
+    pl.kind = f.kind[which];
+    pl.rootP = (const double2 *)f.rootP[which]; pl.rootQ = (const double2 *)f.rootQ[which];
     pl.M = f.M[which]; pl.P = f.P[which]; pl.Q = f.Q[which]; pl.L = f.L[which]; pl.logL = f.logL[which];
     pl.chirp = (const double2 *)f.chirp[which]; pl.bhat = (const double2 *)f.bhat[which]; pl.tw = (const double2 *)f.tw[which];
     pl.in_pos = (const int *)f.in_pos[which]; pl.out_idx = (const int *)f.out_idx[which]; pl.wp = (const double2 *)f.wp[which];
@@ -516,22 +553,31 @@ void setup_own_fft(picsp_ctx *c) {
     const int flags = c->prm.flags;
     if (flags & PICSP_FLAG_CUFFT_ONLY) return;
     // ... and the small grids where cuFFT's launches cost more than the transform (65^2 .. 257^2 nodes: 1.2-1.5x, same file)
+    // ... and node counts that split into two coprime factors <= 64, both done as direct DFTs (1025 = 25 * 41: 1.28x cuFFT)
     const int big = std::max(g.nix, g.niy);
+    int dp, dq;
+    const bool direct_both = choose_direct_split(g.nix, &dp, &dq) && choose_direct_split(g.niy, &dp, &dq);
     const bool wanted = (flags & PICSP_FLAG_OWN_FFT) || largest_prime_factor(g.nix) > 127 || largest_prime_factor(g.niy) > 127 ||
-                        (big >= 65 && big <= 257);
+                        (big >= 65 && (big <= 257 || direct_both));
     if (!wanted) return;
     int P, Q, L, logL;
-    if (!choose_fft_split(g.niy, &P, &Q, &L, &logL) || !choose_fft_split(g.nix, &P, &Q, &L, &logL)) {
+    auto fits = [&](int M) { return choose_direct_split(M, &P, &Q) || choose_fft_split(M, &P, &Q, &L, &logL); };
+    if (!fits(g.niy) || !fits(g.nix)) {
         PICSP_REQUIRE(!(flags & PICSP_FLAG_OWN_FFT), PICSP_ERR_INVALID, "PICSP_FLAG_OWN_FFT: a transform of this length does not fit shared memory");
         return;                                        // too long for shared memory: cuFFT
     }
     build_own_fft_plan(c, 0, g.niy);
     build_own_fft_plan(c, 1, g.nix);
     picsp_ctx::OwnFft &f = c->fft;
-    PICSP_CUDA(cudaFuncSetAttribute(k_fft_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem[0]));
-    PICSP_CUDA(cudaFuncSetAttribute(k_fft_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem[0]));
-    PICSP_CUDA(cudaFuncSetAttribute(k_fft_cols<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem[1]));
-    PICSP_CUDA(cudaFuncSetAttribute(k_fft_cols<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem[1]));
+    const int big_smem = (int)OWN_FFT_MAX_SMEM;       // (an upper bound: each launch passes its own size)
+    PICSP_CUDA(cudaFuncSetAttribute(k_fft_rows_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem));
+    PICSP_CUDA(cudaFuncSetAttribute(k_fft_rows_inv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem));
+    PICSP_CUDA(cudaFuncSetAttribute((k_fft_cols<0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem));
+    PICSP_CUDA(cudaFuncSetAttribute((k_fft_cols<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem));
+    PICSP_CUDA(cudaFuncSetAttribute(k_fft_rows_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem));
+    PICSP_CUDA(cudaFuncSetAttribute(k_fft_rows_inv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem));
+    PICSP_CUDA(cudaFuncSetAttribute((k_fft_cols<1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem));
+    PICSP_CUDA(cudaFuncSetAttribute((k_fft_cols<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem));
     f.on = true;
 }
 
@@ -543,12 +589,16 @@ void op_solve_spectral(picsp_ctx *c) {
         // D2Z = rows forward (two real rows per transform) + columns forward; Z2D = columns inverse + rows inverse
         const BluePlanDev py = own_fft_plan(c, 0), px = own_fft_plan(c, 1);
         double2 *rhok = reinterpret_cast<double2 *>(c->rhok), *phik = reinterpret_cast<double2 *>(c->phik);
-        PICSP_LAUNCH(c, k_fft_rows_fwd, (g.nix + 1) / 2, fft_threads(c, 0), c->fft.smem[0], py, c->rho, rhok, g.nix);
-        PICSP_LAUNCH(c, (k_fft_cols<false>), Nh, fft_threads(c, 1), c->fft.smem[1], px, rhok, Nh);
+        if (py.kind == 1) PICSP_LAUNCH(c, k_fft_rows_fwd<1>, (g.nix + 1) / 2, fft_threads(c, 0), c->fft.smem[0], py, c->rho, rhok, g.nix);
+        else PICSP_LAUNCH(c, k_fft_rows_fwd<0>, (g.nix + 1) / 2, fft_threads(c, 0), c->fft.smem[0], py, c->rho, rhok, g.nix);
+        if (px.kind == 1) PICSP_LAUNCH(c, (k_fft_cols<1, false>), Nh, fft_threads(c, 1), c->fft.smem[1], px, rhok, Nh);
+        else PICSP_LAUNCH(c, (k_fft_cols<0, false>), Nh, fft_threads(c, 1), c->fft.smem[1], px, rhok, Nh);
         PICSP_LAUNCH(c, k_kspace_green, blocks_for((long long)g.nix * Nh, 256, c->num_sms * 8), 256, 0, c->rhok, c->phik,
                      g.nix, g.niy, g.xl, g.yl);
-        PICSP_LAUNCH(c, (k_fft_cols<true>), Nh, fft_threads(c, 1), c->fft.smem[1], px, phik, Nh);
-        PICSP_LAUNCH(c, k_fft_rows_inv, (g.nix + 1) / 2, fft_threads(c, 0), c->fft.smem[0], py, (const double2 *)phik, c->phi, g.nix);
+        if (px.kind == 1) PICSP_LAUNCH(c, (k_fft_cols<1, true>), Nh, fft_threads(c, 1), c->fft.smem[1], px, phik, Nh);
+        else PICSP_LAUNCH(c, (k_fft_cols<0, true>), Nh, fft_threads(c, 1), c->fft.smem[1], px, phik, Nh);
+        if (py.kind == 1) PICSP_LAUNCH(c, k_fft_rows_inv<1>, (g.nix + 1) / 2, fft_threads(c, 0), c->fft.smem[0], py, (const double2 *)phik, c->phi, g.nix);
+        else PICSP_LAUNCH(c, k_fft_rows_inv<0>, (g.nix + 1) / 2, fft_threads(c, 0), c->fft.smem[0], py, (const double2 *)phik, c->phi, g.nix);
         return;
     }
     PICSP_REQUIRE(c->have_plans, PICSP_ERR_STATE, "cuFFT plans missing");
@@ -976,6 +1026,7 @@ void picsp_destroy(picsp_ctx *c) {
     if (c->comm) { try { nccl().CommDestroy(c->comm); } catch (...) {} }
     if (c->have_plans) { cufftDestroy(c->plan_fwd); cufftDestroy(c->plan_inv); }
     for (int w = 0; w < 2; w++) {
+        cudaFree(c->fft.rootP[w]); cudaFree(c->fft.rootQ[w]);
         cudaFree(c->fft.chirp[w]); cudaFree(c->fft.bhat[w]); cudaFree(c->fft.tw[w]); cudaFree(c->fft.in_pos[w]); cudaFree(c->fft.out_idx[w]); cudaFree(c->fft.wp[w]);
     }
     for (int s = 0; s < 2; s++) {

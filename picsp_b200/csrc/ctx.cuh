@@ -150,8 +150,8 @@ struct picsp_ctx {
     // plan 1: length nix (columns; the same tables when nix == niy)
     struct OwnFft {
         bool on = false;
-        int M[2] = {0, 0}, P[2] = {0, 0}, Q[2] = {0, 0}, L[2] = {0, 0}, logL[2] = {0, 0};
-        void *chirp[2] = {}, *bhat[2] = {}, *tw[2] = {}, *in_pos[2] = {}, *out_idx[2] = {}, *wp[2] = {};
+        int kind[2] = {0, 0}, M[2] = {0, 0}, P[2] = {0, 0}, Q[2] = {0, 0}, L[2] = {0, 0}, logL[2] = {0, 0};
+        void *chirp[2] = {}, *bhat[2] = {}, *tw[2] = {}, *in_pos[2] = {}, *out_idx[2] = {}, *wp[2] = {}, *rootP[2] = {}, *rootQ[2] = {};
         size_t smem[2] = {0, 0};
     } fft;
 

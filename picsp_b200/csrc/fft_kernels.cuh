@@ -29,6 +29,7 @@ namespace picsp {
 constexpr int FFT_THREADS = 512;       // launch bound; the launch uses fft_threads() <= this
 
 struct BluePlanDev {
+    int kind;                // 0: prime-factor split + Bluestein (below); 1: two DIRECT coprime factors P x Q, both <= 64 (pfa2_transform)
     int M, P, Q, L, logL;
     const double2 *chirp;    // [Q]      c[n]
     const double2 *bhat;     // [L]      DIF(b) / L, b[m] = conj(c[|m|]) wrapped, in DIF output order
@@ -36,6 +37,8 @@ struct BluePlanDev {
     const int *in_pos;       // [M]      n -> n1 * L + n2   (n = (n1 Q + n2 P) mod M)
     const int *out_idx;      // [P * Q]  k1 * Q + k2 -> k   (k = k1 mod P, k = k2 mod Q)
     const double2 *wp;       // [P * P]  exp(-2 pi i k1 n1 / P)
+    const double2 *rootP;    // kind 1: [P] exp(-2 pi i m / P)
+    const double2 *rootQ;    // kind 1: [Q] exp(-2 pi i m / Q)
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -185,6 +188,98 @@ __device__ __forceinline__ void blue_transform(const BluePlanDev &pl, double2 *w
     }
 }
 
+// ---------------------------------------------------------------------------
+// Two direct factors (kind 1).  M = P * Q, coprime, both small (1025 = 25 * 41, 513 = 27 * 19, 65 = 5 * 13 ...): the
+// prime-factor map turns the transform into Q-point DFTs along the rows of a P x Q array and P-point DFTs along its
+// columns, both done DIRECTLY as small matrix products — no Bluestein padding, two passes over shared memory and three
+// barriers in all.  A thread computes a block of output pairs (k, N - k) of one 1-D transform: it walks the inputs once
+// and keeps, per pair, four real accumulators and the index of the current root of unity (advanced by k modulo the
+// length: a table of the roots sits in shared memory).  Lanes of a warp work on neighbouring transforms of the same output block, so the
+// root is a broadcast and the inputs are conflict-free.  Shared memory: 2 * M complex + the two root tables.
+// ---------------------------------------------------------------------------
+#ifndef PICSP_PFA2_KP
+#define PICSP_PFA2_KP 3      // measured at 1025^2 (192 threads): 2 / 3 / 4 / 5 pairs -> 108 / 106 / 112 / 115 us
+#endif
+constexpr int PFA2_KP = PICSP_PFA2_KP;        // output PAIRS (k, N - k) per thread
+
+// out[line][k] = sum_n W_N^(k n) in[line][n] for `lines` lines of length N; element (line, n) sits at line * ls + n * ns.
+// Outputs k and N - k use conjugate roots, so with v = a + i b and W^(k n) = c - i s the four sums
+//     S1 = sum a c,  S2 = sum b s,  S3 = sum b c,  S4 = sum a s
+// give BOTH:  X[k] = (S1 + S2) + i (S3 - S4),  X[N-k] = (S1 - S2) + i (S3 + S4)  — four FMAs and one root per input for
+// two outputs (k = 0, and k = N/2 for even N, pair with themselves and are emitted once).
+template <class Emit>
+__device__ __forceinline__ void pfa2_stage(const double2 *__restrict__ in, int lines, int N, int ls, int ns,
+                                           const double2 *__restrict__ root, Emit emit) {
+    const int npair = N / 2 + 1;
+    const int nblk = (npair + PFA2_KP - 1) / PFA2_KP;
+    for (int item = threadIdx.x; item < lines * nblk; item += blockDim.x) {
+        const int blk = item / lines, line = item - blk * lines;       // consecutive lanes: consecutive lines, same output block
+        const int k0 = blk * PFA2_KP;
+        double s1[PFA2_KP], s2[PFA2_KP], s3[PFA2_KP], s4[PFA2_KP];
+        int m[PFA2_KP], kk[PFA2_KP];
+#pragma unroll
+        for (int o = 0; o < PFA2_KP; o++) { s1[o] = s2[o] = s3[o] = s4[o] = 0.0; m[o] = 0; kk[o] = (k0 + o) % N; }
+        const double2 *src = in + line * ls;
+        for (int n = 0; n < N; n++) {
+            const double2 v = src[n * ns];
+#pragma unroll
+            for (int o = 0; o < PFA2_KP; o++) {
+                const double2 w = root[m[o]];                 // (c, -s)
+                s1[o] = fma(v.x, w.x, s1[o]); s2[o] = fma(-v.y, w.y, s2[o]);
+                s3[o] = fma(v.y, w.x, s3[o]); s4[o] = fma(-v.x, w.y, s4[o]);
+                m[o] += kk[o];                                // (k n) mod N
+                if (m[o] >= N) m[o] -= N;
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < PFA2_KP; o++) {
+            const int k = k0 + o;
+            if (k >= npair) continue;
+            emit(line, k, make_double2(s1[o] + s2[o], s3[o] - s4[o]));
+            const int kc = N - k;
+            if (k != 0 && kc != k) emit(line, kc, make_double2(s1[o] - s2[o], s3[o] + s4[o]));
+        }
+    }
+}
+
+template <bool INVERSE, class Load, class Store>
+__device__ __forceinline__ void pfa2_transform(const BluePlanDev &pl, double2 *smem, Load load, Store store) {
+    const int P = pl.P, Q = pl.Q, M = pl.M;
+    double2 *buf0 = smem, *buf1 = smem + M, *rP = smem + 2 * M, *rQ = rP + P;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) rP[i] = pl.rootP[i];
+    for (int i = threadIdx.x; i < Q; i += blockDim.x) rQ[i] = pl.rootQ[i];
+    for (int n = threadIdx.x; n < M; n += blockDim.x) {
+        double2 v = load(n);
+        if (INVERSE) v.y = -v.y;
+        buf0[pl.in_pos[n]] = v;                        // (n1, n2) at n1 * Q + n2
+    }
+    __syncthreads();
+    // Q-point transforms along n2 for every n1: lines = n1 (stride Q), elements stride 1
+    pfa2_stage(buf0, P, Q, Q, 1, rQ, [&](int n1, int k2, double2 v) { buf1[n1 * Q + k2] = v; });
+    __syncthreads();
+    // P-point transforms along n1 for every k2: lines = k2 (stride 1), elements stride Q
+    pfa2_stage(buf1, Q, P, 1, Q, rP, [&](int k2, int k1, double2 v) {
+        if (INVERSE) v.y = -v.y;
+        store(pl.out_idx[k1 * Q + k2], v);
+    });
+}
+
+// one 1-D transform of either kind (a template parameter: each kind gets kernels of its own, with its own register budget)
+template <int KIND, bool INVERSE, class Load, class Store>
+__device__ __forceinline__ void dft_transform(const BluePlanDev &pl, double2 *smem, Load load, Store store) {
+    if (KIND == 1) pfa2_transform<INVERSE>(pl, smem, load, store);
+    else blue_transform<INVERSE>(pl, smem, load, store);
+}
+#ifndef PICSP_PFA2_THREADS
+#define PICSP_PFA2_THREADS 224     // upper bound; the launch uses the work items of the larger stage (1025 = 25 x 41: 175 and 205 -> 224: 97 us)
+#endif
+#ifndef PICSP_PFA2_CTAS
+#define PICSP_PFA2_CTAS 4
+#endif
+constexpr int PFA2_THREADS = PICSP_PFA2_THREADS;     // 1025 = 25 x 41: 150 and 164 work items per stage
+constexpr int BLUE_THREADS = 384;     // kind 0: at most this many threads, two CTAs per SM (<= 85 registers)
+#define PICSP_FFT_BOUNDS(KIND) __launch_bounds__((KIND) == 1 ? PFA2_THREADS : BLUE_THREADS, (KIND) == 1 ? PICSP_PFA2_CTAS : 2)
+
 // bhat = DIF(b) / L, computed with the very routine that will consume it (so the order matches by construction)
 __global__ void __launch_bounds__(FFT_THREADS)
 k_blue_bhat(const double2 *__restrict__ b, double2 *__restrict__ bhat, int L, int logL, const double2 *__restrict__ tw) {
@@ -198,18 +293,21 @@ k_blue_bhat(const double2 *__restrict__ b, double2 *__restrict__ bhat, int L, in
 }
 
 // rows forward: real rows 2a, 2a+1 of x[nrows][M] -> half spectra T[2a][0..Nh), T[2a+1][0..Nh)
-__global__ void __launch_bounds__(FFT_THREADS)
+template <int KIND>
+__global__ void PICSP_FFT_BOUNDS(KIND)
 k_fft_rows_fwd(BluePlanDev pl, const double *__restrict__ x, double2 *__restrict__ T, int nrows) {
     extern __shared__ __align__(16) unsigned char fft_smem[];
     double2 *work = reinterpret_cast<double2 *>(fft_smem);
     // the packed spectrum Z[k] goes to the columns [Q, 2Q) of the work rows (free once the convolution is done; L >= 2Q):
     // element k sits in row k / Q, column Q + k % Q
+    // (kind 1: the first buffer is free once the first stage has read it)
     const int M = pl.M, Nh = M / 2 + 1, Q = pl.Q, L = pl.L;
-    auto zpos = [Q, L](int k) { const int r = k / Q; return padx(r * L + Q + (k - r * Q)); };
+    constexpr bool direct = KIND == 1;
+    auto zpos = [Q, L, direct](int k) { if (direct) return k; const int r = k / Q; return padx(r * L + Q + (k - r * Q)); };
     const int ra = 2 * blockIdx.x, rb = ra + 1;
     const double *xa = x + (size_t)ra * M, *xb = x + (size_t)rb * M;
     const bool has_b = rb < nrows;
-    blue_transform<false>(pl, work,
+    dft_transform<KIND, false>(pl, work,
                           [&](int n) { return make_double2(xa[n], has_b ? xb[n] : 0.0); },
                           [&](int k, double2 v) { work[zpos(k)] = v; });
     __syncthreads();
@@ -222,19 +320,20 @@ k_fft_rows_fwd(BluePlanDev pl, const double *__restrict__ x, double2 *__restrict
 }
 
 // columns, in place on T[M][Nh]: column blockIdx.x
-template <bool INVERSE>
-__global__ void __launch_bounds__(FFT_THREADS)
+template <int KIND, bool INVERSE>
+__global__ void PICSP_FFT_BOUNDS(KIND)
 k_fft_cols(BluePlanDev pl, double2 *__restrict__ T, int Nh) {
     extern __shared__ __align__(16) unsigned char fft_smem[];
     double2 *work = reinterpret_cast<double2 *>(fft_smem);
     double2 *col = T + blockIdx.x;
-    blue_transform<INVERSE>(pl, work,
+    dft_transform<KIND, INVERSE>(pl, work,
                             [&](int n) { return col[(size_t)n * Nh]; },
                             [&](int k, double2 v) { col[(size_t)k * Nh] = v; });      // every load is done before the first store
 }
 
 // rows inverse: Hermitian half rows U[2a], U[2a+1] -> real rows 2a, 2a+1 of out[nrows][M] (un-normalised, like Z2D)
-__global__ void __launch_bounds__(FFT_THREADS)
+template <int KIND>
+__global__ void PICSP_FFT_BOUNDS(KIND)
 k_fft_rows_inv(BluePlanDev pl, const double2 *__restrict__ U, double *__restrict__ out, int nrows) {
     extern __shared__ __align__(16) unsigned char fft_smem[];
     double2 *work = reinterpret_cast<double2 *>(fft_smem);
@@ -243,7 +342,7 @@ k_fft_rows_inv(BluePlanDev pl, const double2 *__restrict__ U, double *__restrict
     const bool has_b = rb < nrows;
     const double2 *ua = U + (size_t)ra * Nh, *ub = U + (size_t)rb * Nh;
     double *oa = out + (size_t)ra * M, *ob = out + (size_t)rb * M;
-    blue_transform<true>(pl, work,
+    dft_transform<KIND, true>(pl, work,
                          [&](int k) {
                              // Z[k] = A[k] + i B[k]; beyond the stored half the rows are Hermitian: conj of the mirror
                              const bool lo = k < Nh;
