@@ -221,16 +221,13 @@ def workload_config(args, n_local):
         "load": args.load,
         "cells": args.cells, "particles_total": int(args.particles),
         "solver": "red-black SOR, Dirichlet walls (k_rb_sor, one cooperative launch)" if bounded else
-                  {"own": "spectral (the library's own shared-memory DFT, fft_kernels.cuh: prime-factor split into two direct factors, or Bluestein on 2^k)",
-                   "cufft": "spectral (cuFFT D2Z/Z2D)"}.get(getattr(args, "spectral_engine", "cufft"), "spectral"),
+                  "spectral (2-D DFT of the node array, k-space Green multiply, inverse DFT: spectralPotentialSolver, main.cpp:960-1058)",
         "sharding": f"particles by index range over {args.gpus} rank(s), grid replicated, the partial rho summed once per step "
                     f"({getattr(args, 'rho_reduction', 'n/a')})",
         "l2_policy": "inputs exceed L2 (particle state per rank >> 126 MB); no explicit flush",
     }
     if n_local is not None:
         cfg["particles_per_rank_per_species"] = int(n_local)
-    if getattr(args, "store_parts", 1) > 1:
-        cfg["store_parts_per_species"] = args.store_parts      # picsp_params::parts resolved (one shared spare buffer set)
     return cfg
 
 
@@ -394,6 +391,9 @@ def main_ours(args, rank, world, local_rank):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_local),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "spectral_engine": {"own": "the library's own shared-memory DFT (fft_kernels.cuh: two direct coprime factors, or a prime-factor split + Bluestein on 2^k)",
+                                "cufft": "cuFFT D2Z / Z2D"}.get(getattr(args, "spectral_engine", ""), None),
+            "store_parts_per_species": int(getattr(args, "store_parts", 1)),     # picsp_params::parts resolved (> 1: one shared spare buffer set)
             "parity_probe": parity_probe,
             "clocks": clocks, "phases_ms_per_step": phases_ms, "wall_ms_per_step": 1e3 * t_wall / args.steps,
         }
