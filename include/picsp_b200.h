@@ -226,6 +226,10 @@ enum {
 int picsp_profile_enable(picsp_ctx *ctx, int on);                       /* CUDA events around every phase on the library's stream */
 int picsp_profile_get(picsp_ctx *ctx, int phase, double *ms, int64_t *calls); /* synchronises; accumulates since last reset */
 int picsp_profile_reset(picsp_ctx *ctx);
+/* How the library's own DFT would split a transform of length M (no device needed): out5 = {kind, P, Q, L, largest prime
+ * factor of M}; kind 1 = two direct coprime factors P x Q (both <= 64), kind 0 = P direct (<= 32) x Q by Bluestein on the
+ * power-of-two length L, kind -1 = does not fit shared memory (cuFFT is used). */
+int picsp_fft_plan_query(int M, int32_t *out5);
 /* Transform behind picsp_solve_spectral: 1 = the library's own shared-memory DFT (node counts with a prime factor > 127 such
  * as 2049 = 3 * 683, and small grids), 0 = cuFFT. */
 int picsp_spectral_engine(picsp_ctx *ctx, int *own);

@@ -1752,6 +1752,16 @@ int picsp_profile_reset(picsp_ctx *c) {
     for (auto &t : c->timers) { t.ms = 0.0; t.calls = 0; }
     PICSP_API_END
 }
+int picsp_fft_plan_query(int M, int32_t *out5) {
+    PICSP_API_BEGIN
+    PICSP_REQUIRE(M >= 2 && out5 != nullptr, PICSP_ERR_INVALID, "bad arguments");
+    int P = 0, Q = 0, L = 0, logL = 0;
+    if (choose_direct_split(M, &P, &Q)) { out5[0] = 1; out5[1] = P; out5[2] = Q; out5[3] = 0; }
+    else if (choose_fft_split(M, &P, &Q, &L, &logL)) { out5[0] = 0; out5[1] = P; out5[2] = Q; out5[3] = L; }
+    else { out5[0] = -1; out5[1] = out5[2] = out5[3] = 0; }
+    out5[4] = largest_prime_factor(M);
+    PICSP_API_END
+}
 int picsp_spectral_engine(picsp_ctx *c, int *own) {
     PICSP_API_BEGIN
     check_ctx(c);

@@ -103,6 +103,7 @@ def load_library():
         "picsp_kernel_launches": ([ctx, _i64p], C.c_int),
         "picsp_parts": ([ctx, C.POINTER(C.c_int)], C.c_int),
         "picsp_spectral_engine": ([ctx, C.POINTER(C.c_int)], C.c_int),
+        "picsp_fft_plan_query": ([C.c_int, C.POINTER(C.c_int32)], C.c_int),
         "picsp_host_parse_ini": ([C.c_char_p, C.POINTER(CRunConfig), C.c_int], C.c_int),
         "picsp_host_ini_dump": ([C.c_char_p, C.c_char_p, C.c_int64], C.c_int64),
         "picsp_host_loader_create": ([C.c_uint32], C.c_void_p),

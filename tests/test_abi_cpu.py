@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 import picsp_b200
@@ -121,3 +122,33 @@ def test_patched_reference_fails_loudly_without_a_gpu(tmp_path):
             "L.picsp_refgpu_main.argtypes = [C.c_char_p]; sys.exit(L.picsp_refgpu_main(os.fsencode(sys.argv[2])))")
     r = subprocess.run([os.sys.executable, "-c", code, orc.REF_GPU_SO, ini], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode != 0 and "no CUDA device" in r.stderr
+
+
+def test_own_dft_plan_selection():
+    """Host logic of the library's own DFT (no device needed): how a node count is split.  kind 1 = two direct coprime
+    factors <= 64, kind 0 = small direct factor x Bluestein on a power of two >= 2Q - 1, kind -1 = too long for shared memory."""
+    import ctypes as C
+    L = picsp_b200.load_library()
+
+    def plan(M):
+        out = (C.c_int32 * 5)()
+        assert L.picsp_fft_plan_query(M, out) == 0
+        return tuple(out)
+
+    assert plan(1025) == (1, 25, 41, 0, 41)            # the bench grid: 25 x 41, both direct
+    assert plan(513) == (1, 19, 27, 0, 19)
+    assert plan(65) == (1, 5, 13, 0, 13)
+    assert plan(48) == (1, 3, 16, 0, 3)
+    assert plan(2049) == (0, 3, 683, 2048, 683)        # BASELINE config 5: 3 x Bluestein(683) on 2048 points
+    assert plan(257) == (0, 1, 257, 1024, 257)         # prime
+    assert plan(49) == (0, 1, 49, 128, 7)              # 7^2: no coprime split
+    assert plan(4097) == (0, 17, 241, 512, 241)
+    assert plan(8193)[0] == -1                         # 3 x 2731: 3 x 8192 complex do not fit
+    for M in (33, 34, 97, 129, 131, 201, 256, 1000, 1537):
+        kind, P, Q, Lp, lpf = plan(M)
+        assert kind in (0, 1) and P * Q == M and np.gcd(P, Q) == 1
+        if kind == 0:
+            assert Lp >= 2 * Q - 1 and Lp & (Lp - 1) == 0 and P <= 32
+        else:
+            assert P <= 64 and Q <= 64
+    assert L.picsp_fft_plan_query(1, (C.c_int32 * 5)()) != 0
