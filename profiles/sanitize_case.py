@@ -58,3 +58,13 @@ for numx, numy in ((32, 32), (48, 48), (47, 47), (64, 130)):
         sim.fill_synthetic(ION, 5000, seed=7, vth=nm["vth_i"]); sim.fill_synthetic(ELECTRON, 5000, seed=8, vth=1.0)
         sim.bootstrap(); sim.step(2)
         print("fft", numx, numy, sim.spectral_engine(), sim.delta_phi())
+# far movers (more than one tile per step): global gather / deposit, individual slots at the re-binning, the far-mover counter
+n = 20000
+x = rng.random(n) * 128 * nm["dx"]; y = rng.random(n) * 128 * nm["dx"]
+vx = 0.3 * rng.standard_normal(n); vy = 0.3 * rng.standard_normal(n)
+vx[:7] = 40 * nm["dx"] / nm["dt"]; vy[7:12] = -70 * nm["dx"] / nm["dt"]
+with Simulation(Params(128, 128, nm["dx"], nm["dt"], nm["mass_i"], n, n, solverType=1)) as sim:
+    sim.set_sort_period(ELECTRON, 2)
+    sim.set_species(ION, x, y, 0 * x, 0 * x); sim.set_species(ELECTRON, x, y, vx, vy)
+    sim.bootstrap(); sim.step(5); sim.sync()
+    print("far", sim.computeKE(ELECTRON), sim.straggler_count(ELECTRON))
