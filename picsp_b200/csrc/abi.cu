@@ -612,7 +612,18 @@ void op_solve_sor(picsp_ctx *c) {
     PhaseScope ph(c, PICSP_PHASE_SOLVE);
     const Geom &g = c->g;
     const int bands = (g.nix + SOR_ROWS - 1) / SOR_ROWS;
-    if (bands <= c->num_sms && !(c->prm.flags & PICSP_FLAG_SOR_SINGLE_CTA)) {
+    const size_t small_bytes = sor_smem_bytes(g.nix, g.niy);
+    if (g.nix >= 3 && g.nix <= 1024 && small_bytes <= 200 * 1024 && !(c->prm.flags & PICSP_FLAG_SOR_SINGLE_CTA) && !getenv("PICSP_SOR_NO_SMEM")) {
+        // small grid (the shipped input.ini: 65^2 nodes, 68 KB): sweep 0 entirely in shared memory, then the same test and fall-through
+        if (!c->sor_smem_opted_in) {
+            PICSP_CUDA(cudaFuncSetAttribute(k_sor_sweep_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            c->sor_smem_opted_in = true;
+        }
+        PICSP_LAUNCH(c, k_sor_sweep_smem, 1, ((g.nix + 31) / 32) * 32, small_bytes, c->phi, c->rho, g.nix, g.niy, g.dx, g.dx);
+        PICSP_LAUNCH(c, k_sor_residual_partial, RED_BLOCKS, RED_THREADS, 0, c->phi, c->rho, g.nix, g.niy, g.dx, c->d_red);
+        PICSP_LAUNCH(c, k_sor_residual_final, 1, 1024, 0, c->d_red, RED_BLOCKS, g.nix, g.niy, c->d_sor_status, c->d_scalars + 3);
+        PICSP_LAUNCH(c, k_sor_solve, 1, 1024, 0, c->phi, c->rho, g.nix, g.niy, g.dx, g.dx, c->d_sor_status, c->d_scalars + 3, 200000, 1);
+    } else if (bands <= c->num_sms && !(c->prm.flags & PICSP_FLAG_SOR_SINGLE_CTA)) {
         // sweep 0 pipelined over co-resident bands, then the reference's convergence test; further sweeps
         // (never needed in practice) fall through to the single-CTA kernel
         PICSP_CUDA(cudaMemsetAsync(c->d_sor_progress, 0, sizeof(int) * bands, c->stream));

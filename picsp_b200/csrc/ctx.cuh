@@ -174,6 +174,7 @@ struct picsp_ctx {
     bool sort2_opted_in = false;
     bool cellsort_opted_in = false;
     bool bankorder_opted_in = false;
+    bool sor_smem_opted_in = false;
 
     // staging for grid component uploads/downloads
     double *stage = nullptr; int64_t stage_cap = 0;

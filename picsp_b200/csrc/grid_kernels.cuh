@@ -399,6 +399,55 @@ k_sor_sweep_pipelined(double *phi, const double *__restrict__ rho, int nix, int 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ---------------------------------------------------------------------------
+// SOR sweep 0 for SMALL grids (the shipped input.ini: 65 x 65 nodes): phi and rho live in shared memory for the
+// whole sweep, one thread per grid row, one block barrier per anti-diagonal.  Same lexicographic iterate and the
+// same arithmetic as the other two kernels (bit-identical, tested); what changes is the cost of a step: four LDS and
+// a barrier among 3 warps instead of an L2 round trip (k_sor_solve) or the ring / progress machinery of the
+// pipelined sweep — ~150 instead of ~560 ns per anti-diagonal.  The row pitch is even, so the threads of a
+// diagonal (stride pitch - 1 doubles) fall on distinct banks.
+// ---------------------------------------------------------------------------
+__host__ __device__ inline int sor_smem_pitch(int niy) { return niy + (niy & 1); }
+inline size_t sor_smem_bytes(int nix, int niy) { return 2 * sizeof(double) * (size_t)nix * sor_smem_pitch(niy); }
+
+__global__ void __launch_bounds__(1024, 1)
+k_sor_sweep_smem(double *phi, const double *__restrict__ rho, int nix, int niy, double dx, double dy) {
+    extern __shared__ __align__(16) unsigned char sor_smem[];
+    const int pitch = sor_smem_pitch(niy);
+    double *sphi = reinterpret_cast<double *>(sor_smem), *srho = sphi + (size_t)nix * pitch;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int k = tid; k < nix * niy; k += nt) {
+        const int i = k / niy, j = k - i * niy;
+        sphi[i * pitch + j] = ldcg(&phi[k]);
+        srho[i * pitch + j] = rho[k];
+    }
+    __syncthreads();
+    const double dx2 = dx * dx, dy2 = dy * dy, eps = 1.0;
+    const double coef = 0.5 * (1 / ((1 / dx2) + (1 / dy2)));
+    const double rdx2 = 1 / dx2, rdy2 = 1 / dy2;
+    const int i = tid;                                           // row of this thread (blockDim.x >= nix)
+    const int p = (i - 1 < 0) ? nix - 2 : i - 1;                 // src/main.cpp:916-919
+    const int q = (i + 1 > nix - 1) ? 1 : i + 1;
+    double *rowp = sphi + i * pitch;
+    const double *up_row = sphi + p * pitch, *down_row = sphi + q * pitch, *rho_row = srho + i * pitch;
+    for (int d = 0; d <= nix + niy - 2; d++) {
+        const int j = d - i;
+        if (i < nix && j >= 0 && j < niy) {
+            const int r = (j - 1 < 0) ? niy - 2 : j - 1;
+            const int sidx = (j + 1 > niy - 1) ? 1 : j + 1;
+            const double g = coef * (sor_div(up_row[j] + down_row[j], dx2, rdx2) + sor_div(rowp[r] + rowp[sidx], dy2, rdy2) +
+                                     (rho_row[j] / eps));
+            const double old = rowp[j];
+            rowp[j] = old + 1.4 * (g - old);
+        }
+        __syncthreads();
+    }
+    for (int k = tid; k < nix * niy; k += nt) {
+        const int ii = k / niy, j = k - ii * niy;
+        __stcg(&phi[k], sphi[ii * pitch + j]);
+    }
+}
+
 // residual of the reference's convergence test (src/main.cpp:930-950), multi-CTA, fixed tree
 __global__ void k_sor_residual_partial(const double *__restrict__ phi, const double *__restrict__ rho, int nix, int niy,
                                        double dx, double *__restrict__ partial) {
