@@ -990,7 +990,7 @@ int picsp_create(const picsp_params *p, picsp_ctx **out) {
         PICSP_CUDA(cudaMemsetAsync(c->phi, 0, sizeof(double) * g.nn, c->stream));
         PICSP_CUDA(cudaMemsetAsync(c->E_alloc, 0, sizeof(double2) * (g.nn + 2 * g.guard), c->stream));
         make_tensor_map(c);
-        dalloc(&c->d_red, RED_BLOCKS); dalloc(&c->d_scalars, 8); dalloc(&c->d_sor_status, 2); dalloc(&c->d_sor_progress, (size_t)(g.nix + SOR_ROWS - 1) / SOR_ROWS + 1); dalloc(&c->d_error, 1);
+        dalloc(&c->d_red, RED_BLOCKS); dalloc(&c->d_scalars, 8); dalloc(&c->d_sor_status, 2); dalloc(&c->d_sor_progress, (size_t)g.nix + 1); dalloc(&c->d_error, 1);
         PICSP_CUDA(cudaMemsetAsync(c->d_scalars, 0, sizeof(double) * 8, c->stream));
         PICSP_CUDA(cudaMemsetAsync(c->d_sor_status, 0, sizeof(long long) * 2, c->stream));
         PICSP_CUDA(cudaMemsetAsync(c->d_error, 0, sizeof(int), c->stream));
