@@ -369,7 +369,17 @@ def main_ours(args, rank, world, local_rank):
     # which makes boxes of many Debye lengths unstable; at this noise level velocities run away after ~510 steps in
     # total (profiles/r02_long_run_instability.md), so the e2e periods must not be stacked on top of the steps above.
     e2e = None
+    e2e_skipped = None
     if not args.no_e2e:
+        # the end-to-end run holds the whole phase space in (page-locked) host memory: 64 bytes per particle of a species
+        try:
+            import psutil
+            need, avail = 64 * n_local, psutil.virtual_memory().available
+            if need > 0.5 * avail:
+                e2e_skipped = f"host buffers of {need / 1e9:.0f} GB against {avail / 1e9:.0f} GB of available host memory"
+        except ImportError:
+            pass
+    if not args.no_e2e and e2e_skipped is None:
         sim.close()
         sim = make_sim()
         sim.bootstrap()
@@ -393,6 +403,7 @@ def main_ours(args, rank, world, local_rank):
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "spectral_engine": {"own": "the library's own shared-memory DFT (fft_kernels.cuh: two direct coprime factors, or a prime-factor split + Bluestein on 2^k)",
                                 "cufft": "cuFFT D2Z / Z2D"}.get(getattr(args, "spectral_engine", ""), None),
+            "e2e_skipped": e2e_skipped,
             "store_parts_per_species": int(getattr(args, "store_parts", 1)),     # picsp_params::parts resolved (> 1: one shared spare buffer set)
             "parity_probe": parity_probe,
             "clocks": clocks, "phases_ms_per_step": phases_ms, "wall_ms_per_step": 1e3 * t_wall / args.steps,
