@@ -77,3 +77,17 @@ def test_own_fft_in_the_time_loop():
                 assert_grid_close(sim.grid(name), o.grid(name), sim.nix, sim.niy, 10 * RTOL, name)
             runs.append(sim.grid("phi"))
     assert np.array_equal(runs[0], runs[1])
+
+
+@pytest.mark.parametrize("numx", [32, 64, 512, 1024])
+def test_bluestein_path_on_lengths_that_normally_split_directly(numx, monkeypatch):
+    """33 = 3*11, 65 = 5*13, 513 = 19*27 and 1025 = 25*41 normally take the two-direct-factor transform; PICSP_FFT_NO_DIRECT
+    forces the prime-factor + Bluestein transform on them (25 rows of length 41 on 128 points ...): both against cuFFT."""
+    rng = np.random.default_rng(numx + 7)
+    rho = np.zeros((numx + 1, numx + 1)); rho[1:-1, 1:-1] = rng.standard_normal((numx - 1, numx - 1))
+    ref = solve(numx, numx, FLAG_CUFFT_ONLY, rho)
+    direct = solve(numx, numx, FLAG_OWN_FFT, rho)
+    monkeypatch.setenv("PICSP_FFT_NO_DIRECT", "1")
+    blue = solve(numx, numx, FLAG_OWN_FFT, rho)
+    assert relerr(direct, ref) <= 1e-13 and relerr(blue, ref) <= 1e-13
+    assert not np.array_equal(direct, blue), "the switch did not select another transform"

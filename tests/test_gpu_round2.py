@@ -237,3 +237,25 @@ def test_picsp_step_reports_a_violation_of_an_earlier_call():
                 break
             time.sleep(0.01)
         assert code == -7
+
+
+@pytest.mark.parametrize("numx,numy", [(64, 64), (32, 100), (100, 47)])
+def test_small_grid_sor_sweep_in_shared_memory_is_bit_identical(numx, numy, monkeypatch):
+    """Grids that fit shared memory sweep in one CTA (k_sor_sweep_smem); PICSP_SOR_NO_SMEM sends them through the
+    pipelined bands instead and PICSP_FLAG_SOR_SINGLE_CTA through the single-CTA global-memory kernel: the three are
+    the same lexicographic iterate with the same arithmetic — bit-identical phi after bootstrap + 3 steps."""
+    nm = normalise()
+    n = 20_000
+
+    def run(flags):
+        with Simulation(Params(numx, numy, nm["dx"], nm["dt"], nm["mass_i"], n, n, solverType=2, flags=flags)) as sim:
+            sim.fill_synthetic(ION, n, seed=3, vth=nm["vth_i"]); sim.fill_synthetic(ELECTRON, n, seed=4, vth=1.0, xdrift=nm["drift_e"])
+            sim.bootstrap(); sim.step(3)
+            return sim.grid("phi"), sim.grid("rho")
+
+    smem = run(0)
+    single = run(8)
+    monkeypatch.setenv("PICSP_SOR_NO_SMEM", "1")
+    pipelined = run(0)
+    for a, b in ((smem, single), (smem, pipelined)):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
